@@ -1,0 +1,127 @@
+/* nlcuda.h -- C ABI of libnlcuda.so, a B200 (sm_100a) neighbour-list engine.
+ *
+ * Drop-in boundary for the sort-based path of JuliaMolSim/NeighbourLists.jl behind
+ *   neighbour_list(X, cutoff, cell, pbc; lazy)            (src/cell_list.jl:897-916)
+ * for device-resident inputs.  Each entry point replaces one STAGE of that path; the Julia side
+ * keeps PairList / SortedCellList (src/types.jl:34-82) and binds these with ccall.
+ *
+ * Conventions
+ *  - All pointers except `params`, `total_pairs_host` are DEVICE pointers owned by the caller
+ *    (CuArray / torch tensor).  The library never allocates or frees device memory and keeps no
+ *    global state; scratch comes from the caller through `ws` (size from nl_workspace_bytes).
+ *  - Work is enqueued on the caller's `stream` (a cudaStream_t / CUstream passed as void*).  Only
+ *    nl_count_pairs synchronises (it must return the data-dependent pair count to the host),
+ *    mirroring the reference's single D2H read (src/gpu_kernels.jl:333,367-371).
+ *  - Element types are selected by params->float_type (positions, R) and params->int_type
+ *    (perm, cell_id, cell_offsets, first, i, j, S).  Arrays are packed AoS exactly like Julia's
+ *    Vector{SVector{3,T}}: X, X_sorted, R are N x 3 T; S is P x 3 TI.
+ *  - All integer outputs are 1-BASED, as in the reference.
+ *  - Matrices are 9 doubles in Julia column-major order, m[r + 3*c] = M[r+1, c+1]; ROWS of `cell`
+ *    are the lattice vectors.  They hold values already rounded to T by the caller, which computes
+ *    them with the reference's own analyze_cell (src/cell_list.jl:152-170) and nxyz formula
+ *    (src/gpu_kernels.jl:315-316): the library never re-derives them.
+ *  - Return value: NL_OK (0) or a negative NL_ERR_* code; nl_strerror() names it.  No exceptions,
+ *    no abort.  N == 0 is legal everywhere.
+ */
+#ifndef NLCUDA_H
+#define NLCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NL_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define NL_API __attribute__((visibility("default")))
+#else
+#define NL_API
+#endif
+
+enum { NL_F32 = 0, NL_F64 = 1 };
+enum { NL_I32 = 0, NL_I64 = 1 };
+
+enum {
+  NL_OK = 0,
+  NL_ERR_BAD_ARG = -1,     /* null pointer, negative N, bad enum, ncells < 1, nxyz < 1 ...            */
+  NL_ERR_WORKSPACE = -2,   /* ws too small / misaligned, or fill called with a ws count did not stamp */
+  NL_ERR_CUDA = -3,        /* a CUDA call failed; nl_last_cuda_error() holds the cudaError_t          */
+  NL_ERR_OVERFLOW = -4,    /* pair count does not fit int_type (reference: silent Int32 wrap)         */
+  NL_ERR_UNSUPPORTED = -5  /* N or prod(ncells) >= 2^31 - 1 (keys are 32-bit internally)              */
+};
+
+/* Geometry of one neighbour-list problem, filled by the caller.
+ * Mirrors the scalar fields of SortedCellList (src/types.jl:70-82) plus nxyz. */
+typedef struct nl_params {
+  int32_t float_type;  /* NL_F32 | NL_F64: element type T of X, X_sorted, R                         */
+  int32_t int_type;    /* NL_I32 | NL_I64: element type TI of every integer array                   */
+  double cell[9];      /* clist.cell                                                                */
+  double inv_cell[9];  /* clist.inv_cell = inv(cell)                                                */
+  double cutoff;       /* clist.cutoff (already converted to T, src/cell_list.jl:639)               */
+  int32_t ncells[3];   /* clist.ncells = max(floor(lens / cutoff), 1)                               */
+  int32_t nxyz[3];     /* ceil(cutoff * ncells / |lens|): stencil half-widths, >= 1                 */
+  uint8_t pbc[3];      /* clist.pbc                                                                 */
+  uint8_t reserved[5]; /* must be zero                                                              */
+} nl_params;
+
+/* Workspace stages for nl_workspace_bytes. */
+enum { NL_STAGE_BUILD = 0, NL_STAGE_PAIRS = 1 };
+
+NL_API int nl_version(void);
+NL_API const char* nl_strerror(int code);
+NL_API int nl_last_cuda_error(void); /* cudaError_t captured by the last NL_ERR_CUDA on this thread */
+NL_API long long nl_launch_count(void); /* kernels launched by this library in this process so far */
+
+/* Bytes of scratch the given stage needs for N atoms (ws must be 256-byte aligned).
+ * NL_STAGE_BUILD: nl_build_cells.  NL_STAGE_PAIRS: nl_count_pairs / nl_fill_pairs / nl_lazy_*. */
+NL_API size_t nl_workspace_bytes(const nl_params* params, int64_t N, int stage);
+
+/* Stage "build_cell_list": replaces _build_sorted_celllist's device stages
+ * (src/cell_list.jl:647-679: _compute_cell_ids gpu_kernels.jl:244-255, _get_sortperm
+ * cell_list.jl:711-718, the two gathers :669-670, _compute_cell_offsets gpu_kernels.jl:262-285).
+ *   X            in   N x 3 T   caller's positions (never written; becomes clist.X_orig)
+ *   X_sorted     out  N x 3 T   clist.X       = X[perm]
+ *   perm         out  N TI      clist.perm    : sorted slot -> original index; the unique STABLE
+ *                               permutation (equals the CPU path's sortperm, cell_list.jl:706-708)
+ *   cell_id      out  N TI      clist.cell_id : linear cell of each sorted slot
+ *   cell_offsets out  prod(ncells)+1 TI  clist.cell_offsets; all ones when N == 0               */
+NL_API int nl_build_cells(const nl_params* params, const void* X, int64_t N, void* X_sorted, void* perm,
+                   void* cell_id, void* cell_offsets, void* ws, size_t ws_bytes, void* stream);
+
+/* Stage "materialize_pairlist", first half (src/gpu_kernels.jl:315-333: count_neighbours_kernel!,
+ * compute_pair_offsets, _scalar_getindex).
+ *   X_sorted, perm, cell_offsets   the SortedCellList fields (from nl_build_cells or the CPU path)
+ *   first            out  N+1 TI   CSR offsets in ORIGINAL atom order, first[0] = 1
+ *   total_pairs_host out  host int64: P = first[N] - 1.  The call synchronises `stream`.
+ * Leaves per-atom records in `ws` for nl_fill_pairs: pass the SAME ws, untouched, to it.          */
+NL_API int nl_count_pairs(const nl_params* params, const void* X_sorted, int64_t N, const void* perm,
+                   const void* cell_offsets, void* first, int64_t* total_pairs_host, void* ws,
+                   size_t ws_bytes, void* stream);
+
+/* Stage "materialize_pairlist", second half (src/gpu_kernels.jl:347-359: fill_pairs_kernel!).
+ *   i_out, j_out  out  P TI      pair (i[n], j[n]); row m occupies first[m]..first[m+1]-1
+ *   S_out         out  P x 3 TI  cell shifts, packed
+ *   R_out         out  P x 3 T   X[j] - X[i] + cell' * S (what _getR recomputes,
+ *                                src/cell_list.jl:525-531); MAY BE NULL (PairList stores no R)
+ * Order inside a row is unspecified (the reference's tests sort before comparing).               */
+NL_API int nl_fill_pairs(const nl_params* params, const void* X_sorted, int64_t N, const void* perm,
+                  const void* cell_offsets, const void* first, void* i_out, void* j_out, void* S_out,
+                  void* R_out, void* ws, size_t ws_bytes, void* stream);
+
+/* Lazy mode: fused for_each_neighbour traversals (src/cell_list.jl:779-801) with fixed sinks.
+ * nl_lazy_count: counts_out[m] (N TI, original order) = count_neighbours(clist, m) (:808-814).
+ * nl_lazy_lj_energy: *energy_out (DEVICE double) = sum over ordered pairs of
+ *   4 eps ((sigma/r)^12 - (sigma/r)^6), r^2 = dot(R,R) evaluated in T, accumulated in double.      */
+NL_API int nl_lazy_count(const nl_params* params, const void* X_sorted, int64_t N, const void* perm,
+                  const void* cell_offsets, void* counts_out, void* ws, size_t ws_bytes, void* stream);
+NL_API int nl_lazy_lj_energy(const nl_params* params, const void* X_sorted, int64_t N, const void* perm,
+                      const void* cell_offsets, double eps, double sigma, double* energy_out, void* ws,
+                      size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLCUDA_H */

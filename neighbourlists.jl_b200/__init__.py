@@ -1,0 +1,16 @@
+"""neighbourlists.jl_b200 -- B200-native drop-in for the sort-based neighbour-list path of
+JuliaMolSim/NeighbourLists.jl.  csrc/ holds the sm_100a CUDA kernels and the C ABI
+(libnlcuda.so, include/nlcuda.h); api.py mirrors the reference's operator interface on top of it.
+
+The directory name contains a dot, so import it through the repo-root shim:
+    import neighbourlists_jl_b200 as nl
+"""
+from . import _lib, cellmath
+from ._lib import NlError
+from .api import (PairList, SortedCellList, build_cell_list, count_neighbours, cutoff, for_each_neighbour, lj_energy,
+                  materialize_pairlist, max_neigs, max_neighbours, maxneigs, neighbour_list, neighbours, neigs, neigss, nneigs,
+                  npairs, nsites, num_neighbours)
+
+__all__ = ["PairList", "SortedCellList", "build_cell_list", "materialize_pairlist", "neighbour_list", "for_each_neighbour",
+           "count_neighbours", "neighbours", "num_neighbours", "npairs", "nsites", "cutoff", "nneigs", "maxneigs",
+           "max_neighbours", "max_neigs", "neigs", "neigss", "lj_energy", "NlError", "cellmath"]

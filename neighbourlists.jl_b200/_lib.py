@@ -1,0 +1,104 @@
+"""ctypes binding of libnlcuda.so (include/nlcuda.h).  One Python function per C entry point, same
+argument order; this file is the tested twin of the Julia `ccall` stubs in INTEGRATION.md.
+
+There is NO fallback: if the shared library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+NL_F32, NL_F64 = 0, 1
+NL_I32, NL_I64 = 0, 1
+NL_STAGE_BUILD, NL_STAGE_PAIRS = 0, 1
+NL_OK, NL_ERR_BAD_ARG, NL_ERR_WORKSPACE, NL_ERR_CUDA, NL_ERR_OVERFLOW, NL_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnlcuda.so")
+
+
+class NlParams(C.Structure):
+    """struct nl_params (include/nlcuda.h)."""
+    _fields_ = [
+        ("float_type", C.c_int32),
+        ("int_type", C.c_int32),
+        ("cell", C.c_double * 9),
+        ("inv_cell", C.c_double * 9),
+        ("cutoff", C.c_double),
+        ("ncells", C.c_int32 * 3),
+        ("nxyz", C.c_int32 * 3),
+        ("pbc", C.c_uint8 * 3),
+        ("reserved", C.c_uint8 * 5),
+    ]
+
+
+class NlError(RuntimeError):
+    """Mirrors the reference's ErrorException convention (src/cell_list.jl:656-658)."""
+
+    def __init__(self, code, msg):
+        super().__init__(msg)
+        self.code = code
+
+
+_lib = None
+
+EXPORTS = ("nl_version", "nl_strerror", "nl_last_cuda_error", "nl_launch_count", "nl_workspace_bytes", "nl_build_cells", "nl_count_pairs",
+           "nl_fill_pairs", "nl_lazy_count", "nl_lazy_lj_energy")
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NlError(-100, f"libnlcuda.so not found at {LIB_PATH}: build it with __graft_entry__.build() "
+                                "(neighbourlists.jl_b200/csrc/build.sh); there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp, i64, sz = C.c_void_p, C.c_int64, C.c_size_t
+        pp = C.POINTER(NlParams)
+        L.nl_version.restype = C.c_int
+        L.nl_strerror.restype = C.c_char_p
+        L.nl_strerror.argtypes = [C.c_int]
+        L.nl_last_cuda_error.restype = C.c_int
+        L.nl_launch_count.restype = C.c_longlong
+        L.nl_workspace_bytes.restype = sz
+        L.nl_workspace_bytes.argtypes = [pp, i64, C.c_int]
+        L.nl_build_cells.argtypes = [pp, vp, i64, vp, vp, vp, vp, vp, sz, vp]
+        L.nl_count_pairs.argtypes = [pp, vp, i64, vp, vp, vp, C.POINTER(C.c_int64), vp, sz, vp]
+        L.nl_fill_pairs.argtypes = [pp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+        L.nl_lazy_count.argtypes = [pp, vp, i64, vp, vp, vp, vp, sz, vp]
+        L.nl_lazy_lj_energy.argtypes = [pp, vp, i64, vp, vp, C.c_double, C.c_double, vp, vp, sz, vp]
+        for n in ("nl_build_cells", "nl_count_pairs", "nl_fill_pairs", "nl_lazy_count", "nl_lazy_lj_energy"):
+            getattr(L, n).restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def check(rc: int):
+    if rc != 0:
+        L = lib()
+        msg = L.nl_strerror(rc).decode()
+        if rc == NL_ERR_CUDA:
+            msg += f" [cudaError_t {L.nl_last_cuda_error()}]"
+        raise NlError(rc, msg)
+
+
+def make_params(geo, float_dtype, int_dtype) -> NlParams:
+    """Fill nl_params from a cellmath.CellGeometry (matrices flattened in Julia column-major order)."""
+    p = NlParams()
+    p.float_type = NL_F64 if np.dtype(float_dtype) == np.float64 else NL_F32
+    p.int_type = NL_I64 if np.dtype(int_dtype) == np.int64 else NL_I32
+    c = np.asarray(geo.cell, dtype=np.float64).ravel(order="F")
+    ic = np.asarray(geo.inv_cell, dtype=np.float64).ravel(order="F")
+    for k in range(9):
+        p.cell[k] = float(c[k])
+        p.inv_cell[k] = float(ic[k])
+    p.cutoff = float(geo.cutoff)
+    for k in range(3):
+        if int(geo.ncells[k]) > 2**31 - 1:
+            raise NlError(NL_ERR_UNSUPPORTED, lib().nl_strerror(NL_ERR_UNSUPPORTED).decode())
+        p.ncells[k] = int(geo.ncells[k])
+        p.nxyz[k] = int(geo.nxyz[k])
+        p.pbc[k] = 1 if geo.pbc[k] else 0
+    return p

@@ -1,0 +1,297 @@
+"""Host-side mirror of the reference's operator interface for the sort-based neighbour-list path.
+
+Same names, argument meaning and error behaviour as NeighbourLists.jl
+(/root/reference/src/cell_list.jl:632-642 build_cell_list, :897-916 neighbour_list,
+/root/reference/src/gpu_kernels.jl:299-364 materialize_pairlist, /root/reference/src/types.jl:34-82
+PairList / SortedCellList), with torch CUDA tensors standing in for CuArrays.  Every stage runs in
+libnlcuda.so through the C ABI (include/nlcuda.h); there is no CPU fallback.
+
+Like the reference's arrays, every integer array is 1-BASED, and atom arguments `i` are 1-based.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .cellmath import CellGeometry, geometry
+
+_T2N = {torch.float32: np.float32, torch.float64: np.float64, torch.int32: np.int32, torch.int64: np.int64}
+_N2T = {np.dtype(np.int32): torch.int32, np.dtype(np.int64): torch.int64,
+        np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}
+
+
+def _int_dtype(int_type) -> torch.dtype:
+    if isinstance(int_type, torch.dtype):
+        if int_type not in (torch.int32, torch.int64):
+            raise TypeError("int_type must be int32 or int64")
+        return int_type
+    return _N2T[np.dtype(int_type)]
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _as_device_positions(X, device=None) -> torch.Tensor:
+    """Accepts an (N,3) torch tensor or array-like.  Host inputs are uploaded (pinned, async): the
+    reference would run its CPU path for them, this engine has none."""
+    if not torch.cuda.is_available():
+        raise _lib.NlError(-101, "no CUDA device: this engine has no CPU path")
+    if isinstance(X, torch.Tensor):
+        t = X
+    else:
+        a = np.asarray(X)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)
+        t = torch.from_numpy(np.ascontiguousarray(a))
+    if t.dtype not in (torch.float32, torch.float64):
+        raise TypeError("positions must be float32 or float64")
+    if t.dim() != 2 or t.shape[1] != 3:
+        # the reference only accepts 3-vectors (AbstractVector{<:SVec}); 2-D systems raise (test_atoms_base.jl:135-144)
+        raise ValueError("positions must be an (N, 3) array")
+    if not t.is_cuda:
+        dev = torch.device(device if device is not None else "cuda")
+        if not t.is_pinned():
+            t = t.pin_memory()
+        t = t.to(dev, non_blocking=True)
+    return t.contiguous()
+
+
+@dataclass
+class SortedCellList:
+    """Field-for-field twin of the reference's SortedCellList (src/types.jl:70-82)."""
+    X: torch.Tensor             # positions sorted by cell, (N,3) T
+    X_orig: torch.Tensor        # the caller's positions (aliased, never modified)
+    perm: torch.Tensor          # sorted slot -> original index (1-based), (N,) TI
+    cell_id: torch.Tensor       # linear cell of each sorted slot (1-based), (N,) TI
+    cell_offsets: torch.Tensor  # (ncells_total+1,) TI, 1-based
+    cell: np.ndarray            # (3,3) T, rows = lattice vectors
+    inv_cell: np.ndarray
+    pbc: tuple
+    cutoff: float
+    ncells: np.ndarray
+    ncells_total: int
+    # host-side extras (not part of the reference struct)
+    geo: CellGeometry = field(repr=False, default=None)
+    params: object = field(repr=False, default=None)
+    _ws: Optional[torch.Tensor] = field(repr=False, default=None)
+    _pl: object = field(repr=False, default=None)
+    _counts: Optional[torch.Tensor] = field(repr=False, default=None)
+
+
+@dataclass
+class PairList:
+    """Twin of the reference's PairList (src/types.jl:34-43); R is an optional extra (not a reference field)."""
+    X: torch.Tensor
+    C: np.ndarray
+    cutoff: float
+    i: torch.Tensor
+    j: torch.Tensor
+    S: torch.Tensor       # (P,3) TI
+    first: torch.Tensor   # (N+1,) TI, 1-based
+    R: Optional[torch.Tensor] = None
+
+    def cpu(self):
+        """Device -> host copies of every array (numpy), for inspection and tests."""
+        torch.cuda.current_stream(self.i.device).synchronize()
+        return dict(i=self.i.cpu().numpy(), j=self.j.cpu().numpy(), S=self.S.cpu().numpy(), first=self.first.cpu().numpy(),
+                    R=None if self.R is None else self.R.cpu().numpy(), X=self.X.cpu().numpy())
+
+
+# ------------------------------------------------------------------ construction
+def _pairs_workspace(clist: SortedCellList) -> torch.Tensor:
+    N = clist.X.shape[0]
+    need = _lib.lib().nl_workspace_bytes(clist.params, N, _lib.NL_STAGE_PAIRS)
+    if clist._ws is None or clist._ws.numel() < need:
+        clist._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=clist.X.device)
+    return clist._ws
+
+
+def build_cell_list(X, cutoff, cell, pbc, *, int_type=np.int32, device=None) -> SortedCellList:
+    """build_cell_list(X, cutoff, cell, pbc; int_type) -> SortedCellList  (src/cell_list.jl:632-679)."""
+    Xd = _as_device_positions(X, device)
+    it = _int_dtype(int_type)
+    fdt = np.dtype(_T2N[Xd.dtype])
+    geo = geometry(cell, cutoff, pbc, fdt)
+    nct = geo.ncells_total
+    tmax = 2**31 - 1 if it == torch.int32 else 2**63 - 1
+    if nct > tmax:
+        # src/cell_list.jl:655-659
+        raise _lib.NlError(_lib.NL_ERR_UNSUPPORTED,
+                           "Ratio of simulation cell size to cutoff is very large. Use a larger integer type (e.g. Int64), "
+                           "larger cutoff, or smaller simulation cell.")
+    params = _lib.make_params(geo, fdt, _T2N[it])
+    N = Xd.shape[0]
+    dev = Xd.device
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        Xs = torch.empty_like(Xd)
+        perm = torch.empty(N, dtype=it, device=dev)
+        cell_id = torch.empty(N, dtype=it, device=dev)
+        cell_offsets = torch.empty(nct + 1, dtype=it, device=dev)
+        need = L.nl_workspace_bytes(params, N, _lib.NL_STAGE_BUILD)
+        ws = torch.empty(max(need, 256), dtype=torch.uint8, device=dev)
+        _lib.check(L.nl_build_cells(params, _ptr(Xd), N, _ptr(Xs), _ptr(perm), _ptr(cell_id), _ptr(cell_offsets), _ptr(ws),
+                                    ws.numel(), _stream(dev)))
+    return SortedCellList(X=Xs, X_orig=Xd, perm=perm, cell_id=cell_id, cell_offsets=cell_offsets, cell=geo.cell,
+                          inv_cell=geo.inv_cell, pbc=geo.pbc, cutoff=geo.cutoff, ncells=geo.ncells, ncells_total=nct,
+                          geo=geo, params=params)
+
+
+def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers: Optional[dict] = None) -> PairList:
+    """materialize_pairlist(clist) -> PairList  (src/gpu_kernels.jl:299-364).  with_R additionally
+    stores R = X[j] - X[i] + C' S per pair (what the reference recomputes in _getR)."""
+    import ctypes as C
+    N = clist.X.shape[0]
+    dev = clist.X.device
+    it = clist.perm.dtype
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        first = torch.empty(N + 1, dtype=it, device=dev)
+        ws = _pairs_workspace(clist)
+        total = C.c_int64(0)
+        if timers is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
+        _lib.check(L.nl_count_pairs(clist.params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
+                                    C.byref(total), _ptr(ws), ws.numel(), _stream(dev)))
+        P = int(total.value)
+        if timers is not None:
+            ev[1].record()
+        i = torch.empty(P, dtype=it, device=dev)
+        j = torch.empty(P, dtype=it, device=dev)
+        S = torch.empty((P, 3), dtype=it, device=dev)
+        R = torch.empty((P, 3), dtype=clist.X.dtype, device=dev) if with_R else None
+        if timers is not None:
+            ev[2].record()
+        if P > 0:
+            _lib.check(L.nl_fill_pairs(clist.params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
+                                       _ptr(i), _ptr(j), _ptr(S), _ptr(R), _ptr(ws), ws.numel(), _stream(dev)))
+        if timers is not None:
+            ev[3].record()
+            timers.setdefault("events", []).append(ev)
+    return PairList(X=clist.X_orig, C=clist.cell, cutoff=clist.cutoff, i=i, j=j, S=S, first=first, R=R)
+
+
+def neighbour_list(X, cutoff, cell, pbc, *, lazy: bool = False, int_type=np.int32, with_R: bool = False, device=None):
+    """neighbour_list(X, cutoff, cell, pbc; lazy, int_type)  (src/cell_list.jl:897-916)."""
+    clist = build_cell_list(X, cutoff, cell, pbc, int_type=int_type, device=device)
+    if lazy:
+        return clist
+    return materialize_pairlist(clist, with_R=with_R)
+
+
+# ------------------------------------------------------------------ accessors (src/cell_list.jl:25-27, 507-611, 753-833, 919-927)
+def npairs(nlist: PairList) -> int:
+    return int(nlist.i.shape[0])
+
+
+def nsites(nl) -> int:
+    if isinstance(nl, PairList):
+        return int(nl.first.shape[0]) - 1
+    return int(nl.X.shape[0])
+
+
+def cutoff(nl) -> float:
+    return nl.cutoff
+
+
+def nneigs(nlist: PairList, i0: int) -> int:
+    f = nlist.first[i0 - 1:i0 + 1].tolist()
+    return int(f[1] - f[0])
+
+
+def maxneigs(nlist: PairList) -> int:
+    if nsites(nlist) == 0:
+        raise ValueError("maxneigs of an empty list")  # reference: maximum over an empty collection throws
+    return int((nlist.first[1:] - nlist.first[:-1]).max().item())
+
+
+max_neighbours = maxneigs
+max_neigs = maxneigs
+
+
+def _getR(nlist: PairList, lo: int, hi: int) -> torch.Tensor:
+    """R[n] = (X[j] - X[i]) + C' * S[n] with the reference's association (src/cell_list.jl:525-531)."""
+    j = nlist.j[lo:hi].long() - 1
+    i = nlist.i[lo:hi].long() - 1
+    d = nlist.X[j] - nlist.X[i]
+    S = nlist.S[lo:hi].to(nlist.X.dtype)
+    Cm = torch.as_tensor(nlist.C, dtype=nlist.X.dtype, device=nlist.X.device)
+    cs = torch.stack([(Cm[0, k] * S[:, 0] + Cm[1, k] * S[:, 1]) + Cm[2, k] * S[:, 2] for k in range(3)], dim=1)
+    return d + cs
+
+
+def neigss(nlist: PairList, i0: int):
+    """(j, R, S) of atom i0 (1-based)."""
+    f = nlist.first[i0 - 1:i0 + 1].tolist()
+    lo, hi = int(f[0]) - 1, int(f[1]) - 1
+    return nlist.j[lo:hi], _getR(nlist, lo, hi), nlist.S[lo:hi]
+
+
+def neigs(nlist: PairList, i0: int):
+    j, R, _ = neigss(nlist, i0)
+    return j, R
+
+
+def count_neighbours(clist: SortedCellList, i: Optional[int] = None):
+    """count_neighbours(clist, i) (src/cell_list.jl:808-814); with i=None, the counts of ALL atoms
+    as a device tensor in original order (one fused traversal, nl_lazy_count)."""
+    if clist._counts is None:
+        N = clist.X.shape[0]
+        dev = clist.X.device
+        with torch.cuda.device(dev):
+            out = torch.zeros(N, dtype=clist.perm.dtype, device=dev)
+            ws = _pairs_workspace(clist)
+            _lib.check(_lib.lib().nl_lazy_count(clist.params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets),
+                                                _ptr(out), _ptr(ws), ws.numel(), _stream(dev)))
+        clist._counts = out
+    if i is None:
+        return clist._counts
+    return int(clist._counts[i - 1].item())
+
+
+def lj_energy(clist: SortedCellList, eps: float, sigma: float) -> torch.Tensor:
+    """Fused for_each_neighbour traversal with a Lennard-Jones sink: sum over ORDERED pairs of
+    4 eps ((sigma/r)^12 - (sigma/r)^6); returns a device float64 scalar (nl_lazy_lj_energy)."""
+    N = clist.X.shape[0]
+    dev = clist.X.device
+    with torch.cuda.device(dev):
+        e = torch.zeros(1, dtype=torch.float64, device=dev)
+        ws = _pairs_workspace(clist)
+        _lib.check(_lib.lib().nl_lazy_lj_energy(clist.params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets),
+                                                float(eps), float(sigma), _ptr(e), _ptr(ws), ws.numel(), _stream(dev)))
+    return e
+
+
+def neighbours(nl, i: int):
+    """neighbours(nlist_or_clist, i) -> (j, R, S)  (src/cell_list.jl:606, :821-833)."""
+    if isinstance(nl, PairList):
+        return neigss(nl, i)
+    if nl._pl is None:
+        nl._pl = materialize_pairlist(nl, with_R=True)
+    pl = nl._pl
+    f = pl.first[i - 1:i + 1].tolist()
+    lo, hi = int(f[0]) - 1, int(f[1]) - 1
+    return pl.j[lo:hi], pl.R[lo:hi], pl.S[lo:hi]
+
+
+def for_each_neighbour(f, clist: SortedCellList, i: int):
+    """for_each_neighbour(f, clist, i): calls f(j, R, S) per neighbour of atom i (host-side
+    convenience over the device lists; device-side traversal sinks are count_neighbours / lj_energy)."""
+    js, Rs, Ss = neighbours(clist, i)
+    js, Rs, Ss = js.tolist(), Rs.tolist(), Ss.tolist()
+    for n in range(len(js)):
+        f(js[n], Rs[n], Ss[n])
+
+
+def num_neighbours(nl, i: int) -> int:
+    return nneigs(nl, i) if isinstance(nl, PairList) else count_neighbours(nl, i)

@@ -1,0 +1,52 @@
+// nl_build.cuh -- stage kernels of build_cell_list: cell binning, gather of the sorted copies and
+// cell_offsets extraction.  The sort between them is nl_scan_sort.cuh.
+#pragma once
+#include "nl_common.cuh"
+
+namespace nl {
+
+// Stage (1): compute_cell_ids_kernel! (src/gpu_kernels.jl:108-125).  One thread per atom in the
+// caller's order; key = 0-based linear cell id (x fastest, src/cell_list.jl:83-86).
+template <class T>
+__global__ void __launch_bounds__(256) k_bin(const T* __restrict__ X, long long n, Geo<T> g, uint32_t* __restrict__ keys) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  T x = X[3 * i], y = X[3 * i + 1], z = X[3 * i + 2];
+  int c[3];
+  long long w[3];
+  cell_of(g, x, y, z, c, w);
+  keys[i] = (uint32_t)c[0] + (uint32_t)g.nc[0] * ((uint32_t)c[1] + (uint32_t)g.nc[1] * (uint32_t)c[2]);
+}
+
+// After the sort: perm, cell_id (1-based, TI) and X_sorted = X[perm] (src/cell_list.jl:669-670).
+template <class T, class TI>
+__global__ void __launch_bounds__(256) k_finalize_sorted(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ svals,
+                                                         const T* __restrict__ X, long long n, T* __restrict__ Xs,
+                                                         TI* __restrict__ perm, TI* __restrict__ cell_id) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  uint32_t o = svals[s];
+  perm[s] = (TI)o + 1;
+  cell_id[s] = (TI)skeys[s] + 1;
+  T x = X[3ll * o], y = X[3ll * o + 1], z = X[3ll * o + 2];
+  Xs[3 * s] = x;
+  Xs[3 * s + 1] = y;
+  Xs[3 * s + 2] = z;
+}
+
+// Stage (3): cell_offsets[c] = 1 + (number of sorted keys < c), c in [0, nct]; no atomics, no scan
+// (replaces _histogram_kernel! + accumulate!, src/gpu_kernels.jl:191-197,262-285).  n == 0 gives all
+// ones (src/gpu_kernels.jl:268-271).
+template <class TI>
+__global__ void __launch_bounds__(256) k_cell_offsets(const uint32_t* __restrict__ skeys, long long n, long long nct, TI* __restrict__ co) {
+  long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c > nct) return;
+  long long lo = 0, hi = n;  // lower_bound(skeys, c)
+  while (lo < hi) {
+    long long mid = (lo + hi) >> 1;
+    if ((long long)skeys[mid] < c) lo = mid + 1; else hi = mid;
+  }
+  co[c] = (TI)(lo + 1);
+}
+
+}  // namespace nl

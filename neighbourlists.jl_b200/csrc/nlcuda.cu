@@ -1,0 +1,345 @@
+// nlcuda.cu -- the C ABI of libnlcuda.so (declared in include/nlcuda.h).
+// Host-side stage orchestration only; kernels live in the .cuh files next to this one.
+#include "../../include/nlcuda.h"
+
+#include "nl_build.cuh"
+#include "nl_common.cuh"
+#include "nl_scan_sort.cuh"
+#include "nl_traverse.cuh"
+#include "nl_tiled.cuh"
+
+namespace {
+
+using namespace nl;
+
+thread_local int g_last_cuda = 0;
+
+static_assert(sizeof(nl_params) == 192, "nl_params layout is part of the ABI");
+
+inline int cuda_fail(cudaError_t e) {
+  g_last_cuda = (int)e;
+  return NL_ERR_CUDA;
+}
+#define NL_CUDA(expr)                          \
+  do {                                         \
+    cudaError_t e__ = (expr);                  \
+    if (e__ != cudaSuccess) return cuda_fail(e__); \
+  } while (0)
+#define NL_LAUNCH_CHECK() NL_CUDA(cudaGetLastError())
+#define NL_LAUNCHED(n) nl::note_launch(n)
+
+inline size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
+inline size_t fsize(const nl_params* p) { return p->float_type == NL_F64 ? 8 : 4; }
+
+int check_params(const nl_params* p, int64_t N) {
+  if (!p) return NL_ERR_BAD_ARG;
+  if (p->float_type != NL_F32 && p->float_type != NL_F64) return NL_ERR_BAD_ARG;
+  if (p->int_type != NL_I32 && p->int_type != NL_I64) return NL_ERR_BAD_ARG;
+  if (N < 0) return NL_ERR_BAD_ARG;
+  long long nct = 1;
+  for (int k = 0; k < 3; k++) {
+    if (p->ncells[k] < 1 || p->nxyz[k] < 1) return NL_ERR_BAD_ARG;
+    nct *= p->ncells[k];
+    if (nct >= 2147483647ll) return NL_ERR_UNSUPPORTED;
+  }
+  if (N >= 2147483647ll) return NL_ERR_UNSUPPORTED;
+  if (!(p->cutoff > 0.0)) return NL_ERR_BAD_ARG;
+  return NL_OK;
+}
+
+template <class T> Geo<T> make_geo(const nl_params* p) {
+  Geo<T> g;
+  for (int k = 0; k < 9; k++) { g.cell[k] = (T)p->cell[k]; g.inv[k] = (T)p->inv_cell[k]; }
+  volatile T c = (T)p->cutoff;  // volatile: one rounded multiply in T, as clist.cutoff^2
+  volatile T c2 = c * c;
+  g.cutoff_sq = c2;
+  long long nct = 1;
+  for (int k = 0; k < 3; k++) { g.nc[k] = p->ncells[k]; g.nxyz[k] = p->nxyz[k]; g.pbc[k] = p->pbc[k] ? 1 : 0; nct *= p->ncells[k]; }
+  g.nct = (int)nct;
+  return g;
+}
+
+int key_bits(long long nct) {
+  int b = 1;
+  while (b < 32 && (1ll << b) < nct) b++;
+  return b;
+}
+
+// ---------------------------------------------------------------- workspace layouts
+struct BuildWs {
+  uint32_t *keyA, *keyB, *valA, *valB;
+  void* rs_scratch;
+  size_t total;
+};
+BuildWs build_ws(void* ws, int64_t N) {
+  BuildWs w;
+  char* p = (char*)ws;
+  size_t o = 0;
+  auto take = [&](size_t b) { char* r = p ? p + o : nullptr; o += al256(b); return (void*)r; };
+  size_t nb = (size_t)(N > 0 ? N : 1) * 4;
+  w.keyA = (uint32_t*)take(nb);
+  w.keyB = (uint32_t*)take(nb);
+  w.valA = (uint32_t*)take(nb);
+  w.valB = (uint32_t*)take(nb);
+  w.rs_scratch = take(rs_scratch_bytes(N > 0 ? N : 1));
+  w.total = o;
+  return w;
+}
+
+struct PairWs {
+  void *px, *py, *pz;
+  uint32_t *pidx, *pw, *counts;
+  unsigned long long* tsum;
+  unsigned long long* total;
+  void* tiled;  // tiled-kernel scratch (tile table, hit masks)
+  size_t total_bytes;
+};
+PairWs pair_ws(void* ws, const nl_params* prm, int64_t N) {
+  PairWs w;
+  char* p = (char*)ws;
+  size_t o = 0;
+  auto take = [&](size_t b) { char* r = p ? p + o : nullptr; o += al256(b); return (void*)r; };
+  size_t n1 = (size_t)(N > 0 ? N : 1);
+  take(256);  // header, reserved
+  w.px = take(n1 * fsize(prm));
+  w.py = take(n1 * fsize(prm));
+  w.pz = take(n1 * fsize(prm));
+  w.pidx = (uint32_t*)take(n1 * 4);
+  w.pw = (uint32_t*)take(n1 * 4);
+  w.counts = (uint32_t*)take(n1 * 4);
+  w.tsum = (unsigned long long*)take((size_t)(scan_tiles((long long)n1) + 1) * 8);
+  w.total = (unsigned long long*)take(256);
+  w.tiled = take(tiled_scratch_bytes(prm, N));
+  w.total_bytes = o;
+  return w;
+}
+
+// ---------------------------------------------------------------- stage implementations
+template <class T, class TI>
+int build_cells_impl(const nl_params* p, const void* X, int64_t N, void* Xs, void* perm, void* cell_id, void* cell_offsets, void* ws,
+                     cudaStream_t st) {
+  Geo<T> g = make_geo<T>(p);
+  const long long nct = g.nct;
+  BuildWs w = build_ws(ws, N);
+  const uint32_t* skeys = w.keyA;
+  if (N > 0) {
+    const unsigned nb = (unsigned)((N + 255) / 256);
+    k_bin<T><<<nb, 256, 0, st>>>((const T*)X, N, g, w.keyA);
+    NL_LAUNCHED(1);
+    NL_LAUNCH_CHECK();
+    int where = radix_sort_pairs(w.keyA, w.valA, w.keyB, w.valB, N, key_bits(nct), w.rs_scratch, st);
+    NL_LAUNCH_CHECK();
+    skeys = where ? w.keyB : w.keyA;
+    const uint32_t* svals = where ? w.valB : w.valA;
+    k_finalize_sorted<T, TI><<<nb, 256, 0, st>>>(skeys, svals, (const T*)X, N, (T*)Xs, (TI*)perm, (TI*)cell_id);
+    NL_LAUNCHED(1);
+    NL_LAUNCH_CHECK();
+  }
+  k_cell_offsets<TI><<<(unsigned)((nct + 1 + 255) / 256), 256, 0, st>>>(skeys, N, nct, (TI*)cell_offsets);
+  NL_LAUNCHED(1);
+  NL_LAUNCH_CHECK();
+  return NL_OK;
+}
+
+template <class T, class TI>
+int prep_impl(const nl_params* p, const void* Xs, int64_t N, const void* perm, PairWs& w, Geo<T>& g, cudaStream_t st) {
+  if (N > 0) {
+    k_prep_records<T, TI><<<(unsigned)((N + 255) / 256), 256, 0, st>>>((const T*)Xs, (const TI*)perm, N, g, (T*)w.px, (T*)w.py, (T*)w.pz,
+                                                                      w.pidx, w.pw);
+    NL_LAUNCHED(1);
+    NL_LAUNCH_CHECK();
+  }
+  return NL_OK;
+}
+
+template <class T> Records<T> records_of(const PairWs& w) {
+  Records<T> r;
+  r.px = (const T*)w.px; r.py = (const T*)w.py; r.pz = (const T*)w.pz; r.pidx = w.pidx; r.pw = w.pw;
+  return r;
+}
+
+template <class T, class TI, int MODE>
+int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, const Geo<T>& g, const Sinks<T, TI>& sk, cudaStream_t st) {
+  if (N <= 0) return NL_OK;
+  Records<T> rec = records_of<T>(w);
+  if (tiled_applicable<T>(p, g)) {
+    int rc = tiled_traverse<T, TI, MODE>(p, N, (const TI*)co, rec, g, sk, w.tiled, st);
+    if (rc != NL_OK) return rc;
+  } else {
+    k_traverse_generic<T, TI, MODE><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(rec, (const TI*)co, N, g, sk);
+    NL_LAUNCHED(1);
+  }
+  NL_LAUNCH_CHECK();
+  return NL_OK;
+}
+
+template <class T, class TI>
+int count_pairs_impl(const nl_params* p, const void* Xs, int64_t N, const void* perm, const void* co, void* first, int64_t* total_host,
+                     void* ws, cudaStream_t st) {
+  Geo<T> g = make_geo<T>(p);
+  PairWs w = pair_ws(ws, p, N);
+  unsigned long long total = 0;
+  if (N > 0) {
+    int rc = prep_impl<T, TI>(p, Xs, N, perm, w, g, st);
+    if (rc) return rc;
+    Sinks<T, TI> sk = {};
+    sk.counts = w.counts;
+    rc = traverse<T, TI, MODE_COUNT>(p, N, co, w, g, sk, st);
+    if (rc) return rc;
+    exclusive_scan<uint32_t, unsigned long long, TI>(w.counts, N, (TI*)first, 1ull, true, w.tsum, w.total, st);
+    NL_LAUNCH_CHECK();
+    NL_CUDA(cudaMemcpyAsync(&total, w.total, sizeof(total), cudaMemcpyDeviceToHost, st));
+  } else {
+    TI one = 1;
+    NL_CUDA(cudaMemcpyAsync(first, &one, sizeof(TI), cudaMemcpyHostToDevice, st));
+  }
+  NL_CUDA(cudaStreamSynchronize(st));
+  *total_host = (int64_t)total;
+  if (sizeof(TI) == 4 && total + 1 > 2147483647ull) return NL_ERR_OVERFLOW;
+  return NL_OK;
+}
+
+template <class T, class TI>
+int fill_pairs_impl(const nl_params* p, int64_t N, const void* co, const void* first, void* io, void* jo, void* So, void* Ro, void* ws,
+                    cudaStream_t st) {
+  Geo<T> g = make_geo<T>(p);
+  PairWs w = pair_ws(ws, p, N);
+  Sinks<T, TI> sk = {};
+  sk.first = (const TI*)first;
+  sk.io = (TI*)io; sk.jo = (TI*)jo; sk.So = (TI*)So; sk.Ro = (T*)Ro;
+  return traverse<T, TI, MODE_FILL>(p, N, co, w, g, sk, st);
+}
+
+template <class TI> __global__ void k_counts_to_ti(const uint32_t* __restrict__ c, long long n, TI* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (TI)c[i];
+}
+
+template <class T, class TI>
+int lazy_count_impl(const nl_params* p, const void* Xs, int64_t N, const void* perm, const void* co, void* counts_out, void* ws,
+                    cudaStream_t st) {
+  if (N <= 0) return NL_OK;
+  Geo<T> g = make_geo<T>(p);
+  PairWs w = pair_ws(ws, p, N);
+  int rc = prep_impl<T, TI>(p, Xs, N, perm, w, g, st);
+  if (rc) return rc;
+  Sinks<T, TI> sk = {};
+  sk.counts = w.counts;
+  rc = traverse<T, TI, MODE_COUNT>(p, N, co, w, g, sk, st);
+  if (rc) return rc;
+  k_counts_to_ti<TI><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(w.counts, N, (TI*)counts_out);
+  NL_LAUNCHED(1);
+  NL_LAUNCH_CHECK();
+  return NL_OK;
+}
+
+template <class T, class TI>
+int lazy_lj_impl(const nl_params* p, const void* Xs, int64_t N, const void* perm, const void* co, double eps, double sigma, double* e_out,
+                 void* ws, cudaStream_t st) {
+  NL_CUDA(cudaMemsetAsync(e_out, 0, sizeof(double), st));
+  if (N <= 0) return NL_OK;
+  Geo<T> g = make_geo<T>(p);
+  PairWs w = pair_ws(ws, p, N);
+  int rc = prep_impl<T, TI>(p, Xs, N, perm, w, g, st);
+  if (rc) return rc;
+  Sinks<T, TI> sk = {};
+  sk.energy = e_out;
+  sk.lj_eps = eps;
+  sk.lj_sigma2 = sigma * sigma;
+  return traverse<T, TI, MODE_LJ>(p, N, co, w, g, sk, st);
+}
+
+#define NL_DISPATCH(p, FN, ...)                                                              \
+  ((p)->float_type == NL_F64                                                                 \
+       ? ((p)->int_type == NL_I64 ? FN<double, int64_t>(__VA_ARGS__) : FN<double, int32_t>(__VA_ARGS__)) \
+       : ((p)->int_type == NL_I64 ? FN<float, int64_t>(__VA_ARGS__) : FN<float, int32_t>(__VA_ARGS__)))
+
+int check_ws(const void* ws, size_t have, size_t need) {
+  if (need == 0) return NL_OK;
+  if (!ws || ((uintptr_t)ws & 255) != 0 || have < need) return NL_ERR_WORKSPACE;
+  return NL_OK;
+}
+
+}  // namespace
+
+// ================================================================ exported C ABI
+extern "C" {
+
+int nl_version(void) { return NL_VERSION; }
+
+const char* nl_strerror(int code) {
+  switch (code) {
+    case NL_OK: return "ok";
+    case NL_ERR_BAD_ARG: return "nlcuda: bad argument (null pointer, negative N, bad type tag, ncells < 1, nxyz < 1 or cutoff <= 0)";
+    case NL_ERR_WORKSPACE: return "nlcuda: workspace missing, misaligned (256 B) or smaller than nl_workspace_bytes()";
+    case NL_ERR_CUDA: return "nlcuda: CUDA error (see nl_last_cuda_error())";
+    case NL_ERR_OVERFLOW: return "nlcuda: number of pairs overflows int_type; use a 64-bit int_type";
+    case NL_ERR_UNSUPPORTED: return "nlcuda: N or prod(ncells) >= 2^31 - 1 is not supported (use a larger cutoff or a smaller simulation cell)";
+    default: return "nlcuda: unknown error code";
+  }
+}
+
+int nl_last_cuda_error(void) { return g_last_cuda; }
+
+long long nl_launch_count(void) { return nl::launch_counter().load(); }
+
+size_t nl_workspace_bytes(const nl_params* params, int64_t N, int stage) {
+  if (check_params(params, N) != NL_OK) return 0;
+  if (stage == NL_STAGE_BUILD) return build_ws(nullptr, N).total;
+  if (stage == NL_STAGE_PAIRS) return pair_ws(nullptr, params, N).total_bytes;
+  return 0;
+}
+
+int nl_build_cells(const nl_params* params, const void* X, int64_t N, void* X_sorted, void* perm, void* cell_id, void* cell_offsets,
+                   void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_params(params, N);
+  if (rc) return rc;
+  if (!cell_offsets || (N > 0 && (!X || !X_sorted || !perm || !cell_id))) return NL_ERR_BAD_ARG;
+  rc = check_ws(ws, ws_bytes, build_ws(nullptr, N).total);
+  if (rc) return rc;
+  return NL_DISPATCH(params, build_cells_impl, params, X, N, X_sorted, perm, cell_id, cell_offsets, ws, (cudaStream_t)stream);
+}
+
+int nl_count_pairs(const nl_params* params, const void* X_sorted, int64_t N, const void* perm, const void* cell_offsets, void* first,
+                   int64_t* total_pairs_host, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_params(params, N);
+  if (rc) return rc;
+  if (!first || !total_pairs_host || !cell_offsets || (N > 0 && (!X_sorted || !perm))) return NL_ERR_BAD_ARG;
+  rc = check_ws(ws, ws_bytes, pair_ws(nullptr, params, N).total_bytes);
+  if (rc) return rc;
+  return NL_DISPATCH(params, count_pairs_impl, params, X_sorted, N, perm, cell_offsets, first, total_pairs_host, ws, (cudaStream_t)stream);
+}
+
+int nl_fill_pairs(const nl_params* params, const void* X_sorted, int64_t N, const void* perm, const void* cell_offsets, const void* first,
+                  void* i_out, void* j_out, void* S_out, void* R_out, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_params(params, N);
+  if (rc) return rc;
+  if (N == 0) return NL_OK;
+  if (!first || !cell_offsets || !X_sorted || !perm || !i_out || !j_out || !S_out) return NL_ERR_BAD_ARG;
+  rc = check_ws(ws, ws_bytes, pair_ws(nullptr, params, N).total_bytes);
+  if (rc) return rc;
+  return NL_DISPATCH(params, fill_pairs_impl, params, N, cell_offsets, first, i_out, j_out, S_out, R_out, ws, (cudaStream_t)stream);
+}
+
+int nl_lazy_count(const nl_params* params, const void* X_sorted, int64_t N, const void* perm, const void* cell_offsets, void* counts_out,
+                  void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_params(params, N);
+  if (rc) return rc;
+  if (N == 0) return NL_OK;
+  if (!counts_out || !cell_offsets || !X_sorted || !perm) return NL_ERR_BAD_ARG;
+  rc = check_ws(ws, ws_bytes, pair_ws(nullptr, params, N).total_bytes);
+  if (rc) return rc;
+  return NL_DISPATCH(params, lazy_count_impl, params, X_sorted, N, perm, cell_offsets, counts_out, ws, (cudaStream_t)stream);
+}
+
+int nl_lazy_lj_energy(const nl_params* params, const void* X_sorted, int64_t N, const void* perm, const void* cell_offsets, double eps,
+                      double sigma, double* energy_out, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_params(params, N);
+  if (rc) return rc;
+  if (!energy_out || (N > 0 && (!cell_offsets || !X_sorted || !perm))) return NL_ERR_BAD_ARG;
+  rc = check_ws(ws, ws_bytes, pair_ws(nullptr, params, N).total_bytes);
+  if (rc) return rc;
+  return NL_DISPATCH(params, lazy_lj_impl, params, X_sorted, N, perm, cell_offsets, eps, sigma, energy_out, ws, (cudaStream_t)stream);
+}
+
+}  // extern "C"

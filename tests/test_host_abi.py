@@ -1,0 +1,93 @@
+"""CPU-only checks of the host logic and the C-ABI boundary: the shared library loads, exports every
+symbol include/nlcuda.h declares, agrees on the nl_params layout, and validates arguments without
+touching a GPU.  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import neighbourlists_jl_b200 as nl
+from oracle import nl_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "nlcuda.h")).read()
+    return sorted(set(re.findall(r"NL_API[^;(]*?\b(nl_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = nl._lib.lib()
+    syms = declared_symbols()
+    assert len(syms) >= 9 and set(syms) == set(nl._lib.EXPORTS)
+    for s in syms:
+        assert hasattr(L, s), s
+    assert L.nl_version() == 100
+    assert b"workspace" in L.nl_strerror(nl._lib.NL_ERR_WORKSPACE)
+    assert L.nl_strerror(0) == b"ok"
+
+
+def test_params_layout_and_validation():
+    assert C.sizeof(nl._lib.NlParams) == 192
+    geo = nl.cellmath.geometry(np.eye(3) * 20.0, 5.0, (True, True, False), np.float64)
+    p = nl._lib.make_params(geo, np.float64, np.int32)
+    L = nl._lib.lib()
+    assert list(p.ncells) == [4, 4, 4] and list(p.nxyz) == [1, 1, 1] and list(p.pbc) == [1, 1, 0]
+    assert L.nl_workspace_bytes(p, 1000, nl._lib.NL_STAGE_BUILD) > 16000
+    assert L.nl_workspace_bytes(p, 1000, nl._lib.NL_STAGE_PAIRS) > 1000 * 36
+    assert L.nl_workspace_bytes(p, 0, nl._lib.NL_STAGE_PAIRS) > 0
+    assert L.nl_workspace_bytes(p, -1, nl._lib.NL_STAGE_BUILD) == 0
+    # argument validation happens before any CUDA call
+    assert L.nl_build_cells(None, None, 0, None, None, None, None, None, 0, None) == nl._lib.NL_ERR_BAD_ARG
+    assert L.nl_build_cells(p, None, 10, None, None, None, None, None, 0, None) == nl._lib.NL_ERR_BAD_ARG
+    dummy = (C.c_char * 64)()
+    ptr = C.cast(dummy, C.c_void_p)
+    assert L.nl_build_cells(p, ptr, 10, ptr, ptr, ptr, ptr, None, 0, None) == nl._lib.NL_ERR_WORKSPACE
+    total = C.c_int64(0)
+    assert L.nl_count_pairs(p, ptr, 10, ptr, ptr, ptr, C.byref(total), None, 0, None) == nl._lib.NL_ERR_WORKSPACE
+    bad = nl._lib.make_params(geo, np.float64, np.int32)
+    bad.nxyz[1] = 0
+    assert L.nl_workspace_bytes(bad, 10, 0) == 0
+    big = nl._lib.make_params(geo, np.float64, np.int64)
+    big.ncells[0] = big.ncells[1] = big.ncells[2] = 2000
+    assert L.nl_build_cells(big, ptr, 10, ptr, ptr, ptr, ptr, ptr, 64, None) == nl._lib.NL_ERR_UNSUPPORTED
+    with pytest.raises(nl.NlError):
+        nl._lib.check(nl._lib.NL_ERR_OVERFLOW)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_host_cell_analysis_matches_oracle(dtype):
+    # cellmath.analyze_cell restates src/cell_list.jl:152-170; must equal the oracle's bit for bit
+    rng = np.random.default_rng(1)
+    for t in range(300):
+        Cm = rng.normal(size=(3, 3)) * 5 + np.eye(3) * 10
+        if t % 5 == 0:
+            Cm = np.diag(rng.random(3) * 50 + 3)
+        if t % 7 == 0:
+            Cm[2] *= -1  # left-handed
+        rc = rng.random() * 6 + 0.5
+        inv, nc, lens, nxyz = nl.cellmath.analyze_cell(Cm, rc, dtype)
+        o = O.analyze_cell(Cm, rc, dtype)
+        assert np.array_equal(inv, o["inv_mat"]) and np.array_equal(nc, o["ncells"])
+        assert np.array_equal(lens, o["lens"]) and np.array_equal(nxyz, o["nxyz"])
+
+
+def test_headline_geometry():
+    # 10 M atoms -> L = 584.80, 116^3 cells; C3 triclinic -> (60, 53, 47)
+    L = (1e7 / 0.05) ** (1 / 3)
+    g = nl.cellmath.geometry(np.eye(3) * L, 5.0, (True, True, True), np.float64)
+    assert g.ncells.tolist() == [116, 116, 116] and g.nxyz.tolist() == [1, 1, 1]
+    s = (1e6 / 0.05 / 720) ** (1 / 3)
+    g = nl.cellmath.geometry(s * np.array([[10, 2, 1], [0, 9, 1.5], [0, 0, 8.0]]), 5.0, (True, True, False), np.float64)
+    assert g.ncells.tolist() == [60, 53, 47]
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(nl.NlError):
+        nl.neighbour_list(np.zeros((4, 3)), 1.0, np.eye(3) * 5, (True, True, True))

@@ -1,0 +1,213 @@
+"""GPU parity: libnlcuda.so (through the C ABI, via the host mirror) against the CPU oracle on the
+same seeded inputs.  Mirrors the structure of the reference's test/test_gpu.jl and
+test/test_sortbased.jl.  Bars: SortedCellList fields, CSR offsets and the (i,j,S) set bit-exact;
+R within 1e-12 relative (Float64) / 1e-5 (Float32)."""
+import numpy as np
+import pytest
+
+from oracle import nl_oracle as O
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+
+RTOL = {np.dtype(np.float64): 1e-12, np.dtype(np.float32): 1e-5}
+
+
+@pytest.fixture(scope="module")
+def nl():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import neighbourlists_jl_b200 as nl
+    nl._lib.lib()  # fail loudly if the extension is missing
+    return nl
+
+
+def run_engine(nl, X, cutoff, cell, pbc, int_type=np.int32, with_R=True):
+    import torch
+    Xd = torch.from_numpy(np.ascontiguousarray(X)).cuda()
+    clist = nl.build_cell_list(Xd, cutoff, cell, pbc, int_type=int_type)
+    pl = nl.materialize_pairlist(clist, with_R=with_R)
+    torch.cuda.synchronize()
+    return clist, pl
+
+
+def check_case(nl, X, cutoff, cell, pbc, dtype=np.float64, int_type=np.int32, msg=""):
+    X = np.asarray(X, dtype=dtype)
+    clist, pl = run_engine(nl, X, cutoff, cell, pbc, int_type)
+    geo = dict(inv=np.asarray(clist.inv_cell).ravel(order="F"), ncells=clist.ncells, nxyz=clist.geo.nxyz)
+    orc = O.sortbased(X, cutoff, cell, pbc, dtype=dtype, int_type=int_type, geo=geo)
+    # host geometry == oracle's own analyze_cell
+    own = O.analyze_cell(cell, cutoff, dtype)
+    assert np.array_equal(own["ncells"], clist.ncells) and np.array_equal(own["nxyz"], clist.geo.nxyz), msg
+    assert np.array_equal(own["inv_mat"], clist.inv_cell), msg
+    # SortedCellList fields, bit-exact (stable sort => same perm as the CPU sortperm)
+    assert clist.perm.dtype == pl.i.dtype
+    assert np.array_equal(clist.perm.cpu().numpy(), orc["perm"]), f"{msg}: perm"
+    assert np.array_equal(clist.cell_id.cpu().numpy(), orc["cell_id"]), f"{msg}: cell_id"
+    assert np.array_equal(clist.cell_offsets.cpu().numpy(), orc["cell_offsets"]), f"{msg}: cell_offsets"
+    assert np.array_equal(clist.X.cpu().numpy(), orc["Xs"]), f"{msg}: X sorted"
+    eng = pl.cpu()
+    assert eng["i"].dtype == np.dtype(int_type) and eng["S"].dtype == np.dtype(int_type) and eng["first"].dtype == np.dtype(int_type)
+    U.assert_engine_matches_oracle(eng, orc, RTOL[np.dtype(dtype)], msg=msg)
+    # lazy sinks
+    counts = nl.count_neighbours(clist).cpu().numpy()
+    assert np.array_equal(counts.astype(np.int64), np.diff(orc["first"].astype(np.int64))), f"{msg}: lazy counts"
+    return clist, pl, orc
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("int_type", [np.int32, np.int64])
+def test_random_configs(nl, dtype, int_type):
+    # test/test_gpu.jl:43-47 (5 random configs, N in 50:200, cutoff L/4 via test_cpu_vs_gpu)
+    rng = np.random.default_rng(7)
+    for k in range(5):
+        N = int(rng.integers(50, 201))
+        X, C, L = U.rand_config(N, seed=100 + k, dtype=dtype)
+        check_case(nl, X, L * 0.25, C, (True, True, True), dtype, int_type, msg=f"rand{k}")
+        check_case(nl, X, L / 3, C, (True, True, True), dtype, int_type, msg=f"rand{k} L/3")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_all_pbc(nl, dtype):
+    for k, pbc in enumerate(U.ALL_PBC):
+        X, C, L = U.rand_config(120, seed=200 + k, dtype=dtype)
+        check_case(nl, X, L * 0.25, C, pbc, dtype, msg=f"pbc{pbc}")
+        Xd = U.displace_by_lattice(X, C, pbc)
+        check_case(nl, Xd, L * 0.25, C, pbc, dtype, msg=f"pbc{pbc} displaced")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_triclinic_all_pbc(nl, dtype):
+    # test/test_gpu.jl:53-60 plus every pbc combination and displaced atoms
+    for k, pbc in enumerate(U.ALL_PBC):
+        X = U.rand_in_cell(80, U.TRICLINIC, seed=300 + k, dtype=dtype)
+        check_case(nl, X, 3.0, U.TRICLINIC.astype(dtype), pbc, dtype, msg=f"tri{pbc}")
+        Xd = U.displace_by_lattice(X, U.TRICLINIC, pbc)
+        check_case(nl, Xd, 3.0, U.TRICLINIC.astype(dtype), pbc, dtype, msg=f"tri{pbc} displaced")
+
+
+def test_edge_cases(nl):
+    # test/test_utils.jl:480-494
+    C = np.eye(3) * 10.0
+    _, pl, _ = check_case(nl, [[5.0, 5.0, 5.0]], 3.0, C, (True, True, True), msg="single")
+    assert nl.npairs(pl) == 0 and pl.first.cpu().tolist() == [1, 1]
+    _, pl, _ = check_case(nl, [[5.0, 5.0, 5.0], [5.0, 5.0, 6.0]], 3.0, C, (True, True, True), msg="two")
+    assert nl.npairs(pl) == 2
+    _, pl, _ = check_case(nl, [[1.0, 1.0, 1.0], [8.0, 8.0, 8.0]], 3.0, C, (False, False, False), msg="far")
+    assert nl.npairs(pl) == 0 and pl.first.cpu().tolist() == [1, 1, 1]
+
+
+def test_empty(nl):
+    # nat == 0: first = [1], cell_offsets all ones (src/gpu_kernels.jl:268-271, 303-312)
+    import torch
+    C = np.eye(3) * 10.0
+    clist = nl.build_cell_list(torch.zeros((0, 3), dtype=torch.float64, device="cuda"), 3.0, C, (True, True, True))
+    assert clist.cell_offsets.cpu().tolist() == [1] * 28
+    pl = nl.materialize_pairlist(clist)
+    assert pl.first.cpu().tolist() == [1] and nl.npairs(pl) == 0 and nl.nsites(pl) == 0
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_large_systems(nl, dtype):
+    # test/test_utils.jl:540-549 (N = 500, 1000, 2000; cutoff 0.25 L) -- full comparison, not just counts
+    for N in (500, 1000, 2000):
+        X, C, L = U.rand_config(N, seed=N, dtype=dtype)
+        check_case(nl, X, L * 0.25, C, (True, True, True), dtype, msg=f"N={N}")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_high_density(nl, dtype):
+    # test/test_gpu.jl:78-86: 200 atoms, L = 5, rc = 2
+    rng = np.random.Generator(np.random.PCG64(5))
+    X = (rng.random((200, 3)) * 5.0).astype(dtype)
+    check_case(nl, X, 2.0, (np.eye(3) * 5.0).astype(dtype), (True, True, True), dtype, msg="dense")
+
+
+def test_elongated_and_large_cutoff(nl):
+    # test/test_sortbased.jl:36-41, 49-55
+    C2 = np.diag([5.0, 5.0, 20.0])
+    X2 = U.rand_in_cell(80, C2, seed=11)
+    check_case(nl, X2, 3.0, C2, (True, True, True), msg="elongated")
+    X, C, L = U.rand_config(30, seed=12)
+    check_case(nl, X, L * 0.6, C, (True, True, True), msg="cutoff 0.6 L")
+    check_case(nl, X, L * 1.7, C, (True, False, True), msg="cutoff 1.7 L mixed")
+
+
+def test_fcc_cu(nl):
+    # BASELINE config 2: fcc Cu 4x4x4, rc = 5 -> 10 752 pairs, 42 per atom, 3 720 with S != 0
+    for a in (3.61, 3.615):
+        X, C = U.fcc(a)
+        _, pl, _ = check_case(nl, X, 5.0, C, (True, True, True), msg=f"fcc a={a}")
+        e = pl.cpu()
+        assert nl.npairs(pl) == 10752 and np.all(np.diff(e["first"]) == 42) and int((np.abs(e["S"]).sum(1) > 0).sum()) == 3720
+    # test/test_atoms_base.jl:13-69: rc = 3.5 -> 12 neighbours for every atom
+    for reps in ((4, 2, 3), (3, 3, 3), (2, 2, 2)):
+        X, C = U.fcc(3.61, reps)
+        _, pl, _ = check_case(nl, X, 3.5, C, (True, True, True), msg=f"fcc {reps}")
+        assert np.all(np.diff(pl.cpu()["first"]) == 12)
+
+
+def test_issue6_outside_box(nl):
+    # test/test_sortbased.jl:143-228
+    C = np.eye(3) * 8.0
+    for X in ([[0.5, 0.5, 0.5], [0.5, 1.5, 0.5]], [[0.5, 0.5, 0.5], [0.5, -0.5, 0.5]], [[0.5, 0.5, 0.5], [0.5, -6.5, 0.5]]):
+        _, pl, _ = check_case(nl, X, 1.5, C, (True, True, True), msg="issue6")
+        e = pl.cpu()
+        assert nl.npairs(pl) == 2
+        assert np.allclose(np.linalg.norm(e["R"], axis=1), 1.0, atol=1e-12)
+    tiny = -5e-17 * 8.0
+    X = np.array([[0.5, 8.0 - 0.3, 0.5], [0.5, tiny, 0.5]])
+    clist, pl, _ = check_case(nl, X, 1.5, C, (True, True, True), msg="tiny negative frac")
+    j, R, S = nl.neighbours(pl, 1)
+    assert 2 in j.cpu().tolist()
+    k = j.cpu().tolist().index(2)
+    Rk = R[k].cpu().numpy()
+    assert abs(np.linalg.norm(Rk) - 0.3) < 1e-9
+    assert np.allclose(X[1] - X[0] + S[k].cpu().numpy() @ C, Rk, atol=1e-12)
+    # far excursions: windings beyond the packed 10-bit range take the recompute path
+    X, C, L = U.rand_config(100, seed=66)
+    Xf = X.copy()
+    Xf[::3, 0] += 1000 * L
+    Xf[1::3, 2] -= 777 * L
+    check_case(nl, Xf, L * 0.25, C, (True, True, True), msg="far windings")
+
+
+def test_left_handed_and_hcp_fixtures(nl):
+    # harvested from the reference's dead test/test_julip.jl:80-86, :126-133
+    X = np.array([[0.0, 0.0, 0.0], [1.92333044, 6.63816518e-17, -1.36], [1.92333044, 1.92333044, -2.72], [3.84666089, 1.92333044, -4.08]])
+    C = np.diag([3.84666089, 3.84666089, -5.44])
+    check_case(nl, X, 2.3 * 2.35, C, (True, True, True), msg="left-handed Si")
+    C1 = np.array([[5.71757, -1.81834e-15, 9.74255e-41], [-2.85879, 4.95156, 4.93924e-25], [4.56368e-40, 9.05692e-25, 9.05629]])
+    X1 = np.array([[0.00533847, 2.85879, -1.42939, 1.42939, 0.0, 2.85879, -1.42939, 1.42939, -1.43e-6, 2.85878, -1.42939, 1.42939, -1.43e-6, 2.85878, -1.42939, 1.42939],
+                   [-0.0, -0.0, 2.47578, 2.47578, 0.0, -0.0, 2.47578, 2.47578, 1.65052, 1.65052, 4.1263, 4.1263, 1.65052, 1.65052, 4.1263, 4.1263],
+                   [0.00845581, 0.0, 0.0, 0.0, 4.52815, 4.52815, 4.52815, 4.52815, 2.26407, 2.26407, 2.26407, 2.26407, 6.79222, 6.79222, 6.79222, 6.79222]]).T
+    check_case(nl, X1, 2.5 * 2.95, C1, (True, True, True), msg="hcp Ti 1")
+
+
+def test_lazy_equals_materialised_and_lj(nl):
+    # test/test_sortbased.jl:74-115 and BASELINE config 5 (Float32, rc = 6, LJ sink) at a small size
+    for dtype, tol in ((np.float32, 1e-6), (np.float64, 1e-12)):
+        X, C, L = U.rand_config(3000, seed=21, dtype=dtype)
+        clist, pl, orc = check_case(nl, X, 6.0, C, (True, True, True), dtype, msg="lazy")
+        assert int(nl.count_neighbours(clist).sum().item()) == nl.npairs(pl)
+        assert nl.count_neighbours(clist, 17) == nl.nneigs(pl, 17) == nl.num_neighbours(pl, 17)
+        e = float(nl.lj_energy(clist, 1.0, 3.4).item())
+        lazy = O.sortbased(X, 6.0, C, (True, True, True), dtype=dtype, lazy=True)
+        e_ref = O.lj_energy(lazy, 1.0, 3.4)
+        assert abs(e - e_ref) <= tol * abs(e_ref), (e, e_ref)
+
+
+def test_config1_10k(nl):
+    # BASELINE config 1: 10k atoms, rho = 0.05, rc = 5, full PBC, Float64 (~262k pairs)
+    X, C, L = U.rand_config(10000, seed=1)
+    _, pl, orc = check_case(nl, X, 5.0, C, (True, True, True), msg="C1")
+    assert 250000 < nl.npairs(pl) < 275000
+
+
+def test_overflow_and_errors(nl):
+    import torch
+    X, C, L = U.rand_config(10, seed=3)
+    with pytest.raises(nl.NlError):
+        nl.build_cell_list(torch.from_numpy(X).cuda(), 1e-4, C * 1000, (True, True, True))  # prod(ncells) > typemax(Int32)
+    with pytest.raises(ValueError):
+        nl.build_cell_list(torch.zeros((4, 2), dtype=torch.float64, device="cuda"), 1.0, C, (True, True, True))
