@@ -95,6 +95,7 @@ template <class TI> inline void wrap_and_shift(TI i, TI n, bool pbc, TI& wrapped
     shift = 0;
     return;
   }
+  if (i >= 1 && i <= n) { wrapped = i; shift = 0; return; }  // neither while loop runs
   TI q = (i - 1) / n, r = (i - 1) % n;
   if (r < 0) { r += n; q -= 1; }
   wrapped = r + 1;
