@@ -49,70 +49,77 @@ __global__ void __launch_bounds__(256) k_prep_records(const T* __restrict__ Xs, 
   pw[s] = pack_wind(w);
 }
 
-// Generic traversal: one thread per atom (sorted order), any nxyz >= 1, any ncells >= 1, any
-// density.  Visits cells in the reference's order (dz, dy, dx, then sorted slot), so a FILL row
-// comes out in the reference's own traversal order.  Used where the tiled kernel's assumptions do
-// not hold (tiny boxes, stencils wider than one cell).
+// Generic traversal of ONE atom (sorted slot s): any nxyz >= 1, any ncells >= 1, any density.
+// Visits cells in the reference's order (dz, dy, dx, then sorted slot), so a FILL row comes out in
+// the reference's own traversal order.  Used where the tiled kernel's assumptions do not hold
+// (tiny boxes, stencils wider than one cell, tiles denser than the shared-memory budget).
+// Returns the atom's LJ energy contribution (MODE_LJ) or 0.
 template <class T, class TI, int MODE>
-__global__ void __launch_bounds__(128) k_traverse_generic(Records<T> rec, const TI* __restrict__ co, long long n, Geo<T> g, Sinks<T, TI> out) {
-  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ double generic_atom(long long s, const Records<T>& rec, const TI* __restrict__ co, const Geo<T>& g,
+                                               const Sinks<T, TI>& out) {
   double e_acc = 0.0;
-  if (s < n) {
-    const T xi = rec.px[s], yi = rec.py[s], zi = rec.pz[s];
-    const uint32_t io = rec.pidx[s];
-    int ci[3];
-    long long wi[3];
-    cell_of(g, xi, yi, zi, ci, wi);
-    uint32_t cnt = 0;
-    long long wpos = 0;
-    if (MODE == MODE_FILL) wpos = (long long)out.first[io] - 1;
-    for (int dz = -g.nxyz[2]; dz <= g.nxyz[2]; dz++) {
-      int cz; long long sz = 0;
-      { long long v = (long long)ci[2] + dz;
-        if (g.pbc[2]) wrap0(v, g.nc[2], cz, sz); else { if (v < 0 || v >= g.nc[2]) continue; cz = (int)v; } }
-      for (int dy = -g.nxyz[1]; dy <= g.nxyz[1]; dy++) {
-        int cy; long long sy = 0;
-        { long long v = (long long)ci[1] + dy;
-          if (g.pbc[1]) wrap0(v, g.nc[1], cy, sy); else { if (v < 0 || v >= g.nc[1]) continue; cy = (int)v; } }
-        for (int dx = -g.nxyz[0]; dx <= g.nxyz[0]; dx++) {
-          int cx; long long sx = 0;
-          { long long v = (long long)ci[0] + dx;
-            if (g.pbc[0]) wrap0(v, g.nc[0], cx, sx); else { if (v < 0 || v >= g.nc[0]) continue; cx = (int)v; } }
-          const long long cl = (long long)cx + (long long)g.nc[0] * ((long long)cy + (long long)g.nc[1] * cz);
-          const long long b0 = (long long)co[cl] - 1, b1 = (long long)co[cl + 1] - 1;
-          const bool zero_shift = (sx == 0 && sy == 0 && sz == 0);
-          for (long long t = b0; t < b1; t++) {
-            const uint32_t jo = rec.pidx[t];
-            if (jo == io && zero_shift) continue;  // _is_self_interaction, src/gpu_kernels.jl:30-33
-            const T xj = rec.px[t], yj = rec.py[t], zj = rec.pz[t];
-            long long wj[3];
-            const uint32_t pwj = rec.pw[t];
-            if (pwj & WIND_OVERFLOW) { int cj[3]; cell_of(g, xj, yj, zj, cj, wj); } else unpack_wind(pwj, wj);
-            const long long S[3] = {sx + wi[0] - wj[0], sy + wi[1] - wj[1], sz + wi[2] - wj[2]};
-            T R[3];
-            const T r2 = pair_r2(g, xi, yi, zi, xj, yj, zj, S, R);
-            if (r2 < g.cutoff_sq) {
-              if (MODE == MODE_COUNT) cnt++;
-              if (MODE == MODE_FILL) {
-                out.io[wpos] = (TI)io + 1;
-                out.jo[wpos] = (TI)jo + 1;
-                out.So[3 * wpos] = (TI)S[0];
-                out.So[3 * wpos + 1] = (TI)S[1];
-                out.So[3 * wpos + 2] = (TI)S[2];
-                if (out.Ro) { out.Ro[3 * wpos] = R[0]; out.Ro[3 * wpos + 1] = R[1]; out.Ro[3 * wpos + 2] = R[2]; }
-                wpos++;
-              }
-              if (MODE == MODE_LJ) {
-                const double s2 = out.lj_sigma2 / (double)r2, s6 = s2 * s2 * s2;
-                e_acc += 4.0 * out.lj_eps * (s6 * s6 - s6);
-              }
+  const T xi = rec.px[s], yi = rec.py[s], zi = rec.pz[s];
+  const uint32_t io = rec.pidx[s];
+  int ci[3];
+  long long wi[3];
+  cell_of(g, xi, yi, zi, ci, wi);
+  uint32_t cnt = 0;
+  long long wpos = 0;
+  if (MODE == MODE_FILL) wpos = (long long)out.first[io] - 1;
+  for (int dz = -g.nxyz[2]; dz <= g.nxyz[2]; dz++) {
+    int cz; long long sz = 0;
+    { long long v = (long long)ci[2] + dz;
+      if (g.pbc[2]) wrap0(v, g.nc[2], cz, sz); else { if (v < 0 || v >= g.nc[2]) continue; cz = (int)v; } }
+    for (int dy = -g.nxyz[1]; dy <= g.nxyz[1]; dy++) {
+      int cy; long long sy = 0;
+      { long long v = (long long)ci[1] + dy;
+        if (g.pbc[1]) wrap0(v, g.nc[1], cy, sy); else { if (v < 0 || v >= g.nc[1]) continue; cy = (int)v; } }
+      for (int dx = -g.nxyz[0]; dx <= g.nxyz[0]; dx++) {
+        int cx; long long sx = 0;
+        { long long v = (long long)ci[0] + dx;
+          if (g.pbc[0]) wrap0(v, g.nc[0], cx, sx); else { if (v < 0 || v >= g.nc[0]) continue; cx = (int)v; } }
+        const long long cl = (long long)cx + (long long)g.nc[0] * ((long long)cy + (long long)g.nc[1] * cz);
+        const long long b0 = (long long)co[cl] - 1, b1 = (long long)co[cl + 1] - 1;
+        const bool zero_shift = (sx == 0 && sy == 0 && sz == 0);
+        for (long long t = b0; t < b1; t++) {
+          const uint32_t jo = rec.pidx[t];
+          if (jo == io && zero_shift) continue;  // _is_self_interaction, src/gpu_kernels.jl:30-33
+          const T xj = rec.px[t], yj = rec.py[t], zj = rec.pz[t];
+          long long wj[3];
+          const uint32_t pwj = rec.pw[t];
+          if (pwj & WIND_OVERFLOW) { int cj[3]; cell_of(g, xj, yj, zj, cj, wj); } else unpack_wind(pwj, wj);
+          const long long S[3] = {sx + wi[0] - wj[0], sy + wi[1] - wj[1], sz + wi[2] - wj[2]};
+          T R[3];
+          const T r2 = pair_r2(g, xi, yi, zi, xj, yj, zj, S, R);
+          if (r2 < g.cutoff_sq) {
+            if (MODE == MODE_COUNT) cnt++;
+            if (MODE == MODE_FILL) {
+              out.io[wpos] = (TI)io + 1;
+              out.jo[wpos] = (TI)jo + 1;
+              out.So[3 * wpos] = (TI)S[0];
+              out.So[3 * wpos + 1] = (TI)S[1];
+              out.So[3 * wpos + 2] = (TI)S[2];
+              if (out.Ro) { out.Ro[3 * wpos] = R[0]; out.Ro[3 * wpos + 1] = R[1]; out.Ro[3 * wpos + 2] = R[2]; }
+              wpos++;
+            }
+            if (MODE == MODE_LJ) {
+              const double s2 = out.lj_sigma2 / (double)r2, s6 = s2 * s2 * s2;
+              e_acc += 4.0 * out.lj_eps * (s6 * s6 - s6);
             }
           }
         }
       }
     }
-    if (MODE == MODE_COUNT) out.counts[io] = cnt;
   }
+  if (MODE == MODE_COUNT) out.counts[io] = cnt;
+  return e_acc;
+}
+
+template <class T, class TI, int MODE>
+__global__ void __launch_bounds__(128) k_traverse_generic(Records<T> rec, const TI* __restrict__ co, long long n, Geo<T> g, Sinks<T, TI> out) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  double e_acc = 0.0;
+  if (s < n) e_acc = generic_atom<T, TI, MODE>(s, rec, co, g, out);
   if (MODE == MODE_LJ) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e_acc += __shfl_xor_sync(FULL, e_acc, o);

@@ -162,8 +162,9 @@ template <class T, class TI, int MODE>
 int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, const Geo<T>& g, const Sinks<T, TI>& sk, cudaStream_t st) {
   if (N <= 0) return NL_OK;
   Records<T> rec = records_of<T>(w);
-  if (tiled_applicable<T>(p, g)) {
-    int rc = tiled_traverse<T, TI, MODE>(p, N, (const TI*)co, rec, g, sk, w.tiled, st);
+  TileShape ts;
+  if (tiled_applicable<T>(p, g, N, ts)) {
+    int rc = tiled_traverse<T, TI, MODE>(p, N, (const TI*)co, rec, g, sk, ts, w.tiled, st);
     if (rc != NL_OK) return rc;
   } else {
     k_traverse_generic<T, TI, MODE><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(rec, (const TI*)co, N, g, sk);

@@ -211,3 +211,27 @@ def test_overflow_and_errors(nl):
         nl.build_cell_list(torch.from_numpy(X).cuda(), 1e-4, C * 1000, (True, True, True))  # prod(ncells) > typemax(Int32)
     with pytest.raises(ValueError):
         nl.build_cell_list(torch.zeros((4, 2), dtype=torch.float64, device="cuda"), 1.0, C, (True, True, True))
+
+
+def test_nonuniform_density(nl):
+    # a dense blob inside a dilute box: tiles over the blob exceed the shared-memory staging capacity and
+    # must take the generic per-atom route inside the tiled kernel
+    rng = np.random.Generator(np.random.PCG64(91))
+    L = 60.0
+    C = np.eye(3) * L
+    bg = rng.random((3000, 3)) * L
+    blob = 30.0 + rng.normal(size=(6000, 3)) * 1.5
+    X = np.concatenate([bg, blob])
+    for dtype in (np.float64, np.float32):
+        check_case(nl, X.astype(dtype), 5.0, C.astype(dtype), (True, True, False), dtype, msg="blob")
+
+
+@pytest.mark.parametrize("dtype,int_type", [(np.float64, np.int32), (np.float32, np.int64)])
+def test_100k_mixed_pbc_triclinic(nl, dtype, int_type):
+    # BASELINE config 3 scaled down: triclinic cell, pbc (T,T,F), rc = 5, 100k atoms
+    s = (1e5 / 0.05 / 720.0) ** (1.0 / 3.0)
+    cell = s * U.TRICLINIC
+    X = U.rand_in_cell(100000, cell, seed=3, dtype=dtype)
+    clist, pl, orc = check_case(nl, X, 5.0, cell.astype(dtype), (True, True, False), dtype, int_type, msg="C3/10")
+    Xd = U.displace_by_lattice(X, cell, (True, True, False))
+    check_case(nl, Xd, 5.0, cell.astype(dtype), (True, True, False), dtype, int_type, msg="C3/10 displaced")
