@@ -15,6 +15,8 @@
 #pragma once
 #include "../../include/nlcuda.h"
 #include "nl_scan_sort.cuh"
+#include <cmath>
+
 #include "nl_traverse.cuh"
 
 namespace nl {
@@ -41,9 +43,8 @@ template <class T, class TI> struct TiledArgs {
 };
 
 // Picks the largest tile whose expected staged population fits the shared-memory capacity.
-template <class T> inline bool pick_tile(const Geo<T>& g, long long n, TileShape& best) {
+template <class T> inline bool pick_tile(const Geo<T>& g, long long n, int cap, TileShape& best) {
   const double dens = (double)n / (double)g.nct;
-  const int cap = tile_cap<T>();
   long long best_home = 0, best_staged = 0;
   for (int tz = 1; tz <= TILE_MAXT; tz++)
     for (int ty = 1; ty <= TILE_MAXT; ty++)
@@ -51,7 +52,8 @@ template <class T> inline bool pick_tile(const Geo<T>& g, long long n, TileShape
         int hx = tx < g.nc[0] ? tx : g.nc[0], hy = ty < g.nc[1] ? ty : g.nc[1], hz = tz < g.nc[2] ? tz : g.nc[2];
         if (hx != tx || hy != ty || hz != tz) continue;
         long long home = (long long)tx * ty * tz, staged = (long long)(tx + 2) * (ty + 2) * (tz + 2);
-        if ((double)staged * dens > 0.80 * cap) continue;
+        const double expect = (double)staged * dens;
+        if (expect + 6.0 * sqrt(expect) + 8.0 > (double)cap) continue;  // mean + 6 sigma (Poisson) must fit
         if (home > best_home || (home == best_home && staged < best_staged)) {
           best_home = home; best_staged = staged; best = {tx, ty, tz};
         }
@@ -59,11 +61,15 @@ template <class T> inline bool pick_tile(const Geo<T>& g, long long n, TileShape
   return best_home > 0;
 }
 
-inline size_t tiled_scratch_bytes(const nl_params*, int64_t) { return 256; }
+// hit masks (8 words per atom) + one flag byte per cell
+inline size_t tiled_scratch_bytes(const nl_params* p, int64_t n) {
+  const size_t nct = (size_t)p->ncells[0] * p->ncells[1] * p->ncells[2];
+  return 512 + (((size_t)(n > 0 ? n : 1) * 32 + 255) & ~(size_t)255) + nct;
+}
 
-template <class T> inline bool tiled_applicable(const nl_params* p, const Geo<T>& g, long long n, TileShape& ts) {
+template <class T> inline bool tiled_applicable(const nl_params* p, const Geo<T>& g, long long n, int cap, TileShape& ts) {
   if (p->nxyz[0] != 1 || p->nxyz[1] != 1 || p->nxyz[2] != 1) return false;
-  return pick_tile<T>(g, n, ts);
+  return pick_tile<T>(g, n, cap, ts);
 }
 
 // 0-based floor-div / mod of a virtual cell coordinate; returns false for a cell beyond an open boundary.

@@ -7,6 +7,7 @@
 #include "nl_scan_sort.cuh"
 #include "nl_traverse.cuh"
 #include "nl_tiled.cuh"
+#include "nl_mask.cuh"
 
 namespace {
 
@@ -158,13 +159,82 @@ template <class T> Records<T> records_of(const PairWs& w) {
   return r;
 }
 
+// Which traversal serves this problem.  A pure function of (params, N): nl_count_pairs and
+// nl_fill_pairs must reach the same verdict.
+enum { PATH_GENERIC = 0, PATH_TILED = 1, PATH_MASK = 2 };
+template <class T> struct Plan {
+  int path;
+  TileShape ts_exact, ts_count, ts_fill;
+  MaskThresholds th;
+};
+template <class T> Plan<T> make_plan(const nl_params* p, const Geo<T>& g, int64_t N) {
+  Plan<T> pl;
+  pl.path = PATH_GENERIC;
+  pl.th = MaskThresholds{0.f, 0.f, 0.f, 0};
+  if (N <= 0) return pl;
+  if (!tiled_applicable<T>(p, g, N, tile_cap<T>(), pl.ts_exact)) return pl;
+  pl.path = PATH_TILED;
+  const double dens = (double)N / (double)g.nct;
+  if (27.0 * dens > 200.0) return pl;  // candidate lists would overflow the 256-bit masks too often
+  if (!pick_tile<T>(g, N, CNT_CAP, pl.ts_count) || !pick_tile<T>(g, N, fill_cap<T>(), pl.ts_fill)) return pl;
+  if (sizeof(T) == 8) {
+    pl.th = mask_thresholds(p->cell, p->ncells, pl.ts_count, (double)g.cutoff_sq);
+    if (!pl.th.ok) return pl;
+  }
+  pl.path = PATH_MASK;
+  return pl;
+}
+
+template <class F> int set_smem_once(F* fn, int bytes, bool& done) {
+  if (!done) {
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return cuda_fail(e);
+    done = true;
+  }
+  return NL_OK;
+}
+
+struct TiledScratch { uint32_t* masks; uint8_t* cellflag; };
+TiledScratch tiled_scratch(void* base, int64_t N) {
+  TiledScratch t;
+  t.masks = (uint32_t*)((char*)base + 256);
+  t.cellflag = (uint8_t*)((char*)base + 256 + al256((size_t)(N > 0 ? N : 1) * 32));
+  return t;
+}
+
+// MODE_COUNT with want_mask (materialisation) or without (lazy count), MODE_FILL, MODE_LJ.
 template <class T, class TI, int MODE>
-int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, const Geo<T>& g, const Sinks<T, TI>& sk, cudaStream_t st) {
+int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, const Geo<T>& g, const Sinks<T, TI>& sk, bool want_mask,
+             cudaStream_t st) {
   if (N <= 0) return NL_OK;
   Records<T> rec = records_of<T>(w);
-  TileShape ts;
-  if (tiled_applicable<T>(p, g, N, ts)) {
-    int rc = tiled_traverse<T, TI, MODE>(p, N, (const TI*)co, rec, g, sk, ts, w.tiled, st);
+  const Plan<T> pl = make_plan<T>(p, g, N);
+  if (pl.path == PATH_MASK && MODE != MODE_LJ) {
+    TiledScratch tsx = tiled_scratch(w.tiled, N);
+    MaskArgs<T, TI> a;
+    mask_args<T, TI>(a, N, (const TI*)co, rec, g, sk, MODE == MODE_FILL ? pl.ts_fill : pl.ts_count, tsx.masks);
+    a.cellflag = tsx.cellflag;
+    a.lo = pl.th.lo; a.hi = pl.th.hi; a.dguard = pl.th.dguard;
+    const unsigned nblk = (unsigned)((long long)a.ntx * a.nty * a.ntz);
+    if (MODE == MODE_FILL) {
+      static bool done = false;
+      int rc = set_smem_once(k_fill_mask<T, TI>, FILL_SMEM_BYTES, done);
+      if (rc) return rc;
+      k_fill_mask<T, TI><<<nblk, TILE_NT, FILL_SMEM_BYTES, st>>>(a);
+    } else if (want_mask) {
+      static bool done = false;
+      int rc = set_smem_once(k_count_mask<T, TI, true>, CNT_SMEM_BYTES, done);
+      if (rc) return rc;
+      k_count_mask<T, TI, true><<<nblk, TILE_NT, CNT_SMEM_BYTES, st>>>(a);
+    } else {
+      static bool done = false;
+      int rc = set_smem_once(k_count_mask<T, TI, false>, CNT_SMEM_BYTES, done);
+      if (rc) return rc;
+      k_count_mask<T, TI, false><<<nblk, TILE_NT, CNT_SMEM_BYTES, st>>>(a);
+    }
+    NL_LAUNCHED(1);
+  } else if (pl.path != PATH_GENERIC) {
+    int rc = tiled_traverse<T, TI, MODE>(p, N, (const TI*)co, rec, g, sk, pl.ts_exact, w.tiled, st);
     if (rc != NL_OK) return rc;
   } else {
     k_traverse_generic<T, TI, MODE><<<(unsigned)((N + 127) / 128), 128, 0, st>>>(rec, (const TI*)co, N, g, sk);
@@ -185,7 +255,7 @@ int count_pairs_impl(const nl_params* p, const void* Xs, int64_t N, const void* 
     if (rc) return rc;
     Sinks<T, TI> sk = {};
     sk.counts = w.counts;
-    rc = traverse<T, TI, MODE_COUNT>(p, N, co, w, g, sk, st);
+    rc = traverse<T, TI, MODE_COUNT>(p, N, co, w, g, sk, true, st);
     if (rc) return rc;
     exclusive_scan<uint32_t, unsigned long long, TI>(w.counts, N, (TI*)first, 1ull, true, w.tsum, w.total, st);
     NL_LAUNCH_CHECK();
@@ -208,7 +278,7 @@ int fill_pairs_impl(const nl_params* p, int64_t N, const void* co, const void* f
   Sinks<T, TI> sk = {};
   sk.first = (const TI*)first;
   sk.io = (TI*)io; sk.jo = (TI*)jo; sk.So = (TI*)So; sk.Ro = (T*)Ro;
-  return traverse<T, TI, MODE_FILL>(p, N, co, w, g, sk, st);
+  return traverse<T, TI, MODE_FILL>(p, N, co, w, g, sk, true, st);
 }
 
 template <class TI> __global__ void k_counts_to_ti(const uint32_t* __restrict__ c, long long n, TI* __restrict__ out) {
@@ -226,7 +296,7 @@ int lazy_count_impl(const nl_params* p, const void* Xs, int64_t N, const void* p
   if (rc) return rc;
   Sinks<T, TI> sk = {};
   sk.counts = w.counts;
-  rc = traverse<T, TI, MODE_COUNT>(p, N, co, w, g, sk, st);
+  rc = traverse<T, TI, MODE_COUNT>(p, N, co, w, g, sk, false, st);
   if (rc) return rc;
   k_counts_to_ti<TI><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(w.counts, N, (TI*)counts_out);
   NL_LAUNCHED(1);
@@ -247,7 +317,7 @@ int lazy_lj_impl(const nl_params* p, const void* Xs, int64_t N, const void* perm
   sk.energy = e_out;
   sk.lj_eps = eps;
   sk.lj_sigma2 = sigma * sigma;
-  return traverse<T, TI, MODE_LJ>(p, N, co, w, g, sk, st);
+  return traverse<T, TI, MODE_LJ>(p, N, co, w, g, sk, false, st);
 }
 
 #define NL_DISPATCH(p, FN, ...)                                                              \
