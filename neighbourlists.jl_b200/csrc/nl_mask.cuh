@@ -16,9 +16,11 @@
 // bounded by delta = 2^-22 * D + 1e-7 (D = tile extent; see mask_thresholds()).  A pair is a sure hit if
 // r2~ < rc2 - E, a sure miss if r2~ > rc2 + E, and only pairs inside the band (about 1 in 10^5) are
 // re-evaluated with the exact Float64 contract (exact_pair_hit).  Slots whose assumptions fail
-// (|x| > 1e5, outside the tile extent on an open axis, winding overflow) are staged as NaN, which
-// lands every comparison in the band.  The decisions are therefore identical to the contract's.
-// Float32 inputs evaluate the contract directly (Float32 is already the native fast path).
+// (|x| > 1e5, outside the tile extent on an open axis, winding overflow) are flagged and always take
+// the exact path.  The decisions are therefore identical to the contract's.  The arithmetic runs on
+// Blackwell's packed Float32 pipe (FFMA2 / FADD2: two home atoms per instruction).
+// Float32 inputs evaluate the contract itself (packed, unfused) whenever the home atoms of a group
+// share one winding number, and fall back to exact_pair_hit otherwise.
 #pragma once
 #include <cmath>
 
@@ -29,9 +31,8 @@ namespace nl {
 constexpr int MASK_WORDS = 8;                  // 256 candidates
 constexpr int MASK_MAXCAND = 32 * MASK_WORDS;
 constexpr int CNT_SMEM_BYTES = 48 * 1024;      // count pass: 16 B per staged slot
-constexpr int CNT_CAP = (CNT_SMEM_BYTES - 3 * TILE_VPAD * 4 - (TILE_NT / 32) * 32 * MASK_WORDS * 4) / 16 / 8 * 8;
 
-struct MaskThresholds { float lo, hi, dguard; int ok; };
+struct MaskThresholds { float mid, hw, dguard; int ok; };
 
 // Error budget of the Float32 pre-filter (derivation in the header comment / DESIGN.md):
 //   |q - q*| <= 2^-24 D + 2e-8 per coordinate (q* = exact image position), same for the home atom,
@@ -49,10 +50,11 @@ inline MaskThresholds mask_thresholds(const double cell[9], const int nc[3], con
   const double rc = std::sqrt(cutoff_sq);
   const double delta = std::ldexp(D, -22) + 1e-7;
   const double E = 2.0 * (2.0 * std::sqrt(3.0) * rc * delta + 3.0 * delta * delta + std::ldexp(cutoff_sq, -21));
-  m.lo = std::nextafterf((float)(cutoff_sq - E), -INFINITY);
-  m.hi = std::nextafterf((float)(cutoff_sq + E), INFINITY);
+  // the kernel evaluates t = r2~ - mid in one FMA chain: sure hit <=> t < -hw, sure miss <=> t > hw
+  m.mid = (float)cutoff_sq;
+  m.hw = std::nextafterf((float)(E + std::fabs((double)m.mid - cutoff_sq)), INFINITY);
   m.dguard = (float)D;
-  m.ok = (E < 0.01 * cutoff_sq && std::isfinite(D) && m.lo > 0.0f) ? 1 : 0;
+  m.ok = (E < 0.01 * cutoff_sq && std::isfinite(D) && std::isfinite(E)) ? 1 : 0;
   return m;
 }
 
@@ -65,7 +67,7 @@ template <class T, class TI> struct MaskArgs {
   uint32_t* masks;    // n * MASK_WORDS, sorted order
   uint8_t* cellflag;  // per cell: 1 if the count pass stored masks for its atoms
   int tx, ty, tz, ntx, nty, ntz;
-  float lo, hi, dguard;
+  float mid, hw, dguard;
 };
 
 __device__ __forceinline__ int pack_shift(int s0, int s1, int s2) { return (s0 + 1) | ((s1 + 1) << 2) | ((s2 + 1) << 4); }
@@ -123,68 +125,119 @@ __device__ __forceinline__ int find_vcell(const int* vstart, int NV, int sl) {
   return lo;
 }
 
+// Per-warp candidate tables of one home cell: flat candidate index -> staged slot / virtual cell.
+struct CellTables {
+  uint16_t* cslot;  // [MASK_MAXCAND]
+  uint8_t* cv;      // [MASK_MAXCAND]
+};
+constexpr int CELLTAB_BYTES = MASK_MAXCAND * 3;
+
+// Builds the tables for home cell (lx, ly, lz) of the tile; returns the number of candidates
+// (tables are valid only if it is <= MASK_MAXCAND).  Lane c < 27 owns neighbour cell
+// c = (dz+1)*9 + (dy+1)*3 + (dx+1); flat order = cell order, then sorted order inside the cell.
+__device__ __forceinline__ int build_cell_tables(const int* vstart, int VX, int VY, int lx, int ly, int lz, int lane, const CellTables& t) {
+  int v = 0, st = 0, cn = 0;
+  if (lane < 27) {
+    v = ((lz + lane / 9) * VY + (ly + (lane / 3) % 3)) * VX + (lx + lane % 3);
+    st = vstart[v];
+    cn = vstart[v + 1] - st;
+  }
+  const int incl = warp_incl_scan(cn, lane);
+  const int ncand = __shfl_sync(FULL, incl, 31);
+  if (ncand <= MASK_MAXCAND) {
+    const int pre = incl - cn;
+    const int mx = __reduce_max_sync(FULL, cn);
+    for (int j = 0; j < mx; j++)
+      if (j < cn) { t.cslot[pre + j] = (uint16_t)(st + j); t.cv[pre + j] = (uint8_t)v; }
+  }
+  __syncwarp();
+  return ncand;
+}
+
+__device__ __forceinline__ long long cell_linear(const int nc[3], int cx, int cy, int cz) {
+  return (long long)cx + (long long)nc[0] * ((long long)cy + (long long)nc[1] * cz);
+}
+
 // ------------------------------------------------------------------------------------------------
-// Counting pass.  WANT_MASK: also store the hit masks for the fill pass.
+// Counting pass.  WANT_MASK: also store the hit masks (and per-cell flags) for the fill pass.
+//
+// Shared memory: tile tables | per-warp {cell tables, chunk-major mask words, home-atom pair buffer} |
+// float4 per staged slot: Float64 -> (q.xyz = Float32 image-relative position, w = 1 if the slot needs
+// the exact path); Float32 -> (absolute x, y, z, packed winding).
+constexpr int CNT_WARP_BYTES = CELLTAB_BYTES + MASK_WORDS * 34 * 4 + 16 * 32;
+constexpr int CNT_FIXED_BYTES = 3 * TILE_VPAD * 4 + 64 * 4 + (TILE_NT / 32) * CNT_WARP_BYTES;
+constexpr int CNT_CAP2 = (CNT_SMEM_BYTES - CNT_FIXED_BYTES) / 16 / 8 * 8;
+static_assert(CNT_WARP_BYTES % 16 == 0 && CNT_FIXED_BYTES % 16 == 0, "alignment");
+
+constexpr float CAND_FAR = 1.0e18f;  // finite "nowhere": squares stay finite in Float32
+
 template <class T, class TI, bool WANT_MASK>
 __global__ void __launch_bounds__(TILE_NT, 4) k_count_mask(const MaskArgs<T, TI> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* vstart = (int*)smem_raw;
   int* vgs = vstart + TILE_VPAD;
   int* vsh = vgs + TILE_VPAD;
-  uint32_t* mk_all = (uint32_t*)(vsh + TILE_VPAD);                   // [8 warps][32 atoms][MASK_WORDS]
-  float4* sq = (float4*)(mk_all + (TILE_NT / 32) * 32 * MASK_WORDS);  // [CNT_CAP]
+  int* hcell = vsh + TILE_VPAD;  // [64] packed (lx, ly, lz) of each home cell
+  unsigned char* wbase = (unsigned char*)(hcell + 64);
+  float4* sq = (float4*)(wbase + (TILE_NT / 32) * CNT_WARP_BYTES);
   __shared__ int scan_sm[33];
   __shared__ int s_next;
 
   const Geo<T>& g = a.g;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  uint32_t* mk = mk_all + wid * 32 * MASK_WORDS;
+  unsigned char* wb = wbase + wid * CNT_WARP_BYTES;
+  CellTables tab;
+  tab.cslot = (uint16_t*)wb;
+  tab.cv = (uint8_t*)(wb + MASK_MAXCAND * 2);
+  uint32_t* mkT = (uint32_t*)(wb + CELLTAB_BYTES);                          // [MASK_WORDS][34]: word kc of home atom aa at kc*34 + aa
+  float* hb = (float*)(wb + CELLTAB_BYTES + MASK_WORDS * 34 * 4);           // [16 pairs][8]: x0 x1 y0 y1 z0 z1 f0 f1
 
   const int b = blockIdx.x;
   const int hx0 = (b % a.ntx) * a.tx, hy0 = ((b / a.ntx) % a.nty) * a.ty, hz0 = (b / (a.ntx * a.nty)) * a.tz;
   const int hxn = min(a.tx, g.nc[0] - hx0), hyn = min(a.ty, g.nc[1] - hy0), hzn = min(a.tz, g.nc[2] - hz0);
   const int VX = hxn + 2, VY = hyn + 2, VZ = hzn + 2, NV = VX * VY * VZ;
   const int total = tile_table<T, TI>(g, a.co, hx0, hy0, hz0, VX, VY, NV, vstart, vgs, vsh, scan_sm);
+  const int nhome = hxn * hyn * hzn;
+  if (tid < nhome) hcell[tid] = (tid % hxn) | (((tid / hxn) % hyn) << 8) | ((tid / (hxn * hyn)) << 16);
   if (tid == 0) s_next = 0;
   __syncthreads();
-  const int nhome = hxn * hyn * hzn;
 
-  if (total > CNT_CAP) {
+  if (total > CNT_CAP2) {
     for (int hc = wid; hc < nhome; hc += TILE_NT / 32) {
-      const int lx = hc % hxn, ly = (hc / hxn) % hyn, lz = hc / (hxn * hyn);
+      const int lx = hcell[hc] & 255, ly = (hcell[hc] >> 8) & 255, lz = hcell[hc] >> 16;
       const int vh = ((lz + 1) * VY + (ly + 1)) * VX + (lx + 1);
       const int nh = vstart[vh + 1] - vstart[vh];
       for (int k = lane; k < nh; k += 32) generic_atom<T, TI, MODE_COUNT>((long long)vgs[vh] + k, a.rec, a.co, g, a.out);
-      if (WANT_MASK && lane == 0) a.cellflag[(long long)(hx0 + lx) + (long long)g.nc[0] * ((hy0 + ly) + (long long)g.nc[1] * (hz0 + lz))] = 0;
+      if (WANT_MASK && lane == 0) a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)] = 0;
     }
     return;
   }
 
   // ---- stage
-  if (sizeof(T) == 8) {
-    // tile origin: the corner of the home block, O = cell' * (h0 / n)
-    double O[3];
+  if constexpr (sizeof(T) == 8) {
+    double O[3];  // tile origin: the corner of the home block, O = cell' * (h0 / n)
     {
       const double f0 = (double)hx0 / g.nc[0], f1 = (double)hy0 / g.nc[1], f2 = (double)hz0 / g.nc[2];
-      for (int k = 0; k < 3; k++) O[k] = (double)g.cell[3 * k] * f0 + (double)g.cell[3 * k + 1] * f1 + (double)g.cell[3 * k + 2] * f2;
+      O[0] = g.cell[0] * f0 + g.cell[1] * f1 + g.cell[2] * f2;
+      O[1] = g.cell[3] * f0 + g.cell[4] * f1 + g.cell[5] * f2;
+      O[2] = g.cell[6] * f0 + g.cell[7] * f1 + g.cell[8] * f2;
     }
-    const float nanf_ = __int_as_float(0x7fc00000);
+    const double dg = (double)a.dguard;
     for (int sl = tid; sl < total; sl += TILE_NT) {
       const int v = find_vcell(vstart, NV, sl);
       const long long src = (long long)vgs[v] + (sl - vstart[v]);
-      const double x = (double)a.rec.px[src], y = (double)a.rec.py[src], z = (double)a.rec.pz[src];
+      const double x = a.rec.px[src], y = a.rec.py[src], z = a.rec.pz[src];
       const uint32_t pw = a.rec.pw[src];
-      long long w[3], s[3];
-      unpack_wind(pw, w);
-      unpack_shift(vsh[v], s);
-      const double m0 = (double)(s[0] - w[0]), m1 = (double)(s[1] - w[1]), m2 = (double)(s[2] - w[2]);
-      const double q0 = (x - O[0]) + (((double)g.cell[0] * m0 + (double)g.cell[1] * m1) + (double)g.cell[2] * m2);
-      const double q1 = (y - O[1]) + (((double)g.cell[3] * m0 + (double)g.cell[4] * m1) + (double)g.cell[5] * m2);
-      const double q2 = (z - O[2]) + (((double)g.cell[6] * m0 + (double)g.cell[7] * m1) + (double)g.cell[8] * m2);
-      const double dg = (double)a.dguard;
+      const int sh = vsh[v];
+      const double m0 = (double)(((sh & 3) - 1) - ((int)(pw & 1023u) - 512));
+      const double m1 = (double)((((sh >> 2) & 3) - 1) - ((int)((pw >> 10) & 1023u) - 512));
+      const double m2 = (double)((((sh >> 4) & 3) - 1) - ((int)((pw >> 20) & 1023u) - 512));
+      const double q0 = (x - O[0]) + ((g.cell[0] * m0 + g.cell[1] * m1) + g.cell[2] * m2);
+      const double q1 = (y - O[1]) + ((g.cell[3] * m0 + g.cell[4] * m1) + g.cell[5] * m2);
+      const double q2 = (z - O[2]) + ((g.cell[6] * m0 + g.cell[7] * m1) + g.cell[8] * m2);
       const bool good = !(pw & WIND_OVERFLOW) && fabs(x) <= 1e5 && fabs(y) <= 1e5 && fabs(z) <= 1e5 && fabs(q0) <= dg && fabs(q1) <= dg &&
-                        fabs(q2) <= dg;
-      sq[sl] = good ? make_float4((float)q0, (float)q1, (float)q2, 0.f) : make_float4(nanf_, nanf_, nanf_, 0.f);
+                        fabs(q2) <= dg;  // false for NaN too
+      sq[sl] = good ? make_float4((float)q0, (float)q1, (float)q2, 0.f) : make_float4(CAND_FAR, CAND_FAR, CAND_FAR, 1.f);
     }
   } else {
     for (int sl = tid; sl < total; sl += TILE_NT) {
@@ -195,112 +248,160 @@ __global__ void __launch_bounds__(TILE_NT, 4) k_count_mask(const MaskArgs<T, TI>
   }
   __syncthreads();
 
-  const float inff_ = __int_as_float(0x7f800000);
+  // Float64 pre-filter constants: t = r2~ - mid; sure hit <=> t < -hw; in the band <=> |t| <= hw
+  const float mid = a.mid, hw = a.hw;
+  const float2 nmid2 = make_float2(-mid, -mid);
+  const float csqf = (float)g.cutoff_sq;
 
   while (true) {
     int hc = 0;
     if (lane == 0) hc = atomicAdd(&s_next, 1);
     hc = __shfl_sync(FULL, hc, 0);
     if (hc >= nhome) break;
-    const int lx = hc % hxn, ly = (hc / hxn) % hyn, lz = hc / (hxn * hyn);
+    const int lx = hcell[hc] & 255, ly = (hcell[hc] >> 8) & 255, lz = hcell[hc] >> 16;
     const int vh = ((lz + 1) * VY + (ly + 1)) * VX + (lx + 1);
     const int hstart = vstart[vh], nh = vstart[vh + 1] - hstart;
     if (nh == 0) continue;
     const long long hg0 = vgs[vh];
-
-    int rstart = 0, rlen = 0;
-    if (lane < 9) {
-      const int vrow = ((lz + lane / 3) * VY + (ly + lane % 3)) * VX + lx;
-      rstart = vstart[vrow];
-      rlen = vstart[vrow + 3] - rstart;
-    }
-    const int rincl = warp_incl_scan(rlen, lane);
-    const int ncand = __shfl_sync(FULL, rincl, 8);
-
-    if (WANT_MASK && lane == 0)
-      a.cellflag[(long long)(hx0 + lx) + (long long)g.nc[0] * ((hy0 + ly) + (long long)g.nc[1] * (hz0 + lz))] = ncand <= MASK_MAXCAND ? 1 : 0;
+    const int ncand = build_cell_tables(vstart, VX, VY, lx, ly, lz, lane, tab);
+    if (WANT_MASK && lane == 0) a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)] = ncand <= MASK_MAXCAND ? 1 : 0;
     if (ncand > MASK_MAXCAND) {  // too many candidates for a 256-bit mask: generic route (the fill pass does the same)
       for (int k = lane; k < nh; k += 32) generic_atom<T, TI, MODE_COUNT>(hg0 + k, a.rec, a.co, g, a.out);
       continue;
     }
     const int nchunk = (ncand + 31) >> 5;
+    int fh;  // flat index of home atom 0 as a candidate (cell 13 of the stencil): used to drop the self pair
+    {
+      int cn = 0;
+      if (lane < 13) {
+        const int v = ((lz + lane / 9) * VY + (ly + (lane / 3) % 3)) * VX + (lx + lane % 3);
+        cn = vstart[v + 1] - vstart[v];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cn += __shfl_xor_sync(FULL, cn, o);
+      fh = cn;
+    }
 
     for (int g0 = 0; g0 < nh; g0 += 32) {
       const int ng = min(32, nh - g0);
+      const int npair = (ng + 1) >> 1;
       __syncwarp();
-      for (int k0 = 0, kc = 0; k0 < ncand; k0 += 32, kc++) {
-        const int f = k0 + lane;
+      // home atoms -> pair-interleaved buffer; group-uniformity of the winding (Float32 path)
+      bool my_bad = false;
+      uint32_t my_w = 0;
+      {
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < ng) p = sq[hstart + g0 + lane];
+        float* d = hb + (lane >> 1) * 8 + (lane & 1);
+        d[0] = p.x; d[2] = p.y; d[4] = p.z;
+        if constexpr (sizeof(T) == 8) my_bad = (lane < ng) && p.w != 0.f; else my_w = __float_as_uint(p.w);
+      }
+      bool slow_group = false;   // every pair of this group must take the exact path
+      uint32_t W0 = 0;
+      if constexpr (sizeof(T) == 4) {
+        W0 = __shfl_sync(FULL, my_w, 0);
+        slow_group = __any_sync(FULL, lane < ng && (my_w != W0 || (my_w & WIND_OVERFLOW)));
+      }
+      const unsigned hbad = (sizeof(T) == 8) ? __ballot_sync(FULL, my_bad) : 0u;
+      __syncwarp();
+
+      for (int kc = 0; kc < nchunk; kc++) {
+        const int f = kc * 32 + lane;
         const bool valid = f < ncand;
-        int rr = 0;
-#pragma unroll
-        for (int r = 0; r < 8; r++) rr += (f >= __shfl_sync(FULL, rincl, r)) ? 1 : 0;
-        const int r_incl = __shfl_sync(FULL, rincl, rr);
-        const int r_len = __shfl_sync(FULL, rlen, rr);
-        const int r_start = __shfl_sync(FULL, rstart, rr);
-        int slot = -1, gj = 0, shp = 0;
-        float qx = inff_, qy = inff_, qz = inff_;  // +inf: an invalid lane is a sure miss
+        int gj = 0, shp = 0;
+        float qx = CAND_FAR, qy = CAND_FAR, qz = CAND_FAR;
         float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f;
-        uint32_t wj = 0;
+        bool cand_bad = false;
         if (valid) {
-          slot = r_start + (f - (r_incl - r_len));
-          const int vrow = ((lz + rr / 3) * VY + (ly + rr % 3)) * VX + lx;
-          const int v = vrow + (slot >= vstart[vrow + 1] ? 1 : 0) + (slot >= vstart[vrow + 2] ? 1 : 0);
+          const int slot = tab.cslot[f], v = tab.cv[f];
           gj = vgs[v] + (slot - vstart[v]);
           shp = vsh[v];
           const float4 q = sq[slot];
           qx = q.x; qy = q.y; qz = q.z;
-          if constexpr (sizeof(T) == 4) {
-            wj = __float_as_uint(q.w);
-            long long s[3];
-            unpack_shift(shp, s);
-            mtv(g.cell, (float)s[0], (float)s[1], (float)s[2], cs0, cs1, cs2);
-          }
-        }
-        const int self_aa = slot - (hstart + g0);  // the home atom this lane's candidate IS (zero shift), if in [0, ng)
-        uint32_t umask = 0;                        // home atoms whose pair with this candidate needs the exact test
-
-#pragma unroll 4
-        for (int aa = 0; aa < ng; aa++) {
-          const float4 p = sq[hstart + g0 + aa];
-          bool sure, unsure;
-          if (sizeof(T) == 8) {
-            const float dx = qx - p.x, dy = qy - p.y, dz = qz - p.z;
-            const float r2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-            const bool ge = !(r2 < a.lo);          // true for r2 >= lo and for NaN
-            unsure = ge && !(r2 > a.hi);
-            sure = !ge && (aa != self_aa);
+          if constexpr (sizeof(T) == 8) {
+            cand_bad = q.w != 0.f;
           } else {
-            const uint32_t wi = __float_as_uint(p.w);
-            const float R0 = __fadd_rn(__fsub_rn(qx, p.x), cs0), R1 = __fadd_rn(__fsub_rn(qy, p.y), cs1), R2 = __fadd_rn(__fsub_rn(qz, p.z), cs2);
-            const float r2 = __fadd_rn(__fadd_rn(__fmul_rn(R0, R0), __fmul_rn(R1, R1)), __fmul_rn(R2, R2));
-            const bool same_w = (wi == wj) && !(wi & WIND_OVERFLOW);
-            unsure = valid && !same_w;
-            sure = same_w && (r2 < (float)g.cutoff_sq) && (aa != self_aa);
+            const uint32_t wj = __float_as_uint(q.w);
+            cand_bad = (wj & WIND_OVERFLOW) != 0;
+            long long s[3], w0[3], w1[3];
+            unpack_shift(shp, s);
+            unpack_wind(W0, w0);
+            unpack_wind(wj, w1);
+            mtv(g.cell, (T)(s[0] + w0[0] - w1[0]), (T)(s[1] + w0[1] - w1[1]), (T)(s[2] + w0[2] - w1[2]), cs0, cs1, cs2);
           }
-          if (unsure) umask |= 1u << aa;
-          const unsigned bal = __ballot_sync(FULL, sure);
-          if (lane == 0) mk[aa * MASK_WORDS + kc] = bal;
         }
-        // deferred exact evaluations (rare): OR the confirmed hits into the masks
-        if (__any_sync(FULL, umask != 0)) {
-          __syncwarp();
-          while (umask) {
-            const int aa = __ffs(umask) - 1;
-            umask &= umask - 1;
-            if (valid && aa != self_aa && exact_pair_hit<T>(g, a.rec, hg0 + g0 + aa, gj, shp)) atomicOr(&mk[aa * MASK_WORDS + kc], 1u << lane);
+        bool band = false;  // some pair of this lane fell in the uncertainty band
+        uint32_t* mrow = mkT + kc * 34;
+
+        if constexpr (sizeof(T) == 8) {
+          const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy), nqz = make_float2(-qz, -qz);
+#pragma unroll 2
+          for (int pr = 0; pr < npair; pr++) {
+            const float4 A = *(const float4*)(hb + pr * 8);
+            const float2 Z = *(const float2*)(hb + pr * 8 + 4);
+            const float2 dx = __fadd2_rn(make_float2(A.x, A.y), nqx);
+            const float2 dy = __fadd2_rn(make_float2(A.z, A.w), nqy);
+            const float2 dz = __fadd2_rn(Z, nqz);
+            float2 t = __ffma2_rn(dx, dx, nmid2);
+            t = __ffma2_rn(dy, dy, t);
+            t = __ffma2_rn(dz, dz, t);
+            band = band || (fabsf(t.x) <= hw) || (fabsf(t.y) <= hw);
+            const unsigned b0 = __ballot_sync(FULL, t.x < -hw);
+            const unsigned b1 = __ballot_sync(FULL, t.y < -hw);
+            *(uint2*)(mrow + 2 * pr) = make_uint2(b0, b1);  // every lane stores the same words: no branch
           }
+        } else {
+          const float2 qx2 = make_float2(qx, qx), qy2 = make_float2(qy, qy), qz2 = make_float2(qz, qz);
+          const float2 c0 = make_float2(cs0, cs0), c1 = make_float2(cs1, cs1), c2 = make_float2(cs2, cs2);
+#pragma unroll 2
+          for (int pr = 0; pr < npair; pr++) {
+            const float4 A = *(const float4*)(hb + pr * 8);
+            const float2 Z = *(const float2*)(hb + pr * 8 + 4);
+            // contract: R = (xj - xi) + cs ; r2 = (R0 R0 + R1 R1) + R2 R2, no fused operations
+            const float2 R0 = __fadd2_rn(__fadd2_rn(qx2, make_float2(-A.x, -A.y)), c0);
+            const float2 R1 = __fadd2_rn(__fadd2_rn(qy2, make_float2(-A.z, -A.w)), c1);
+            const float2 R2 = __fadd2_rn(__fadd2_rn(qz2, make_float2(-Z.x, -Z.y)), c2);
+            const float2 r2 = __fadd2_rn(__fadd2_rn(__fmul2_rn(R0, R0), __fmul2_rn(R1, R1)), __fmul2_rn(R2, R2));
+            const unsigned b0 = __ballot_sync(FULL, valid && r2.x < csqf);
+            const unsigned b1 = __ballot_sync(FULL, valid && r2.y < csqf);
+            *(uint2*)(mrow + 2 * pr) = make_uint2(b0, b1);
+          }
+        }
+        __syncwarp();
+        // ---- rare: redo this chunk with the exact contract wherever the fast loop cannot be trusted
+        if (__any_sync(FULL, band || cand_bad) || hbad != 0 || slow_group) {
+          for (int aa = 0; aa < ng; aa++) {
+            bool hit;
+            if constexpr (sizeof(T) == 8) {
+              const float px = hb[(aa >> 1) * 8 + (aa & 1)], py = hb[(aa >> 1) * 8 + 2 + (aa & 1)], pz = hb[(aa >> 1) * 8 + 4 + (aa & 1)];
+              const float dx = px - qx, dy = py - qy, dz = pz - qz;
+              const float t = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, -mid)));
+              hit = t < -hw;
+              if (valid && (cand_bad || ((hbad >> aa) & 1u) || fabsf(t) <= hw)) hit = exact_pair_hit<T>(g, a.rec, hg0 + g0 + aa, gj, shp);
+            } else {
+              hit = valid && exact_pair_hit<T>(g, a.rec, hg0 + g0 + aa, gj, shp);
+            }
+            const unsigned bal = __ballot_sync(FULL, hit);
+            if (lane == 0) mrow[aa] = bal;
+          }
+          __syncwarp();
+        }
+        // drop the self pair (same atom, zero shift): flat index fh + g0 + aa of home atom aa
+        if (lane < ng) {
+          const int fs = fh + g0 + lane;
+          if ((fs >> 5) == kc) mrow[lane] &= ~(1u << (fs & 31));
         }
       }
       __syncwarp();
-      // per-atom counts from the masks; masks to global
+      // per-atom counts from the masks; masks to global (atom-major, MASK_WORDS per atom)
       if (lane < ng) {
         uint32_t c = 0;
-        for (int k = 0; k < nchunk; k++) c += __popc(mk[lane * MASK_WORDS + k]);
+        for (int k = 0; k < nchunk; k++) c += __popc(mkT[k * 34 + lane]);
         a.out.counts[a.rec.pidx[hg0 + g0 + lane]] = c;
       }
       if (WANT_MASK) {
         uint32_t* dst = a.masks + (hg0 + g0) * MASK_WORDS;
-        for (int w = lane; w < ng * MASK_WORDS; w += 32) dst[w] = mk[w];
+        for (int w = lane; w < ng * MASK_WORDS; w += 32) dst[w] = (w & 7) < nchunk ? mkT[(w & 7) * 34 + (w >> 3)] : 0u;
       }
     }
   }
@@ -308,8 +409,13 @@ __global__ void __launch_bounds__(TILE_NT, 4) k_count_mask(const MaskArgs<T, TI>
 
 // ------------------------------------------------------------------------------------------------
 // Fill pass: expands the masks.  Stages full records (positions in T, original index, winding).
-constexpr int FILL_SMEM_BYTES = 56 * 1024;
-template <class T> __host__ __device__ constexpr int fill_cap() { return (FILL_SMEM_BYTES - 3 * TILE_VPAD * 4) / TileRecBytes<T>::value / 8 * 8; }
+// Four atoms' masks are compacted at once (lane = 8*atom + word); each atom's row is then produced
+// by the whole warp, transposed through shared memory and written with contiguous full-sector stores.
+constexpr int FILL_SMEM_BYTES = 72 * 1024;
+constexpr int FILL_WARP_BYTES = CELLTAB_BYTES + 4 * MASK_MAXCAND + 32 * 3 * 4 + 32 * 3 * 8;  // tables | 4 hit lists | S stage | R stage
+constexpr int FILL_FIXED_BYTES = 3 * TILE_VPAD * 4 + 64 * 4 + (TILE_NT / 32) * FILL_WARP_BYTES;
+template <class T> __host__ __device__ constexpr int fill_cap() { return (FILL_SMEM_BYTES - FILL_FIXED_BYTES) / TileRecBytes<T>::value / 8 * 8; }
+static_assert(FILL_WARP_BYTES % 16 == 0 && FILL_FIXED_BYTES % 16 == 0, "alignment");
 
 template <class T, class TI>
 __global__ void __launch_bounds__(TILE_NT, 3) k_fill_mask(const MaskArgs<T, TI> a) {
@@ -318,33 +424,44 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_fill_mask(const MaskArgs<T, TI> 
   int* vstart = (int*)smem_raw;
   int* vgs = vstart + TILE_VPAD;
   int* vsh = vgs + TILE_VPAD;
-  T* sx = (T*)(vsh + TILE_VPAD);
+  int* hcell = vsh + TILE_VPAD;
+  unsigned char* wbase = (unsigned char*)(hcell + 64);
+  T* sx = (T*)(wbase + (TILE_NT / 32) * FILL_WARP_BYTES);
   T* sy = sx + CAP;
   T* sz = sy + CAP;
   uint32_t* sidx = (uint32_t*)(sz + CAP);
   uint32_t* sw = sidx + CAP;
   __shared__ int scan_sm[33];
   __shared__ int s_next;
-  __shared__ uint32_t s_mk[TILE_NT / 32][32 * MASK_WORDS];
-  __shared__ uint8_t s_list[TILE_NT / 32][MASK_MAXCAND];
 
   const Geo<T>& g = a.g;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const unsigned lt = (1u << lane) - 1u;
+  const int grp = lane >> 3, sub = lane & 7;
+  unsigned char* wb = wbase + wid * FILL_WARP_BYTES;
+  CellTables tab;
+  tab.cslot = (uint16_t*)wb;
+  tab.cv = (uint8_t*)(wb + MASK_MAXCAND * 2);
+  uint8_t* lists = wb + CELLTAB_BYTES;                                        // [4][MASK_MAXCAND]
+  TI* stS = (TI*)nullptr;
+  uint32_t* stS32 = (uint32_t*)(wb + CELLTAB_BYTES + 4 * MASK_MAXCAND);       // [32][3] shifts (as int32)
+  T* stR = (T*)(wb + CELLTAB_BYTES + 4 * MASK_MAXCAND + 32 * 3 * 4);          // [32][3]
+  (void)stS;
 
   const int b = blockIdx.x;
   const int hx0 = (b % a.ntx) * a.tx, hy0 = ((b / a.ntx) % a.nty) * a.ty, hz0 = (b / (a.ntx * a.nty)) * a.tz;
   const int hxn = min(a.tx, g.nc[0] - hx0), hyn = min(a.ty, g.nc[1] - hy0), hzn = min(a.tz, g.nc[2] - hz0);
   const int VX = hxn + 2, VY = hyn + 2, VZ = hzn + 2, NV = VX * VY * VZ;
   const int total = tile_table<T, TI>(g, a.co, hx0, hy0, hz0, VX, VY, NV, vstart, vgs, vsh, scan_sm);
+  const int nhome = hxn * hyn * hzn;
+  if (tid < nhome) hcell[tid] = (tid % hxn) | (((tid / hxn) % hyn) << 8) | ((tid / (hxn * hyn)) << 16);
   if (tid == 0) s_next = 0;
   __syncthreads();
-  const int nhome = hxn * hyn * hzn;
 
   if (total > CAP) {
     // denser than the staging capacity: the generic route needs no masks
     for (int hc = wid; hc < nhome; hc += TILE_NT / 32) {
-      const int vh = ((hc / (hxn * hyn) + 1) * VY + ((hc / hxn) % hyn + 1)) * VX + (hc % hxn + 1);
+      const int lx = hcell[hc] & 255, ly = (hcell[hc] >> 8) & 255, lz = hcell[hc] >> 16;
+      const int vh = ((lz + 1) * VY + (ly + 1)) * VX + (lx + 1);
       const int nh = vstart[vh + 1] - vstart[vh];
       for (int k = lane; k < nh; k += 32) generic_atom<T, TI, MODE_FILL>((long long)vgs[vh] + k, a.rec, a.co, g, a.out);
     }
@@ -366,81 +483,69 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_fill_mask(const MaskArgs<T, TI> 
     if (lane == 0) hc = atomicAdd(&s_next, 1);
     hc = __shfl_sync(FULL, hc, 0);
     if (hc >= nhome) break;
-    const int lx = hc % hxn, ly = (hc / hxn) % hyn, lz = hc / (hxn * hyn);
+    const int lx = hcell[hc] & 255, ly = (hcell[hc] >> 8) & 255, lz = hcell[hc] >> 16;
     const int vh = ((lz + 1) * VY + (ly + 1)) * VX + (lx + 1);
     const int hstart = vstart[vh], nh = vstart[vh + 1] - hstart;
     if (nh == 0) continue;
     const long long hg0 = vgs[vh];
-
-    int rstart = 0, rlen = 0;
-    if (lane < 9) {
-      const int vrow = ((lz + lane / 3) * VY + (ly + lane % 3)) * VX + lx;
-      rstart = vstart[vrow];
-      rlen = vstart[vrow + 3] - rstart;
-    }
-    const int rincl = warp_incl_scan(rlen, lane);
-    const int ncand = __shfl_sync(FULL, rincl, 8);
-    const int have_mask = a.cellflag[(long long)(hx0 + lx) + (long long)g.nc[0] * ((hy0 + ly) + (long long)g.nc[1] * (hz0 + lz))];
-    if (!have_mask) {
+    if (!a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)]) {
       for (int k = lane; k < nh; k += 32) generic_atom<T, TI, MODE_FILL>(hg0 + k, a.rec, a.co, g, a.out);
       continue;
     }
-    const int nchunk = (ncand + 31) >> 5;
+    build_cell_tables(vstart, VX, VY, lx, ly, lz, lane, tab);
 
-    for (int g0 = 0; g0 < nh; g0 += 32) {
-      const int ng = min(32, nh - g0);
-      // masks of the whole group -> shared memory (coalesced), row bases gathered in parallel
-      __syncwarp();
-      {
-        const uint32_t* src = a.masks + (hg0 + g0) * MASK_WORDS;
-        for (int w = lane; w < ng * MASK_WORDS; w += 32) s_mk[wid][w] = src[w];
-      }
+    for (int a0 = 0; a0 < nh; a0 += 4) {
+      // ---- four atoms at once: lane = 8 * atom + mask word
+      const int my_atom = a0 + grp;
+      uint32_t word = 0;
       uint32_t my_io = 0;
       long long my_base = 0;
-      if (lane < ng) {
-        my_io = sidx[hstart + g0 + lane];
+      if (my_atom < nh) {
+        word = a.masks[(hg0 + my_atom) * MASK_WORDS + sub];
+        my_io = sidx[hstart + my_atom];
         my_base = (long long)a.out.first[my_io] - 1;
+      }
+      const int pc = __popc(word);
+      int incl = pc;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o, 8);
+        if (sub >= o) incl += t;
+      }
+      const int my_nhit = __shfl_sync(FULL, incl, 7, 8);
+      __syncwarp();
+      {
+        uint8_t* L = lists + grp * MASK_MAXCAND + (incl - pc);
+        const int fb = sub * 32;
+        while (word) {
+          const int bit = __ffs(word) - 1;
+          word &= word - 1;
+          *L++ = (uint8_t)(fb + bit);
+        }
       }
       __syncwarp();
 
-      for (int aa = 0; aa < ng; aa++) {
-        const int hs = hstart + g0 + aa;
-        // ---- this atom's mask -> dense list of flat candidate indices
-        const uint32_t word = lane < nchunk ? s_mk[wid][aa * MASK_WORDS + lane] : 0u;
-        const int pc = __popc(word);
-        const int incl = warp_incl_scan(pc, lane);
-        const int nhit = __shfl_sync(FULL, incl, 31);
+      const int na = min(4, nh - a0);
+      for (int q = 0; q < na; q++) {
+        const int hs = hstart + a0 + q;
+        const int nhit = __shfl_sync(FULL, my_nhit, q * 8);
         if (nhit == 0) continue;
-        __syncwarp();
-        for (int k = 0; k < nchunk; k++) {
-          const uint32_t wk = __shfl_sync(FULL, word, k);
-          const int pre = __shfl_sync(FULL, incl - pc, k);
-          if ((wk >> lane) & 1u) s_list[wid][pre + __popc(wk & lt)] = (uint8_t)(k * 32 + lane);
-        }
-        __syncwarp();
-
+        const uint32_t io = __shfl_sync(FULL, my_io, q * 8);
+        const long long base = __shfl_sync(FULL, my_base, q * 8);
         const T xi = sx[hs], yi = sy[hs], zi = sz[hs];
         const uint32_t wi = sw[hs];
-        const uint32_t io = __shfl_sync(FULL, my_io, aa);
-        const long long base = __shfl_sync(FULL, my_base, aa);
+        const uint8_t* L = lists + q * MASK_MAXCAND;
 
         for (int r0 = 0; r0 < nhit; r0 += 32) {
           const int r = r0 + lane;
-          const bool act = r < nhit;
-          // the row search uses warp shuffles: every lane executes it
-          const int f = act ? (int)s_list[wid][r] : 0;
-          int rr = 0;
-#pragma unroll
-          for (int q = 0; q < 8; q++) rr += (f >= __shfl_sync(FULL, rincl, q)) ? 1 : 0;
-          const int r_incl = __shfl_sync(FULL, rincl, rr);
-          const int r_len = __shfl_sync(FULL, rlen, rr);
-          const int r_start = __shfl_sync(FULL, rstart, rr);
-          if (act) {
-            const int slot = r_start + (f - (r_incl - r_len));
-            const int vrow = ((lz + rr / 3) * VY + (ly + rr % 3)) * VX + lx;
-            const int v = vrow + (slot >= vstart[vrow + 1] ? 1 : 0) + (slot >= vstart[vrow + 2] ? 1 : 0);
+          const int nr = min(32, nhit - r0);
+          uint32_t jo = 0;
+          if (r < nhit) {
+            const int f = L[r];
+            const int slot = tab.cslot[f], v = tab.cv[f];
             const T xj = sx[slot], yj = sy[slot], zj = sz[slot];
             const uint32_t wj = sw[slot];
+            jo = sidx[slot];
             long long S[3];
             unpack_shift(vsh[v], S);
             if (wi != wj || (wi & WIND_OVERFLOW)) {
@@ -450,20 +555,32 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_fill_mask(const MaskArgs<T, TI> 
               if (wj & WIND_OVERFLOW) cell_of(g, xj, yj, zj, cc, w_j); else unpack_wind(wj, w_j);
               S[0] += w_i[0] - w_j[0]; S[1] += w_i[1] - w_j[1]; S[2] += w_i[2] - w_j[2];
             }
-            const long long pos = base + r;
-            a.out.io[pos] = (TI)io + 1;
-            a.out.jo[pos] = (TI)sidx[slot] + 1;
-            a.out.So[3 * pos] = (TI)S[0];
-            a.out.So[3 * pos + 1] = (TI)S[1];
-            a.out.So[3 * pos + 2] = (TI)S[2];
+            if (sizeof(TI) == 4) {
+              stS32[3 * lane] = (uint32_t)(int)S[0]; stS32[3 * lane + 1] = (uint32_t)(int)S[1]; stS32[3 * lane + 2] = (uint32_t)(int)S[2];
+            }
             if (a.out.Ro) {
               T R[3];
               pair_r2(g, xi, yi, zi, xj, yj, zj, S, R);
-              a.out.Ro[3 * pos] = R[0];
-              a.out.Ro[3 * pos + 1] = R[1];
-              a.out.Ro[3 * pos + 2] = R[2];
+              stR[3 * lane] = R[0]; stR[3 * lane + 1] = R[1]; stR[3 * lane + 2] = R[2];
+            }
+            const long long pos = base + r;
+            a.out.io[pos] = (TI)io + 1;
+            a.out.jo[pos] = (TI)jo + 1;
+            if (sizeof(TI) == 8) {
+              a.out.So[3 * pos] = (TI)S[0]; a.out.So[3 * pos + 1] = (TI)S[1]; a.out.So[3 * pos + 2] = (TI)S[2];
             }
           }
+          __syncwarp();
+          // transposed, contiguous stores of the row segment [base + r0, base + r0 + nr)
+          if (sizeof(TI) == 4) {
+            uint32_t* dst = (uint32_t*)a.out.So + 3 * (base + r0);
+            for (int w = lane; w < 3 * nr; w += 32) dst[w] = stS32[w];
+          }
+          if (a.out.Ro) {
+            T* dst = a.out.Ro + 3 * (base + r0);
+            for (int w = lane; w < 3 * nr; w += 32) dst[w] = stR[w];
+          }
+          __syncwarp();
         }
       }
     }
@@ -476,7 +593,7 @@ inline void mask_args(MaskArgs<T, TI>& a, int64_t n, const TI* co, const Records
   a.rec = rec; a.co = co; a.n = n; a.g = g; a.out = sk; a.masks = masks; a.cellflag = nullptr;
   a.tx = ts.tx; a.ty = ts.ty; a.tz = ts.tz;
   a.ntx = (g.nc[0] + ts.tx - 1) / ts.tx; a.nty = (g.nc[1] + ts.ty - 1) / ts.ty; a.ntz = (g.nc[2] + ts.tz - 1) / ts.tz;
-  a.lo = a.hi = a.dguard = 0.f;
+  a.mid = a.hw = a.dguard = 0.f;
 }
 
 }  // namespace nl

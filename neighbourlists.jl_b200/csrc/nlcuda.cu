@@ -176,7 +176,7 @@ template <class T> Plan<T> make_plan(const nl_params* p, const Geo<T>& g, int64_
   pl.path = PATH_TILED;
   const double dens = (double)N / (double)g.nct;
   if (27.0 * dens > 200.0) return pl;  // candidate lists would overflow the 256-bit masks too often
-  if (!pick_tile<T>(g, N, CNT_CAP, pl.ts_count) || !pick_tile<T>(g, N, fill_cap<T>(), pl.ts_fill)) return pl;
+  if (!pick_tile<T>(g, N, CNT_CAP2, pl.ts_count) || !pick_tile<T>(g, N, fill_cap<T>(), pl.ts_fill)) return pl;
   if (sizeof(T) == 8) {
     pl.th = mask_thresholds(p->cell, p->ncells, pl.ts_count, (double)g.cutoff_sq);
     if (!pl.th.ok) return pl;
@@ -214,7 +214,7 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
     MaskArgs<T, TI> a;
     mask_args<T, TI>(a, N, (const TI*)co, rec, g, sk, MODE == MODE_FILL ? pl.ts_fill : pl.ts_count, tsx.masks);
     a.cellflag = tsx.cellflag;
-    a.lo = pl.th.lo; a.hi = pl.th.hi; a.dguard = pl.th.dguard;
+    a.mid = pl.th.mid; a.hw = pl.th.hw; a.dguard = pl.th.dguard;
     const unsigned nblk = (unsigned)((long long)a.ntx * a.nty * a.ntz);
     if (MODE == MODE_FILL) {
       static bool done = false;
