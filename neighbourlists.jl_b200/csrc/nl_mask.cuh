@@ -169,7 +169,8 @@ constexpr int CNT_FIXED_BYTES = 3 * TILE_VPAD * 4 + 64 * 4 + (TILE_NT / 32) * CN
 constexpr int CNT_CAP2 = (CNT_SMEM_BYTES - CNT_FIXED_BYTES) / 16 / 8 * 8;
 static_assert(CNT_WARP_BYTES % 16 == 0 && CNT_FIXED_BYTES % 16 == 0, "alignment");
 
-constexpr float CAND_FAR = 1.0e18f;  // finite "nowhere": squares stay finite in Float32
+constexpr float CAND_FAR = 1.0e18f;   // lanes beyond the candidate list: finite "nowhere" (squares stay finite in Float32)
+constexpr float SLOT_FAR = -1.0e18f;  // staged slots that need the exact path: far from everything, including CAND_FAR
 
 template <class T, class TI, bool WANT_MASK>
 __global__ void __launch_bounds__(TILE_NT, 4) k_count_mask(const MaskArgs<T, TI> a) {
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(TILE_NT, 4) k_count_mask(const MaskArgs<T, TI>
       const double q2 = (z - O[2]) + ((g.cell[6] * m0 + g.cell[7] * m1) + g.cell[8] * m2);
       const bool good = !(pw & WIND_OVERFLOW) && fabs(x) <= 1e5 && fabs(y) <= 1e5 && fabs(z) <= 1e5 && fabs(q0) <= dg && fabs(q1) <= dg &&
                         fabs(q2) <= dg;  // false for NaN too
-      sq[sl] = good ? make_float4((float)q0, (float)q1, (float)q2, 0.f) : make_float4(CAND_FAR, CAND_FAR, CAND_FAR, 1.f);
+      sq[sl] = good ? make_float4((float)q0, (float)q1, (float)q2, 0.f) : make_float4(SLOT_FAR, SLOT_FAR, SLOT_FAR, 1.f);
     }
   } else {
     for (int sl = tid; sl < total; sl += TILE_NT) {
@@ -376,7 +377,7 @@ __global__ void __launch_bounds__(TILE_NT, 4) k_count_mask(const MaskArgs<T, TI>
               const float px = hb[(aa >> 1) * 8 + (aa & 1)], py = hb[(aa >> 1) * 8 + 2 + (aa & 1)], pz = hb[(aa >> 1) * 8 + 4 + (aa & 1)];
               const float dx = px - qx, dy = py - qy, dz = pz - qz;
               const float t = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, -mid)));
-              hit = t < -hw;
+              hit = valid && t < -hw;
               if (valid && (cand_bad || ((hbad >> aa) & 1u) || fabsf(t) <= hw)) hit = exact_pair_hit<T>(g, a.rec, hg0 + g0 + aa, gj, shp);
             } else {
               hit = valid && exact_pair_hit<T>(g, a.rec, hg0 + g0 + aa, gj, shp);
