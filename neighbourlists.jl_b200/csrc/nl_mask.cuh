@@ -173,7 +173,7 @@ constexpr float CAND_FAR = 1.0e18f;   // lanes beyond the candidate list: finite
 constexpr float SLOT_FAR = -1.0e18f;  // staged slots that need the exact path: far from everything, including CAND_FAR
 
 template <class T, class TI, bool WANT_MASK>
-__global__ void __launch_bounds__(TILE_NT, 4) k_count_mask(const MaskArgs<T, TI> a) {
+__global__ void __launch_bounds__(TILE_NT, 3) k_count_mask(const MaskArgs<T, TI> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* vstart = (int*)smem_raw;
   int* vgs = vstart + TILE_VPAD;
@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(TILE_NT, 4) k_count_mask(const MaskArgs<T, TI>
             mtv(g.cell, (T)(s[0] + w0[0] - w1[0]), (T)(s[1] + w0[1] - w1[1]), (T)(s[2] + w0[2] - w1[2]), cs0, cs1, cs2);
           }
         }
-        bool band = false;  // some pair of this lane fell in the uncertainty band
+        float bmin = 3.0e38f;  // min |t| over this lane's pairs: <= hw means some pair fell in the uncertainty band
         uint32_t* mrow = mkT + kc * 34;
 
         if constexpr (sizeof(T) == 8) {
@@ -346,7 +346,7 @@ __global__ void __launch_bounds__(TILE_NT, 4) k_count_mask(const MaskArgs<T, TI>
             float2 t = __ffma2_rn(dx, dx, nmid2);
             t = __ffma2_rn(dy, dy, t);
             t = __ffma2_rn(dz, dz, t);
-            band = band || (fabsf(t.x) <= hw) || (fabsf(t.y) <= hw);
+            bmin = fminf(bmin, fminf(fabsf(t.x), fabsf(t.y)));
             const unsigned b0 = __ballot_sync(FULL, t.x < -hw);
             const unsigned b1 = __ballot_sync(FULL, t.y < -hw);
             *(uint2*)(mrow + 2 * pr) = make_uint2(b0, b1);  // every lane stores the same words: no branch
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(TILE_NT, 4) k_count_mask(const MaskArgs<T, TI>
         }
         __syncwarp();
         // ---- rare: redo this chunk with the exact contract wherever the fast loop cannot be trusted
-        if (__any_sync(FULL, band || cand_bad) || hbad != 0 || slow_group) {
+        if (__any_sync(FULL, bmin <= hw || cand_bad) || hbad != 0 || slow_group) {
           for (int aa = 0; aa < ng; aa++) {
             bool hit;
             if constexpr (sizeof(T) == 8) {
@@ -412,8 +412,8 @@ __global__ void __launch_bounds__(TILE_NT, 4) k_count_mask(const MaskArgs<T, TI>
 // Fill pass: expands the masks.  Stages full records (positions in T, original index, winding).
 // Four atoms' masks are compacted at once (lane = 8*atom + word); each atom's row is then produced
 // by the whole warp, transposed through shared memory and written with contiguous full-sector stores.
-constexpr int FILL_SMEM_BYTES = 72 * 1024;
-constexpr int FILL_WARP_BYTES = CELLTAB_BYTES + 4 * MASK_MAXCAND + 32 * 3 * 4 + 32 * 3 * 8;  // tables | 4 hit lists | S stage | R stage
+constexpr int FILL_SMEM_BYTES = 75 * 1024;
+constexpr int FILL_WARP_BYTES = CELLTAB_BYTES + 4 * MASK_MAXCAND + 32 * 3 * 4 + 32 * 3 * 8 + 28 * 3 * 8;  // tables | 4 hit lists | S stage | R stage | cs table
 constexpr int FILL_FIXED_BYTES = 3 * TILE_VPAD * 4 + 64 * 4 + (TILE_NT / 32) * FILL_WARP_BYTES;
 template <class T> __host__ __device__ constexpr int fill_cap() { return (FILL_SMEM_BYTES - FILL_FIXED_BYTES) / TileRecBytes<T>::value / 8 * 8; }
 static_assert(FILL_WARP_BYTES % 16 == 0 && FILL_FIXED_BYTES % 16 == 0, "alignment");
@@ -443,10 +443,9 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_fill_mask(const MaskArgs<T, TI> 
   tab.cslot = (uint16_t*)wb;
   tab.cv = (uint8_t*)(wb + MASK_MAXCAND * 2);
   uint8_t* lists = wb + CELLTAB_BYTES;                                        // [4][MASK_MAXCAND]
-  TI* stS = (TI*)nullptr;
-  uint32_t* stS32 = (uint32_t*)(wb + CELLTAB_BYTES + 4 * MASK_MAXCAND);       // [32][3] shifts (as int32)
-  T* stR = (T*)(wb + CELLTAB_BYTES + 4 * MASK_MAXCAND + 32 * 3 * 4);          // [32][3]
-  (void)stS;
+  int* stS = (int*)(wb + CELLTAB_BYTES + 4 * MASK_MAXCAND);                   // [32][3] shifts of the current row segment
+  T* stR = (T*)(wb + CELLTAB_BYTES + 4 * MASK_MAXCAND + 32 * 3 * 4);          // [32][3] R of the current row segment
+  T* cst = (T*)(wb + CELLTAB_BYTES + 4 * MASK_MAXCAND + 32 * 3 * 4 + 32 * 3 * 8);  // [27][3] cell' * s_loop per stencil cell
 
   const int b = blockIdx.x;
   const int hx0 = (b % a.ntx) * a.tx, hy0 = ((b / a.ntx) % a.nty) * a.ty, hz0 = (b / (a.ntx * a.nty)) * a.tz;
@@ -494,17 +493,38 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_fill_mask(const MaskArgs<T, TI> 
       continue;
     }
     build_cell_tables(vstart, VX, VY, lx, ly, lz, lane, tab);
+    // lane c < 27: packed periodic shift of stencil cell c and its shift vector cs = cell' * s_loop (contract arithmetic)
+    int my_shp = 0;
+    if (lane < 27) {
+      const int v = ((lz + lane / 9) * VY + (ly + (lane / 3) % 3)) * VX + (lx + lane % 3);
+      my_shp = vsh[v];
+      T c0, c1, c2;
+      mtv(g.cell, (T)((my_shp & 3) - 1), (T)(((my_shp >> 2) & 3) - 1), (T)(((my_shp >> 4) & 3) - 1), c0, c1, c2);
+      cst[3 * lane] = c0; cst[3 * lane + 1] = c1; cst[3 * lane + 2] = c2;
+    }
+    // first virtual cell of the stencil: stencil cell index of virtual cell v is recovered from v's coordinates
+    const int v000 = (lz * VY + ly) * VX + lx;
+    __syncwarp();
+
+    // prefetch of the first pass
+    uint32_t nx_word = 0, nx_io = 0;
+    long long nx_base = 0;
+    if (grp < nh) {
+      nx_word = a.masks[(hg0 + grp) * MASK_WORDS + sub];
+      nx_io = sidx[hstart + grp];
+      nx_base = (long long)a.out.first[nx_io] - 1;
+    }
 
     for (int a0 = 0; a0 < nh; a0 += 4) {
       // ---- four atoms at once: lane = 8 * atom + mask word
-      const int my_atom = a0 + grp;
-      uint32_t word = 0;
-      uint32_t my_io = 0;
-      long long my_base = 0;
-      if (my_atom < nh) {
-        word = a.masks[(hg0 + my_atom) * MASK_WORDS + sub];
-        my_io = sidx[hstart + my_atom];
-        my_base = (long long)a.out.first[my_io] - 1;
+      uint32_t word = nx_word;
+      const uint32_t my_io = nx_io;
+      const long long my_base = nx_base;
+      nx_word = 0;
+      if (a0 + 4 + grp < nh) {  // next pass in flight while this one is expanded
+        nx_word = a.masks[(hg0 + a0 + 4 + grp) * MASK_WORDS + sub];
+        nx_io = sidx[hstart + a0 + 4 + grp];
+        nx_base = (long long)a.out.first[nx_io] - 1;
       }
       const int pc = __popc(word);
       int incl = pc;
@@ -536,50 +556,57 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_fill_mask(const MaskArgs<T, TI> 
         const T xi = sx[hs], yi = sy[hs], zi = sz[hs];
         const uint32_t wi = sw[hs];
         const uint8_t* L = lists + q * MASK_MAXCAND;
+        TI* const io_row = a.out.io + base;
+        TI* const jo_row = a.out.jo + base;
+        TI* const So_row = a.out.So + 3 * base;
+        T* const Ro_row = a.out.Ro ? a.out.Ro + 3 * base : nullptr;
 
         for (int r0 = 0; r0 < nhit; r0 += 32) {
           const int r = r0 + lane;
           const int nr = min(32, nhit - r0);
-          uint32_t jo = 0;
-          if (r < nhit) {
-            const int f = L[r];
-            const int slot = tab.cslot[f], v = tab.cv[f];
+          const bool act = r < nhit;
+          const int f = act ? (int)L[r] : 0;
+          const int slot = tab.cslot[f], v = tab.cv[f];
+          // stencil cell index c = (dz+1)*9 + (dy+1)*3 + (dx+1) from the virtual cell id
+          const int dv = v - v000;
+          const int cz = dv / (VX * VY), cy = (dv - cz * VX * VY) / VX, cx = dv - cz * VX * VY - cy * VX;
+          const int c = cz * 9 + cy * 3 + cx;
+          const int shp = __shfl_sync(FULL, my_shp, c);
+          if (act) {
             const T xj = sx[slot], yj = sy[slot], zj = sz[slot];
             const uint32_t wj = sw[slot];
-            jo = sidx[slot];
-            long long S[3];
-            unpack_shift(vsh[v], S);
-            if (wi != wj || (wi & WIND_OVERFLOW)) {
+            int S0 = (shp & 3) - 1, S1 = ((shp >> 2) & 3) - 1, S2 = ((shp >> 4) & 3) - 1;
+            T R0, R1, R2;
+            if (wi == wj && !(wi & WIND_OVERFLOW)) {
+              R0 = add_rn(sub_rn(xj, xi), cst[3 * c]);
+              R1 = add_rn(sub_rn(yj, yi), cst[3 * c + 1]);
+              R2 = add_rn(sub_rn(zj, zi), cst[3 * c + 2]);
+            } else {
               long long w_i[3], w_j[3];
               int cc[3];
               if (wi & WIND_OVERFLOW) cell_of(g, xi, yi, zi, cc, w_i); else unpack_wind(wi, w_i);
               if (wj & WIND_OVERFLOW) cell_of(g, xj, yj, zj, cc, w_j); else unpack_wind(wj, w_j);
-              S[0] += w_i[0] - w_j[0]; S[1] += w_i[1] - w_j[1]; S[2] += w_i[2] - w_j[2];
-            }
-            if (sizeof(TI) == 4) {
-              stS32[3 * lane] = (uint32_t)(int)S[0]; stS32[3 * lane + 1] = (uint32_t)(int)S[1]; stS32[3 * lane + 2] = (uint32_t)(int)S[2];
-            }
-            if (a.out.Ro) {
+              const long long S[3] = {S0 + w_i[0] - w_j[0], S1 + w_i[1] - w_j[1], S2 + w_i[2] - w_j[2]};
               T R[3];
               pair_r2(g, xi, yi, zi, xj, yj, zj, S, R);
-              stR[3 * lane] = R[0]; stR[3 * lane + 1] = R[1]; stR[3 * lane + 2] = R[2];
+              R0 = R[0]; R1 = R[1]; R2 = R[2];
+              S0 = (int)S[0]; S1 = (int)S[1]; S2 = (int)S[2];
             }
-            const long long pos = base + r;
-            a.out.io[pos] = (TI)io + 1;
-            a.out.jo[pos] = (TI)jo + 1;
-            if (sizeof(TI) == 8) {
-              a.out.So[3 * pos] = (TI)S[0]; a.out.So[3 * pos + 1] = (TI)S[1]; a.out.So[3 * pos + 2] = (TI)S[2];
-            }
+            stS[3 * lane] = S0; stS[3 * lane + 1] = S1; stS[3 * lane + 2] = S2;
+            if (Ro_row) { stR[3 * lane] = R0; stR[3 * lane + 1] = R1; stR[3 * lane + 2] = R2; }
+            io_row[r] = (TI)io + 1;
+            jo_row[r] = (TI)sidx[slot] + 1;
           }
           __syncwarp();
-          // transposed, contiguous stores of the row segment [base + r0, base + r0 + nr)
-          if (sizeof(TI) == 4) {
-            uint32_t* dst = (uint32_t*)a.out.So + 3 * (base + r0);
-            for (int w = lane; w < 3 * nr; w += 32) dst[w] = stS32[w];
-          }
-          if (a.out.Ro) {
-            T* dst = a.out.Ro + 3 * (base + r0);
-            for (int w = lane; w < 3 * nr; w += 32) dst[w] = stR[w];
+          // transposed, contiguous stores of the row segment [r0, r0 + nr): 3 nr words of S, 3 nr of R
+          const int nw = 3 * nr;
+#pragma unroll
+          for (int m = 0; m < 3; m++) {
+            const int w = m * 32 + lane;
+            if (w < nw) {
+              So_row[3 * r0 + w] = (TI)stS[w];
+              if (Ro_row) Ro_row[3 * r0 + w] = stR[w];
+            }
           }
           __syncwarp();
         }
