@@ -111,6 +111,18 @@ NL_API int nl_fill_pairs(const nl_params* params, const void* X_sorted, int64_t 
                   const void* cell_offsets, const void* first, void* i_out, void* j_out, void* S_out,
                   void* R_out, void* ws, size_t ws_bytes, void* stream);
 
+/* nl_fill_pairs for a SHARD (multi-GPU slabs): local atoms are ordered owned-first, only the
+ * first n_rows of them (the owned atoms) get rows, and i/j are written as index_map[local index - 1]
+ * (the atoms' GLOBAL 1-based indices; N TI, may be NULL for local indices).  `first` comes from
+ * nl_count_pairs on the same local set; the owned rows occupy first[0] .. first[n_rows]-1. */
+NL_API int nl_fill_pairs_rows(const nl_params* params, const void* X_sorted, int64_t N, const void* perm,
+                       const void* cell_offsets, const void* first, int64_t n_rows, const void* index_map,
+                       void* i_out, void* j_out, void* S_out, void* R_out, void* ws, size_t ws_bytes, void* stream);
+
+/* Stage (1) alone: cell_id_out[n] (N TI) = 1-based linear cell of atom n in the caller's order
+ * (replaces _compute_cell_ids, src/gpu_kernels.jl:244-255,378).  The slab sharding bins atoms with it. */
+NL_API int nl_cell_ids(const nl_params* params, const void* X, int64_t N, void* cell_id_out, void* stream);
+
 /* Lazy mode: fused for_each_neighbour traversals (src/cell_list.jl:779-801) with fixed sinks.
  * nl_lazy_count: counts_out[m] (N TI, original order) = count_neighbours(clist, m) (:808-814).
  * nl_lazy_lj_energy: *energy_out (DEVICE double) = sum over ordered pairs of

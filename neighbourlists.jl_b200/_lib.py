@@ -16,7 +16,7 @@ NL_STAGE_BUILD, NL_STAGE_PAIRS = 0, 1
 NL_OK, NL_ERR_BAD_ARG, NL_ERR_WORKSPACE, NL_ERR_CUDA, NL_ERR_OVERFLOW, NL_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnlcuda.so")
+LIB_PATH = os.environ.get("NLCUDA_LIB") or os.path.join(_HERE, "libnlcuda.so")  # NLCUDA_LIB: A/B testing of kernel builds
 
 
 class NlParams(C.Structure):
@@ -45,7 +45,7 @@ class NlError(RuntimeError):
 _lib = None
 
 EXPORTS = ("nl_version", "nl_strerror", "nl_last_cuda_error", "nl_launch_count", "nl_workspace_bytes", "nl_build_cells", "nl_count_pairs",
-           "nl_fill_pairs", "nl_lazy_count", "nl_lazy_lj_energy")
+           "nl_fill_pairs", "nl_fill_pairs_rows", "nl_cell_ids", "nl_lazy_count", "nl_lazy_lj_energy")
 
 
 def lib():
@@ -67,9 +67,11 @@ def lib():
         L.nl_build_cells.argtypes = [pp, vp, i64, vp, vp, vp, vp, vp, sz, vp]
         L.nl_count_pairs.argtypes = [pp, vp, i64, vp, vp, vp, C.POINTER(C.c_int64), vp, sz, vp]
         L.nl_fill_pairs.argtypes = [pp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+        L.nl_fill_pairs_rows.argtypes = [pp, vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, sz, vp]
+        L.nl_cell_ids.argtypes = [pp, vp, i64, vp, vp]
         L.nl_lazy_count.argtypes = [pp, vp, i64, vp, vp, vp, vp, sz, vp]
         L.nl_lazy_lj_energy.argtypes = [pp, vp, i64, vp, vp, C.c_double, C.c_double, vp, vp, sz, vp]
-        for n in ("nl_build_cells", "nl_count_pairs", "nl_fill_pairs", "nl_lazy_count", "nl_lazy_lj_energy"):
+        for n in ("nl_build_cells", "nl_count_pairs", "nl_fill_pairs", "nl_fill_pairs_rows", "nl_cell_ids", "nl_lazy_count", "nl_lazy_lj_energy"):
             getattr(L, n).restype = C.c_int
         _lib = L
     return _lib

@@ -146,9 +146,13 @@ def build_cell_list(X, cutoff, cell, pbc, *, int_type=np.int32, device=None) -> 
                           geo=geo, params=params)
 
 
-def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers: Optional[dict] = None) -> PairList:
+def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers: Optional[dict] = None,
+                         n_rows: Optional[int] = None, index_map: Optional[torch.Tensor] = None) -> PairList:
     """materialize_pairlist(clist) -> PairList  (src/gpu_kernels.jl:299-364).  with_R additionally
-    stores R = X[j] - X[i] + C' S per pair (what the reference recomputes in _getR)."""
+    stores R = X[j] - X[i] + C' S per pair (what the reference recomputes in _getR).
+
+    Shard mode (sharded.py): with n_rows, only the first n_rows atoms get rows (`first` has n_rows+1
+    entries) and i/j are written through index_map (global 1-based indices, one per local atom)."""
     import ctypes as C
     N = clist.X.shape[0]
     dev = clist.X.device
@@ -164,6 +168,10 @@ def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers:
         _lib.check(L.nl_count_pairs(clist.params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
                                     C.byref(total), _ptr(ws), ws.numel(), _stream(dev)))
         P = int(total.value)
+        if n_rows is not None:
+            if not 0 <= n_rows <= N:
+                raise ValueError("n_rows out of range")
+            P = int(first[n_rows].item()) - 1
         if timers is not None:
             ev[1].record()
         i = torch.empty(P, dtype=it, device=dev)
@@ -172,13 +180,35 @@ def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers:
         R = torch.empty((P, 3), dtype=clist.X.dtype, device=dev) if with_R else None
         if timers is not None:
             ev[2].record()
-        if P > 0:
+        if P > 0 and n_rows is None and index_map is None:
             _lib.check(L.nl_fill_pairs(clist.params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
                                        _ptr(i), _ptr(j), _ptr(S), _ptr(R), _ptr(ws), ws.numel(), _stream(dev)))
+        elif P > 0:
+            if index_map is not None:
+                index_map = index_map.to(device=dev, dtype=it).contiguous()
+                assert index_map.shape[0] == N
+            _lib.check(L.nl_fill_pairs_rows(clist.params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
+                                            N if n_rows is None else n_rows, _ptr(index_map), _ptr(i), _ptr(j), _ptr(S), _ptr(R),
+                                            _ptr(ws), ws.numel(), _stream(dev)))
+        if n_rows is not None:
+            first = first[:n_rows + 1]
         if timers is not None:
             ev[3].record()
             timers.setdefault("events", []).append(ev)
     return PairList(X=clist.X_orig, C=clist.cell, cutoff=clist.cutoff, i=i, j=j, S=S, first=first, R=R)
+
+
+def cell_ids(X, cutoff, cell, pbc, *, int_type=np.int32, device=None) -> torch.Tensor:
+    """1-based linear cell id of every atom in the caller's order (_compute_cell_ids, src/gpu_kernels.jl:244-255)."""
+    Xd = _as_device_positions(X, device)
+    it = _int_dtype(int_type)
+    fdt = np.dtype(_T2N[Xd.dtype])
+    geo = geometry(cell, cutoff, pbc, fdt)
+    params = _lib.make_params(geo, fdt, _T2N[it])
+    out = torch.empty(Xd.shape[0], dtype=it, device=Xd.device)
+    with torch.cuda.device(Xd.device):
+        _lib.check(_lib.lib().nl_cell_ids(params, _ptr(Xd), Xd.shape[0], _ptr(out), _stream(Xd.device)))
+    return out
 
 
 def neighbour_list(X, cutoff, cell, pbc, *, lazy: bool = False, int_type=np.int32, with_R: bool = False, device=None):

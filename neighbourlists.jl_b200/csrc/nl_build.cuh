@@ -18,6 +18,18 @@ __global__ void __launch_bounds__(256) k_bin(const T* __restrict__ X, long long 
   keys[i] = (uint32_t)c[0] + (uint32_t)g.nc[0] * ((uint32_t)c[1] + (uint32_t)g.nc[1] * (uint32_t)c[2]);
 }
 
+// The same binning with the reference's output convention: 1-based linear cell id per atom in the caller's
+// order (_compute_cell_ids, src/gpu_kernels.jl:244-255,378).  Used by the slab sharding.
+template <class T, class TI>
+__global__ void __launch_bounds__(256) k_cell_ids(const T* __restrict__ X, long long n, Geo<T> g, TI* __restrict__ out) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int c[3];
+  long long w[3];
+  cell_of(g, X[3 * i], X[3 * i + 1], X[3 * i + 2], c, w);
+  out[i] = (TI)c[0] + (TI)g.nc[0] * ((TI)c[1] + (TI)g.nc[1] * (TI)c[2]) + 1;
+}
+
 // After the sort: perm, cell_id (1-based, TI) and X_sorted = X[perm] (src/cell_list.jl:669-670).
 template <class T, class TI>
 __global__ void __launch_bounds__(256) k_finalize_sorted(const uint32_t* __restrict__ skeys, const uint32_t* __restrict__ svals,

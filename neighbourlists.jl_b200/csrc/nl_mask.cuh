@@ -125,16 +125,39 @@ __device__ __forceinline__ int find_vcell(const int* vstart, int NV, int sl) {
   return lo;
 }
 
+// Rare path of the fill pass: atoms i and j carry different (or overflowed) winding numbers, so the
+// shift is S = s_loop + w_i - w_j and cell' * S is not the per-cell table entry.  Kept out of line so
+// that none of it is hoisted into the common path.
+template <class T>
+__device__ __noinline__ void slow_shift_and_R(const Geo<T>& g, T xi, T yi, T zi, T xj, T yj, T zj, uint32_t wi, uint32_t wj, int* S012, T* R012) {
+  long long w_i[3], w_j[3];
+  int cc[3];
+  if (wi & WIND_OVERFLOW) cell_of(g, xi, yi, zi, cc, w_i); else unpack_wind(wi, w_i);
+  if (wj & WIND_OVERFLOW) cell_of(g, xj, yj, zj, cc, w_j); else unpack_wind(wj, w_j);
+  const long long S[3] = {S012[0] + w_i[0] - w_j[0], S012[1] + w_i[1] - w_j[1], S012[2] + w_i[2] - w_j[2]};
+  T R[3];
+  pair_r2(g, xi, yi, zi, xj, yj, zj, S, R);
+  R012[0] = R[0]; R012[1] = R[1]; R012[2] = R[2];
+  S012[0] = (int)S[0]; S012[1] = (int)S[1]; S012[2] = (int)S[2];
+}
+
+// Generic per-atom route for the atoms [g0, g0 + n) of one cell (out of line: rare).
+template <class T, class TI, int MODE>
+__device__ __noinline__ void generic_cell(long long g0, int n, int lane, const Records<T>& rec, const TI* co, const Geo<T>& g, const Sinks<T, TI>& out) {
+  for (int k = lane; k < n; k += 32) generic_atom<T, TI, MODE>(g0 + k, rec, co, g, out);
+}
+
 // Per-warp candidate tables of one home cell: flat candidate index -> staged slot / virtual cell.
 struct CellTables {
   uint16_t* cslot;  // [MASK_MAXCAND]
-  uint8_t* cv;      // [MASK_MAXCAND]
+  uint8_t* cv;      // [MASK_MAXCAND] virtual cell id (count pass) or stencil cell index 0..26 (fill pass)
 };
 constexpr int CELLTAB_BYTES = MASK_MAXCAND * 3;
 
 // Builds the tables for home cell (lx, ly, lz) of the tile; returns the number of candidates
 // (tables are valid only if it is <= MASK_MAXCAND).  Lane c < 27 owns neighbour cell
 // c = (dz+1)*9 + (dy+1)*3 + (dx+1); flat order = cell order, then sorted order inside the cell.
+template <bool STORE_STENCIL_INDEX>
 __device__ __forceinline__ int build_cell_tables(const int* vstart, int VX, int VY, int lx, int ly, int lz, int lane, const CellTables& t) {
   int v = 0, st = 0, cn = 0;
   if (lane < 27) {
@@ -148,7 +171,7 @@ __device__ __forceinline__ int build_cell_tables(const int* vstart, int VX, int 
     const int pre = incl - cn;
     const int mx = __reduce_max_sync(FULL, cn);
     for (int j = 0; j < mx; j++)
-      if (j < cn) { t.cslot[pre + j] = (uint16_t)(st + j); t.cv[pre + j] = (uint8_t)v; }
+      if (j < cn) { t.cslot[pre + j] = (uint16_t)(st + j); t.cv[pre + j] = (uint8_t)(STORE_STENCIL_INDEX ? lane : v); }
   }
   __syncwarp();
   return ncand;
@@ -172,8 +195,11 @@ static_assert(CNT_WARP_BYTES % 16 == 0 && CNT_FIXED_BYTES % 16 == 0, "alignment"
 constexpr float CAND_FAR = 1.0e18f;   // lanes beyond the candidate list: finite "nowhere" (squares stay finite in Float32)
 constexpr float SLOT_FAR = -1.0e18f;  // staged slots that need the exact path: far from everything, including CAND_FAR
 
+#ifndef NL_CNT_MINB
+#define NL_CNT_MINB 4
+#endif
 template <class T, class TI, bool WANT_MASK>
-__global__ void __launch_bounds__(TILE_NT, 3) k_count_mask(const MaskArgs<T, TI> a) {
+__global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_mask(const MaskArgs<T, TI> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* vstart = (int*)smem_raw;
   int* vgs = vstart + TILE_VPAD;
@@ -208,7 +234,7 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_count_mask(const MaskArgs<T, TI>
       const int lx = hcell[hc] & 255, ly = (hcell[hc] >> 8) & 255, lz = hcell[hc] >> 16;
       const int vh = ((lz + 1) * VY + (ly + 1)) * VX + (lx + 1);
       const int nh = vstart[vh + 1] - vstart[vh];
-      for (int k = lane; k < nh; k += 32) generic_atom<T, TI, MODE_COUNT>((long long)vgs[vh] + k, a.rec, a.co, g, a.out);
+      generic_cell<T, TI, MODE_COUNT>((long long)vgs[vh], nh, lane, a.rec, a.co, g, a.out);
       if (WANT_MASK && lane == 0) a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)] = 0;
     }
     return;
@@ -264,10 +290,10 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_count_mask(const MaskArgs<T, TI>
     const int hstart = vstart[vh], nh = vstart[vh + 1] - hstart;
     if (nh == 0) continue;
     const long long hg0 = vgs[vh];
-    const int ncand = build_cell_tables(vstart, VX, VY, lx, ly, lz, lane, tab);
+    const int ncand = build_cell_tables<false>(vstart, VX, VY, lx, ly, lz, lane, tab);
     if (WANT_MASK && lane == 0) a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)] = ncand <= MASK_MAXCAND ? 1 : 0;
     if (ncand > MASK_MAXCAND) {  // too many candidates for a 256-bit mask: generic route (the fill pass does the same)
-      for (int k = lane; k < nh; k += 32) generic_atom<T, TI, MODE_COUNT>(hg0 + k, a.rec, a.co, g, a.out);
+      generic_cell<T, TI, MODE_COUNT>(hg0, nh, lane, a.rec, a.co, g, a.out);
       continue;
     }
     const int nchunk = (ncand + 31) >> 5;
@@ -412,14 +438,20 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_count_mask(const MaskArgs<T, TI>
 // Fill pass: expands the masks.  Stages full records (positions in T, original index, winding).
 // Four atoms' masks are compacted at once (lane = 8*atom + word); each atom's row is then produced
 // by the whole warp, transposed through shared memory and written with contiguous full-sector stores.
-constexpr int FILL_SMEM_BYTES = 75 * 1024;
+#ifndef NL_FILL_SMEM_KB
+#define NL_FILL_SMEM_KB 100
+#endif
+constexpr int FILL_SMEM_BYTES = NL_FILL_SMEM_KB * 1024;
 constexpr int FILL_WARP_BYTES = CELLTAB_BYTES + 4 * MASK_MAXCAND + 32 * 3 * 4 + 32 * 3 * 8 + 28 * 3 * 8;  // tables | 4 hit lists | S stage | R stage | cs table
 constexpr int FILL_FIXED_BYTES = 3 * TILE_VPAD * 4 + 64 * 4 + (TILE_NT / 32) * FILL_WARP_BYTES;
 template <class T> __host__ __device__ constexpr int fill_cap() { return (FILL_SMEM_BYTES - FILL_FIXED_BYTES) / TileRecBytes<T>::value / 8 * 8; }
 static_assert(FILL_WARP_BYTES % 16 == 0 && FILL_FIXED_BYTES % 16 == 0, "alignment");
 
+#ifndef NL_FILL_MINB
+#define NL_FILL_MINB 2
+#endif
 template <class T, class TI>
-__global__ void __launch_bounds__(TILE_NT, 3) k_fill_mask(const MaskArgs<T, TI> a) {
+__global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskArgs<T, TI> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int CAP = fill_cap<T>();
   int* vstart = (int*)smem_raw;
@@ -463,7 +495,7 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_fill_mask(const MaskArgs<T, TI> 
       const int lx = hcell[hc] & 255, ly = (hcell[hc] >> 8) & 255, lz = hcell[hc] >> 16;
       const int vh = ((lz + 1) * VY + (ly + 1)) * VX + (lx + 1);
       const int nh = vstart[vh + 1] - vstart[vh];
-      for (int k = lane; k < nh; k += 32) generic_atom<T, TI, MODE_FILL>((long long)vgs[vh] + k, a.rec, a.co, g, a.out);
+      generic_cell<T, TI, MODE_FILL>((long long)vgs[vh], nh, lane, a.rec, a.co, g, a.out);
     }
     return;
   }
@@ -489,10 +521,10 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_fill_mask(const MaskArgs<T, TI> 
     if (nh == 0) continue;
     const long long hg0 = vgs[vh];
     if (!a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)]) {
-      for (int k = lane; k < nh; k += 32) generic_atom<T, TI, MODE_FILL>(hg0 + k, a.rec, a.co, g, a.out);
+      generic_cell<T, TI, MODE_FILL>(hg0, nh, lane, a.rec, a.co, g, a.out);
       continue;
     }
-    build_cell_tables(vstart, VX, VY, lx, ly, lz, lane, tab);
+    build_cell_tables<true>(vstart, VX, VY, lx, ly, lz, lane, tab);
     // lane c < 27: packed periodic shift of stencil cell c and its shift vector cs = cell' * s_loop (contract arithmetic)
     int my_shp = 0;
     if (lane < 27) {
@@ -502,17 +534,17 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_fill_mask(const MaskArgs<T, TI> 
       mtv(g.cell, (T)((my_shp & 3) - 1), (T)(((my_shp >> 2) & 3) - 1), (T)(((my_shp >> 4) & 3) - 1), c0, c1, c2);
       cst[3 * lane] = c0; cst[3 * lane + 1] = c1; cst[3 * lane + 2] = c2;
     }
-    // first virtual cell of the stencil: stencil cell index of virtual cell v is recovered from v's coordinates
-    const int v000 = (lz * VY + ly) * VX + lx;
     __syncwarp();
 
     // prefetch of the first pass
     uint32_t nx_word = 0, nx_io = 0;
     long long nx_base = 0;
     if (grp < nh) {
-      nx_word = a.masks[(hg0 + grp) * MASK_WORDS + sub];
       nx_io = sidx[hstart + grp];
-      nx_base = (long long)a.out.first[nx_io] - 1;
+      if ((long long)nx_io < a.out.n_rows) {  // atoms without a row (halo atoms of a shard) expand to nothing
+        nx_word = a.masks[(hg0 + grp) * MASK_WORDS + sub];
+        nx_base = (long long)a.out.first[nx_io] - 1;
+      }
     }
 
     for (int a0 = 0; a0 < nh; a0 += 4) {
@@ -522,9 +554,11 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_fill_mask(const MaskArgs<T, TI> 
       const long long my_base = nx_base;
       nx_word = 0;
       if (a0 + 4 + grp < nh) {  // next pass in flight while this one is expanded
-        nx_word = a.masks[(hg0 + a0 + 4 + grp) * MASK_WORDS + sub];
         nx_io = sidx[hstart + a0 + 4 + grp];
-        nx_base = (long long)a.out.first[nx_io] - 1;
+        if ((long long)nx_io < a.out.n_rows) {
+          nx_word = a.masks[(hg0 + a0 + 4 + grp) * MASK_WORDS + sub];
+          nx_base = (long long)a.out.first[nx_io] - 1;
+        }
       }
       const int pc = __popc(word);
       int incl = pc;
@@ -553,6 +587,7 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_fill_mask(const MaskArgs<T, TI> 
         if (nhit == 0) continue;
         const uint32_t io = __shfl_sync(FULL, my_io, q * 8);
         const long long base = __shfl_sync(FULL, my_base, q * 8);
+        const TI io_out = out_index(a.out, io);
         const T xi = sx[hs], yi = sy[hs], zi = sz[hs];
         const uint32_t wi = sw[hs];
         const uint8_t* L = lists + q * MASK_MAXCAND;
@@ -566,11 +601,7 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_fill_mask(const MaskArgs<T, TI> 
           const int nr = min(32, nhit - r0);
           const bool act = r < nhit;
           const int f = act ? (int)L[r] : 0;
-          const int slot = tab.cslot[f], v = tab.cv[f];
-          // stencil cell index c = (dz+1)*9 + (dy+1)*3 + (dx+1) from the virtual cell id
-          const int dv = v - v000;
-          const int cz = dv / (VX * VY), cy = (dv - cz * VX * VY) / VX, cx = dv - cz * VX * VY - cy * VX;
-          const int c = cz * 9 + cy * 3 + cx;
+          const int slot = tab.cslot[f], c = tab.cv[f];  // c: stencil cell index (dz+1)*9 + (dy+1)*3 + (dx+1)
           const int shp = __shfl_sync(FULL, my_shp, c);
           if (act) {
             const T xj = sx[slot], yj = sy[slot], zj = sz[slot];
@@ -582,20 +613,16 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_fill_mask(const MaskArgs<T, TI> 
               R1 = add_rn(sub_rn(yj, yi), cst[3 * c + 1]);
               R2 = add_rn(sub_rn(zj, zi), cst[3 * c + 2]);
             } else {
-              long long w_i[3], w_j[3];
-              int cc[3];
-              if (wi & WIND_OVERFLOW) cell_of(g, xi, yi, zi, cc, w_i); else unpack_wind(wi, w_i);
-              if (wj & WIND_OVERFLOW) cell_of(g, xj, yj, zj, cc, w_j); else unpack_wind(wj, w_j);
-              const long long S[3] = {S0 + w_i[0] - w_j[0], S1 + w_i[1] - w_j[1], S2 + w_i[2] - w_j[2]};
-              T R[3];
-              pair_r2(g, xi, yi, zi, xj, yj, zj, S, R);
-              R0 = R[0]; R1 = R[1]; R2 = R[2];
-              S0 = (int)S[0]; S1 = (int)S[1]; S2 = (int)S[2];
+              int S3[3] = {S0, S1, S2};
+              T R3[3];
+              slow_shift_and_R<T>(g, xi, yi, zi, xj, yj, zj, wi, wj, S3, R3);
+              S0 = S3[0]; S1 = S3[1]; S2 = S3[2];
+              R0 = R3[0]; R1 = R3[1]; R2 = R3[2];
             }
             stS[3 * lane] = S0; stS[3 * lane + 1] = S1; stS[3 * lane + 2] = S2;
             if (Ro_row) { stR[3 * lane] = R0; stR[3 * lane + 1] = R1; stR[3 * lane + 2] = R2; }
-            io_row[r] = (TI)io + 1;
-            jo_row[r] = (TI)sidx[slot] + 1;
+            io_row[r] = io_out;
+            jo_row[r] = out_index(a.out, sidx[slot]);
           }
           __syncwarp();
           // transposed, contiguous stores of the row segment [r0, r0 + nr): 3 nr words of S, 3 nr of R

@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_tiled(const TiledArgs<T, TI> a) 
         uint32_t my_io = 0;
         if (lane < ng) {
           my_io = sidx[my_home];
-          if (MODE == MODE_FILL) my_base = (long long)a.out.first[my_io] - 1;
+          if (MODE == MODE_FILL && (long long)my_io < a.out.n_rows) my_base = (long long)a.out.first[my_io] - 1;
         }
 
         for (int k0 = 0; k0 < ncand; k0 += 32) {
@@ -254,10 +254,10 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_tiled(const TiledArgs<T, TI> a) 
               if (MODE == MODE_FILL) {
                 const long long base = __shfl_sync(FULL, my_base, aa) + __shfl_sync(FULL, my_cnt, aa);
                 const uint32_t io_b = __shfl_sync(FULL, my_io, aa);
-                if (hit) {
+                if (hit && (long long)io_b < a.out.n_rows) {
                   const long long pos = base + __popc(bal & lt);
-                  a.out.io[pos] = (TI)io_b + 1;
-                  a.out.jo[pos] = (TI)jo + 1;
+                  a.out.io[pos] = out_index(a.out, io_b);
+                  a.out.jo[pos] = out_index(a.out, jo);
                   a.out.So[3 * pos] = (TI)S0;
                   a.out.So[3 * pos + 1] = (TI)S1;
                   a.out.So[3 * pos + 2] = (TI)S2;

@@ -13,6 +13,7 @@ namespace nl {
 
 enum { MODE_COUNT = 0, MODE_FILL = 1, MODE_LJ = 2 };
 
+
 template <class T> struct Records {
   const T* px;
   const T* py;
@@ -28,9 +29,15 @@ template <class T, class TI> struct Sinks {
   TI* jo;
   TI* So;
   T* Ro;                 //            may be null
+  long long n_rows;      //            only atoms with original index < n_rows get a row (sharding: owned atoms first)
+  const TI* gmap;        //            may be null; else i/j are written as gmap[original index] (global, 1-based)
   double* energy;        // MODE_LJ: device scalar
   double lj_eps, lj_sigma2;
 };
+
+template <class T, class TI> __device__ __forceinline__ TI out_index(const Sinks<T, TI>& out, uint32_t orig) {
+  return out.gmap ? out.gmap[orig] : (TI)orig + 1;
+}
 
 template <class T, class TI>
 __global__ void __launch_bounds__(256) k_prep_records(const T* __restrict__ Xs, const TI* __restrict__ perm, long long n, Geo<T> g,
@@ -65,7 +72,10 @@ __device__ __forceinline__ double generic_atom(long long s, const Records<T>& re
   cell_of(g, xi, yi, zi, ci, wi);
   uint32_t cnt = 0;
   long long wpos = 0;
-  if (MODE == MODE_FILL) wpos = (long long)out.first[io] - 1;
+  if (MODE == MODE_FILL) {
+    if ((long long)io >= out.n_rows) return 0.0;
+    wpos = (long long)out.first[io] - 1;
+  }
   for (int dz = -g.nxyz[2]; dz <= g.nxyz[2]; dz++) {
     int cz; long long sz = 0;
     { long long v = (long long)ci[2] + dz;
@@ -94,8 +104,8 @@ __device__ __forceinline__ double generic_atom(long long s, const Records<T>& re
           if (r2 < g.cutoff_sq) {
             if (MODE == MODE_COUNT) cnt++;
             if (MODE == MODE_FILL) {
-              out.io[wpos] = (TI)io + 1;
-              out.jo[wpos] = (TI)jo + 1;
+              out.io[wpos] = out_index(out, io);
+              out.jo[wpos] = out_index(out, jo);
               out.So[3 * wpos] = (TI)S[0];
               out.So[3 * wpos + 1] = (TI)S[1];
               out.So[3 * wpos + 2] = (TI)S[2];

@@ -143,6 +143,15 @@ int build_cells_impl(const nl_params* p, const void* X, int64_t N, void* Xs, voi
 }
 
 template <class T, class TI>
+int cell_ids_impl(const nl_params* p, const void* X, int64_t N, void* out, cudaStream_t st) {
+  Geo<T> g = make_geo<T>(p);
+  k_cell_ids<T, TI><<<(unsigned)((N + 255) / 256), 256, 0, st>>>((const T*)X, N, g, (TI*)out);
+  NL_LAUNCHED(1);
+  NL_LAUNCH_CHECK();
+  return NL_OK;
+}
+
+template <class T, class TI>
 int prep_impl(const nl_params* p, const void* Xs, int64_t N, const void* perm, PairWs& w, Geo<T>& g, cudaStream_t st) {
   if (N > 0) {
     k_prep_records<T, TI><<<(unsigned)((N + 255) / 256), 256, 0, st>>>((const T*)Xs, (const TI*)perm, N, g, (T*)w.px, (T*)w.py, (T*)w.pz,
@@ -272,12 +281,13 @@ int count_pairs_impl(const nl_params* p, const void* Xs, int64_t N, const void* 
 
 template <class T, class TI>
 int fill_pairs_impl(const nl_params* p, int64_t N, const void* co, const void* first, void* io, void* jo, void* So, void* Ro, void* ws,
-                    cudaStream_t st) {
+                    int64_t n_rows, const void* gmap, cudaStream_t st) {
   Geo<T> g = make_geo<T>(p);
   PairWs w = pair_ws(ws, p, N);
   Sinks<T, TI> sk = {};
   sk.first = (const TI*)first;
   sk.io = (TI*)io; sk.jo = (TI*)jo; sk.So = (TI*)So; sk.Ro = (T*)Ro;
+  sk.n_rows = n_rows; sk.gmap = (const TI*)gmap;
   return traverse<T, TI, MODE_FILL>(p, N, co, w, g, sk, true, st);
 }
 
@@ -389,7 +399,29 @@ int nl_fill_pairs(const nl_params* params, const void* X_sorted, int64_t N, cons
   if (!first || !cell_offsets || !X_sorted || !perm || !i_out || !j_out || !S_out) return NL_ERR_BAD_ARG;
   rc = check_ws(ws, ws_bytes, pair_ws(nullptr, params, N).total_bytes);
   if (rc) return rc;
-  return NL_DISPATCH(params, fill_pairs_impl, params, N, cell_offsets, first, i_out, j_out, S_out, R_out, ws, (cudaStream_t)stream);
+  return NL_DISPATCH(params, fill_pairs_impl, params, N, cell_offsets, first, i_out, j_out, S_out, R_out, ws, N, nullptr, (cudaStream_t)stream);
+}
+
+int nl_fill_pairs_rows(const nl_params* params, const void* X_sorted, int64_t N, const void* perm, const void* cell_offsets, const void* first,
+                       int64_t n_rows, const void* index_map, void* i_out, void* j_out, void* S_out, void* R_out, void* ws, size_t ws_bytes,
+                       void* stream) {
+  int rc = check_params(params, N);
+  if (rc) return rc;
+  if (N == 0 || n_rows == 0) return NL_OK;
+  if (n_rows < 0 || n_rows > N) return NL_ERR_BAD_ARG;
+  if (!first || !cell_offsets || !X_sorted || !perm || !i_out || !j_out || !S_out) return NL_ERR_BAD_ARG;
+  rc = check_ws(ws, ws_bytes, pair_ws(nullptr, params, N).total_bytes);
+  if (rc) return rc;
+  return NL_DISPATCH(params, fill_pairs_impl, params, N, cell_offsets, first, i_out, j_out, S_out, R_out, ws, n_rows, index_map,
+                     (cudaStream_t)stream);
+}
+
+int nl_cell_ids(const nl_params* params, const void* X, int64_t N, void* cell_id_out, void* stream) {
+  int rc = check_params(params, N);
+  if (rc) return rc;
+  if (N == 0) return NL_OK;
+  if (!X || !cell_id_out) return NL_ERR_BAD_ARG;
+  return NL_DISPATCH(params, cell_ids_impl, params, X, N, cell_id_out, (cudaStream_t)stream);
 }
 
 int nl_lazy_count(const nl_params* params, const void* X_sorted, int64_t N, const void* perm, const void* cell_offsets, void* counts_out,

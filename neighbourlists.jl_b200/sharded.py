@@ -1,0 +1,192 @@
+"""Multi-GPU neighbour lists: 1-D spatial slabs with a cutoff-wide halo.
+
+One process per GPU (torch.distributed, NCCL over NVLink; gloo on CPU in the tests).  The box is cut
+into slabs of whole cell PLANES along the axis with the most cells; rank r owns planes
+[bounds[r], bounds[r+1]) balanced by atom count.  Three exchanges, all plain point-to-point data
+movement (no reduction on the data path):
+
+  0. all-to-all-v: atoms (position + global index) move to the rank that owns their plane;
+  1. halo: every rank sends the atoms of its `halo` top planes to rank r+1 and of its `halo` bottom
+     planes to rank r-1 (ring when the slab axis is periodic; the same peer twice when G = 2);
+  2. none afterwards: the local atom set (owned first, then halo) goes through the UNCHANGED
+     single-GPU pipeline with the GLOBAL cell, cutoff and pbc.  Every neighbour of an owned atom is
+     present locally and planes owned by nobody are empty, so the rows of the owned atoms -- and
+     their periodic shifts S -- are exactly the global ones; the kernel writes i/j as global indices
+     and skips the (incomplete) rows of the halo atoms (nl_fill_pairs_rows).
+
+The reference has no multi-GPU code; concatenating the ranks' rows by global i reproduces its
+single-device CSR (tests/test_sharded_*).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .cellmath import CellGeometry, geometry
+
+
+@dataclass
+class SlabPlan:
+    axis: int            # slab axis (0, 1, 2)
+    bounds: np.ndarray   # (G+1,) plane boundaries, bounds[0] = 0, bounds[G] = ncells[axis]
+    halo: int            # halo width in planes = nxyz[axis]
+    periodic: bool
+
+
+def plan_slabs(plane_hist: np.ndarray, world: int, halo: int, periodic: bool, axis: int) -> SlabPlan:
+    """Plane boundaries balanced by atom count; every slab at least 2*halo+1 planes wide so that a
+    halo only ever comes from the two adjacent ranks and the two halos of a rank never overlap."""
+    n = int(plane_hist.shape[0])
+    minw = 2 * halo + 1 if world > 1 else 1
+    if world * minw > n:
+        raise ValueError(f"cannot cut {n} cell planes into {world} slabs of >= {minw} planes: use fewer ranks (replicas)")
+    cum = np.concatenate([[0], np.cumsum(plane_hist.astype(np.int64))])
+    total = int(cum[-1])
+    bounds = [0]
+    for r in range(1, world):
+        target = total * r / world
+        b = int(np.searchsorted(cum, target, side="left"))
+        b = max(b, bounds[-1] + minw)            # this slab wide enough
+        b = min(b, n - (world - r) * minw)       # room for the remaining slabs
+        bounds.append(b)
+    bounds.append(n)
+    return SlabPlan(axis=axis, bounds=np.asarray(bounds, dtype=np.int64), halo=halo, periodic=periodic)
+
+
+class CudaEngine:
+    """Local stages on this rank's GPU through libnlcuda.so."""
+
+    def __init__(self, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+    def cell_ids(self, X, cutoff, cell, pbc):
+        from . import api
+        return api.cell_ids(X, cutoff, cell, pbc, int_type=np.int64).long()
+
+    def build(self, X_all, n_owned, gmap, cutoff, cell, pbc, int_type, with_R):
+        from . import api
+        clist = api.build_cell_list(X_all, cutoff, cell, pbc, int_type=int_type)
+        pl = api.materialize_pairlist(clist, with_R=with_R, n_rows=n_owned, index_map=gmap)
+        return dict(first=pl.first, i=pl.i, j=pl.j, S=pl.S, R=pl.R)
+
+
+@dataclass
+class ShardedPairList:
+    """Rows of this rank's owned atoms: row m belongs to global atom owned_index[m]; i, j global (1-based)."""
+    owned_index: torch.Tensor
+    X_owned: torch.Tensor
+    first: torch.Tensor
+    i: torch.Tensor
+    j: torch.Tensor
+    S: torch.Tensor
+    R: Optional[torch.Tensor]
+    n_halo: int
+    plan: SlabPlan
+
+
+def _a2a(t: torch.Tensor, send_counts, recv_counts, group):
+    out = t.new_empty((int(sum(recv_counts)),) + tuple(t.shape[1:]))
+    dist.all_to_all_single(out, t.contiguous(), output_split_sizes=[int(c) for c in recv_counts],
+                           input_split_sizes=[int(c) for c in send_counts], group=group)
+    return out
+
+
+def neighbour_list_sharded(X_local, gidx_local, cutoff, cell, pbc, *, group=None, int_type=np.int32, with_R=False,
+                           engine=None, redistribute=True) -> ShardedPairList:
+    """Neighbour list of a system distributed over the ranks of `group`.
+
+    X_local (n,3) and gidx_local (n,) hold ANY subset of the atoms per rank (global 1-based indices);
+    with redistribute=False the caller guarantees they already lie in this rank's slab of `plan_slabs`.
+    """
+    engine = engine or CudaEngine()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    dev = engine.device
+    X = torch.as_tensor(X_local).to(dev)
+    gidx = torch.as_tensor(gidx_local).to(dev).long()
+    fdt = np.float64 if X.dtype == torch.float64 else np.float32
+    geo: CellGeometry = geometry(cell, cutoff, pbc, fdt)
+    nc = [int(v) for v in geo.ncells]
+    axis = int(np.argmax(nc))                        # most planes (ties: lowest axis) -- the longest cell axis
+    halo = int(geo.nxyz[axis])
+    stride = [1, nc[0], nc[0] * nc[1]][axis]
+
+    def planes_of(Xt):
+        cid = engine.cell_ids(Xt, cutoff, cell, pbc) - 1
+        return (cid // stride) % nc[axis]
+
+    # ---- slab plan from the global plane histogram
+    planes = planes_of(X) if X.shape[0] else torch.zeros(0, dtype=torch.long, device=dev)
+    hist = torch.bincount(planes, minlength=nc[axis]).long()
+    if world > 1:
+        dist.all_reduce(hist, group=group)
+    plan = plan_slabs(hist.cpu().numpy(), world, halo, bool(geo.pbc[axis]), axis)
+    bounds_t = torch.as_tensor(plan.bounds, device=dev)
+
+    # ---- step 0: all-to-all-v to the owners
+    if world > 1 and redistribute:
+        owner = torch.bucketize(planes, bounds_t[1:], right=True)
+        order = torch.argsort(owner, stable=True)
+        send_counts = torch.bincount(owner, minlength=world).long()
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=group)
+        sc, rc = send_counts.cpu().tolist(), recv_counts.cpu().tolist()
+        X = _a2a(X[order], sc, rc, group)
+        gidx = _a2a(gidx[order], sc, rc, group)
+        planes = _a2a(planes[order], sc, rc, group)
+    n_owned = int(X.shape[0])
+
+    # ---- step 1: halo exchange with ranks r-1 / r+1
+    halos_X, halos_g = [], []
+    if world > 1:
+        lo, hi = int(plan.bounds[rank]), int(plan.bounds[rank + 1])
+        up_peer, dn_peer = rank + 1, rank - 1
+        if plan.periodic:
+            up_peer %= world
+            dn_peer %= world
+        has_up, has_dn = 0 <= up_peer < world, 0 <= dn_peer < world
+        sel_up = (planes >= hi - halo).nonzero().flatten() if has_up else planes.new_zeros(0)
+        sel_dn = (planes < lo + halo).nonzero().flatten() if has_dn else planes.new_zeros(0)
+        # sizes first (tiny all-gather), then the payloads as point-to-point messages
+        mine = torch.tensor([sel_up.numel(), sel_dn.numel()], dtype=torch.long, device=dev)
+        sizes = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(sizes, mine, group=group)
+        sizes = [s.cpu().tolist() for s in sizes]
+        # Message order matters when both neighbours are the same rank (G = 2, periodic): every rank sends
+        # [up, down] and receives [from below, from above], so the k-th send to a peer meets its k-th receive.
+        sends, recvs, keep = [], [], []
+        rX_dn = rg_dn = rX_up = rg_up = None
+        if has_up:   # my top planes are rank up_peer's lower halo
+            sX, sg = X[sel_up].contiguous(), gidx[sel_up].contiguous()
+            sends += [dist.P2POp(dist.isend, sX, up_peer, group, tag=1), dist.P2POp(dist.isend, sg, up_peer, group, tag=2)]
+            keep += [sX, sg]
+        if has_dn:   # my bottom planes are rank dn_peer's upper halo
+            sX, sg = X[sel_dn].contiguous(), gidx[sel_dn].contiguous()
+            sends += [dist.P2POp(dist.isend, sX, dn_peer, group, tag=3), dist.P2POp(dist.isend, sg, dn_peer, group, tag=4)]
+            keep += [sX, sg]
+        if has_dn:   # lower halo: the top planes of the rank below
+            rX_dn = X.new_empty((sizes[dn_peer][0], 3))
+            rg_dn = gidx.new_empty((sizes[dn_peer][0],))
+            recvs += [dist.P2POp(dist.irecv, rX_dn, dn_peer, group, tag=1), dist.P2POp(dist.irecv, rg_dn, dn_peer, group, tag=2)]
+            halos_X.append(rX_dn); halos_g.append(rg_dn)
+        if has_up:   # upper halo: the bottom planes of the rank above
+            rX_up = X.new_empty((sizes[up_peer][1], 3))
+            rg_up = gidx.new_empty((sizes[up_peer][1],))
+            recvs += [dist.P2POp(dist.irecv, rX_up, up_peer, group, tag=3), dist.P2POp(dist.irecv, rg_up, up_peer, group, tag=4)]
+            halos_X.append(rX_up); halos_g.append(rg_up)
+        ops = sends + recvs
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+    X_all = torch.cat([X] + halos_X) if halos_X else X
+    g_all = torch.cat([gidx] + halos_g) if halos_g else gidx
+    n_halo = int(X_all.shape[0]) - n_owned
+
+    # ---- step 2: the unchanged single-GPU pipeline on owned + halo atoms, global geometry
+    res = engine.build(X_all, n_owned, g_all, cutoff, cell, pbc, int_type, with_R)
+    return ShardedPairList(owned_index=gidx, X_owned=X, first=res["first"], i=res["i"], j=res["j"], S=res["S"], R=res["R"],
+                           n_halo=n_halo, plan=plan)

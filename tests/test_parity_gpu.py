@@ -235,3 +235,42 @@ def test_100k_mixed_pbc_triclinic(nl, dtype, int_type):
     clist, pl, orc = check_case(nl, X, 5.0, cell.astype(dtype), (True, True, False), dtype, int_type, msg="C3/10")
     Xd = U.displace_by_lattice(X, cell, (True, True, False))
     check_case(nl, Xd, 5.0, cell.astype(dtype), (True, True, False), dtype, int_type, msg="C3/10 displaced")
+
+
+def test_shard_mode_rows_and_global_indices(nl):
+    """nl_fill_pairs_rows on the GPU: emulate the slab sharding of sharded.py for G = 3 ranks one after the
+    other (the exchange itself is covered by the gloo tests) and merge the ranks' rows."""
+    import torch
+    from importlib import import_module
+    sh = import_module("neighbourlists_jl_b200.sharded")
+    for dtype, pbc, cutoff in ((np.float64, (True, True, True), 5.0), (np.float32, (True, False, True), 5.0)):
+        cell = np.diag([25.0, 25.0, 120.0])
+        N = 4000
+        X = U.rand_in_cell(N, cell, seed=8, dtype=dtype)
+        orc = O.sortbased(X, cutoff, cell, pbc, dtype=dtype)
+        eng = sh.CudaEngine()
+        cid = eng.cell_ids(torch.from_numpy(X).cuda(), cutoff, cell, pbc).cpu().numpy() - 1
+        nc = nl.cellmath.geometry(cell, cutoff, pbc, dtype).ncells
+        planes = (cid // (nc[0] * nc[1])) % nc[2]
+        plan = sh.plan_slabs(np.bincount(planes, minlength=nc[2]), 3, 1, bool(pbc[2]), 2)
+        merged = dict(i=[], j=[], S=[], R=[])
+        counts = np.zeros(N, np.int64)
+        for r in range(3):
+            lo, hi = plan.bounds[r], plan.bounds[r + 1]
+            owned = np.nonzero((planes >= lo) & (planes < hi))[0]
+            below = np.nonzero(planes == (lo - 1) % nc[2])[0] if (pbc[2] or lo > 0) else np.zeros(0, np.int64)
+            above = np.nonzero(planes == hi % nc[2])[0] if (pbc[2] or hi < nc[2]) else np.zeros(0, np.int64)
+            local = np.concatenate([owned, below, above])
+            res = eng.build(torch.from_numpy(X[local]).cuda(), len(owned), torch.from_numpy(local + 1).cuda(), cutoff, cell, pbc,
+                            np.int32, True)
+            f = res["first"].cpu().numpy()
+            assert f.shape[0] == len(owned) + 1 and res["i"].shape[0] == f[-1] - 1
+            counts[owned] = np.diff(f)
+            assert np.array_equal(res["i"].cpu().numpy(), np.repeat(owned + 1, np.diff(f)))
+            for k in merged:
+                merged[k].append(res[k].cpu().numpy())
+        merged = {k: np.concatenate(v) for k, v in merged.items()}
+        merged["first"] = np.concatenate([[1], 1 + np.cumsum(counts)])
+        order = np.argsort(merged["i"], kind="stable")
+        merged = dict(first=merged["first"], i=merged["i"][order], j=merged["j"][order], S=merged["S"][order], R=merged["R"][order])
+        U.assert_engine_matches_oracle(merged, orc, RTOL[np.dtype(dtype)], msg="shards")
