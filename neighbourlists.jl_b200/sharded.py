@@ -60,8 +60,9 @@ def plan_slabs(plane_hist: np.ndarray, world: int, halo: int, periodic: bool, ax
 class CudaEngine:
     """Local stages on this rank's GPU through libnlcuda.so."""
 
-    def __init__(self, device=None):
+    def __init__(self, device=None, timers=None):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.timers = timers  # optional dict: CUDA events around the count and fill stages (bench.py)
 
     def cell_ids(self, X, cutoff, cell, pbc):
         from . import api
@@ -70,7 +71,7 @@ class CudaEngine:
     def build(self, X_all, n_owned, gmap, cutoff, cell, pbc, int_type, with_R):
         from . import api
         clist = api.build_cell_list(X_all, cutoff, cell, pbc, int_type=int_type)
-        pl = api.materialize_pairlist(clist, with_R=with_R, n_rows=n_owned, index_map=gmap)
+        pl = api.materialize_pairlist(clist, with_R=with_R, n_rows=n_owned, index_map=gmap, timers=self.timers)
         return dict(first=pl.first, i=pl.i, j=pl.j, S=pl.S, R=pl.R)
 
 
