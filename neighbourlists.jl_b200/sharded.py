@@ -131,14 +131,18 @@ def neighbour_list_sharded(X_local, gidx_local, cutoff, cell, pbc, *, group=None
     # ---- step 0: all-to-all-v to the owners
     if world > 1 and redistribute:
         owner = torch.bucketize(planes, bounds_t[1:], right=True)
-        order = torch.argsort(owner, stable=True)
-        send_counts = torch.bincount(owner, minlength=world).long()
+        # atoms already on their owner stay put; only the leavers are sorted by destination and exchanged
+        stay = owner == rank
+        leave = (~stay).nonzero().flatten()
+        lo_owner = owner[leave]
+        order = leave[torch.argsort(lo_owner, stable=True)]
+        send_counts = torch.bincount(lo_owner, minlength=world).long()
         recv_counts = torch.empty_like(send_counts)
         dist.all_to_all_single(recv_counts, send_counts, group=group)
         sc, rc = send_counts.cpu().tolist(), recv_counts.cpu().tolist()
-        X = _a2a(X[order], sc, rc, group)
-        gidx = _a2a(gidx[order], sc, rc, group)
-        planes = _a2a(planes[order], sc, rc, group)
+        X = torch.cat([X[stay], _a2a(X[order], sc, rc, group)])
+        gidx = torch.cat([gidx[stay], _a2a(gidx[order], sc, rc, group)])
+        planes = torch.cat([planes[stay], _a2a(planes[order], sc, rc, group)])
     n_owned = int(X.shape[0])
 
     # ---- step 1: halo exchange with ranks r-1 / r+1
