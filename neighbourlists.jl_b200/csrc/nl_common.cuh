@@ -30,6 +30,36 @@ __device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, 
 __device__ __forceinline__ long long floor_ll(double v) { return __double2ll_rd(v); }
 __device__ __forceinline__ long long floor_ll(float v) { return __float2ll_rd(v); }
 
+// Packed Float32 pairs (Blackwell FADD2 / FMUL2 / FFMA2), in PTX with explicit .rn.
+// CAUTION (verified in SASS, CUDA 12.9): ptxas contracts a packed multiply feeding a packed add into FFMA2
+// even with explicit .rn and -fmad=false.  Contract arithmetic may therefore use mul2_rn and add2_rn, but
+// never add2_rn on the result of mul2_rn: sum packed products with scalar __fadd_rn.
+__device__ __forceinline__ unsigned long long f2_bits(float2 v) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(v.x), "f"(v.y));
+  return r;
+}
+__device__ __forceinline__ float2 bits_f2(unsigned long long r) {
+  float2 v;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(v.x), "=f"(v.y) : "l"(r));
+  return v;
+}
+__device__ __forceinline__ float2 add2_rn(float2 a, float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(r);
+}
+__device__ __forceinline__ float2 mul2_rn(float2 a, float2 b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)));
+  return bits_f2(r);
+}
+__device__ __forceinline__ float2 fma2_rn(float2 a, float2 b, float2 c) {  // deliberately fused (pre-filter only)
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(f2_bits(a)), "l"(f2_bits(b)), "l"(f2_bits(c)));
+  return bits_f2(r);
+}
+
 // Geometry in the compute type T (device-side copy of nl_params).
 template <class T> struct Geo {
   T cell[9];  // column-major, rows = lattice vectors

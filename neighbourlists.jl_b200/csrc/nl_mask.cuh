@@ -366,12 +366,12 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_mask(const MaskA
           for (int pr = 0; pr < npair; pr++) {
             const float4 A = *(const float4*)(hb + pr * 8);
             const float2 Z = *(const float2*)(hb + pr * 8 + 4);
-            const float2 dx = __fadd2_rn(make_float2(A.x, A.y), nqx);
-            const float2 dy = __fadd2_rn(make_float2(A.z, A.w), nqy);
-            const float2 dz = __fadd2_rn(Z, nqz);
-            float2 t = __ffma2_rn(dx, dx, nmid2);
-            t = __ffma2_rn(dy, dy, t);
-            t = __ffma2_rn(dz, dz, t);
+            const float2 dx = add2_rn(make_float2(A.x, A.y), nqx);
+            const float2 dy = add2_rn(make_float2(A.z, A.w), nqy);
+            const float2 dz = add2_rn(Z, nqz);
+            float2 t = fma2_rn(dx, dx, nmid2);
+            t = fma2_rn(dy, dy, t);
+            t = fma2_rn(dz, dz, t);
             bmin = fminf(bmin, fminf(fabsf(t.x), fabsf(t.y)));
             const unsigned b0 = __ballot_sync(FULL, t.x < -hw);
             const unsigned b1 = __ballot_sync(FULL, t.y < -hw);
@@ -385,12 +385,15 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_mask(const MaskA
             const float4 A = *(const float4*)(hb + pr * 8);
             const float2 Z = *(const float2*)(hb + pr * 8 + 4);
             // contract: R = (xj - xi) + cs ; r2 = (R0 R0 + R1 R1) + R2 R2, no fused operations
-            const float2 R0 = __fadd2_rn(__fadd2_rn(qx2, make_float2(-A.x, -A.y)), c0);
-            const float2 R1 = __fadd2_rn(__fadd2_rn(qy2, make_float2(-A.z, -A.w)), c1);
-            const float2 R2 = __fadd2_rn(__fadd2_rn(qz2, make_float2(-Z.x, -Z.y)), c2);
-            const float2 r2 = __fadd2_rn(__fadd2_rn(__fmul2_rn(R0, R0), __fmul2_rn(R1, R1)), __fmul2_rn(R2, R2));
-            const unsigned b0 = __ballot_sync(FULL, valid && r2.x < csqf);
-            const unsigned b1 = __ballot_sync(FULL, valid && r2.y < csqf);
+            const float2 R0 = add2_rn(add2_rn(qx2, make_float2(-A.x, -A.y)), c0);
+            const float2 R1 = add2_rn(add2_rn(qy2, make_float2(-A.z, -A.w)), c1);
+            const float2 R2 = add2_rn(add2_rn(qz2, make_float2(-Z.x, -Z.y)), c2);
+            // packed multiplies, SCALAR adds: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even with
+            // explicit .rn and -fmad=false (verified in SASS), which would break the unfused contract
+            const float2 p0 = mul2_rn(R0, R0), p1 = mul2_rn(R1, R1), p2 = mul2_rn(R2, R2);
+            const float r2x = __fadd_rn(__fadd_rn(p0.x, p1.x), p2.x), r2y = __fadd_rn(__fadd_rn(p0.y, p1.y), p2.y);
+            const unsigned b0 = __ballot_sync(FULL, valid && r2x < csqf);
+            const unsigned b1 = __ballot_sync(FULL, valid && r2y < csqf);
             *(uint2*)(mrow + 2 * pr) = make_uint2(b0, b1);
           }
         }

@@ -274,3 +274,25 @@ def test_shard_mode_rows_and_global_indices(nl):
         order = np.argsort(merged["i"], kind="stable")
         merged = dict(first=merged["first"], i=merged["i"][order], j=merged["j"][order], S=merged["S"][order], R=merged["R"][order])
         U.assert_engine_matches_oracle(merged, orc, RTOL[np.dtype(dtype)], msg="shards")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_near_threshold_decisions(nl, dtype):
+    """Rounding-sensitive decisions: 60 000 isolated dimers whose separation is within a few ulps of the
+    cutoff (both sides), in random orientations, some straddling a periodic face.  Any fused multiply-add,
+    reassociation or pre-filter slip in the kernels flips pairs here."""
+    rng = np.random.Generator(np.random.PCG64(77))
+    n_d, rc, L = 60000, 5.0, 4000.0
+    g = int(np.ceil(n_d ** (1 / 3)))
+    grid = np.stack(np.meshgrid(*[np.arange(g)] * 3, indexing="ij"), -1).reshape(-1, 3)[:n_d]
+    centres = (grid + 0.5) * (L / g)                                    # dimers ~100 A apart
+    centres[: n_d // 8, 0] = rng.random(n_d // 8) * 2.0                 # some straddle the x = 0 face
+    u = rng.normal(size=(n_d, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    eps = np.finfo(dtype).eps
+    r = rc * (1.0 + rng.integers(-6, 7, n_d) * eps)
+    X = np.concatenate([centres - 0.5 * r[:, None] * u, centres + 0.5 * r[:, None] * u]).astype(dtype)
+    C = (np.eye(3) * L).astype(dtype)
+    _, pl, orc = check_case(nl, X, rc, C, (True, True, True), dtype, msg="near threshold")
+    frac_hit = nl.npairs(pl) / (2 * n_d)
+    assert 0.2 < frac_hit < 0.8, frac_hit   # the set really straddles the threshold
