@@ -294,5 +294,7 @@ def test_near_threshold_decisions(nl, dtype):
     X = np.concatenate([centres - 0.5 * r[:, None] * u, centres + 0.5 * r[:, None] * u]).astype(dtype)
     C = (np.eye(3) * L).astype(dtype)
     _, pl, orc = check_case(nl, X, rc, C, (True, True, True), dtype, msg="near threshold")
-    frac_hit = nl.npairs(pl) / (2 * n_d)
-    assert 0.2 < frac_hit < 0.8, frac_hit   # the set really straddles the threshold
+    # the designed dimer pairs (atom k with atom k + n_d) really straddle the threshold
+    e = pl.cpu()
+    dimer = int((np.abs(e["i"].astype(np.int64) - e["j"].astype(np.int64)) == n_d).sum()) / (2 * n_d)
+    assert 0.2 < dimer < 0.8, dimer
