@@ -80,14 +80,18 @@ template <class T, class TI> struct ListArgs {
   int hl;                  // hit-list stride
   int tx, ty, tz, ntx, nty, ntz;
   float mid, hw, dguard;
+  const ListArgs<T, TI>* self;  // this struct in GLOBAL memory: the rare out-of-line paths read their inputs from there, so
+                                // the kernels never materialise parameter copies on the local-memory stack
 };
 
 __device__ __forceinline__ int pack_shift(int s0, int s1, int s2) { return (s0 + 1) | ((s1 + 1) << 2) | ((s2 + 1) << 4); }
 __device__ __forceinline__ void unpack_shift(int p, long long s[3]) { s[0] = (p & 3) - 1; s[1] = ((p >> 2) & 3) - 1; s[2] = ((p >> 4) & 3) - 1; }
 
 // The exact contract for one pair given global sorted indices; returns r2 < cutoff_sq.
-template <class T>
-__device__ __noinline__ bool exact_pair_hit(const Geo<T>& g, const Records<T>& rec, long long gi, long long gj, int shp) {
+template <class T, class TI>
+__device__ __noinline__ bool exact_pair_hit(const ListArgs<T, TI>* ad, long long gi, long long gj, int shp) {
+  const Geo<T>& g = ad->g;
+  const Records<T>& rec = ad->rec;
   const T xi = rec.px[gi], yi = rec.py[gi], zi = rec.pz[gi];
   const T xj = rec.px[gj], yj = rec.py[gj], zj = rec.pz[gj];
   long long wi[3], wj[3], sl[3];
@@ -140,8 +144,10 @@ __device__ __forceinline__ int find_vcell(const int* vstart, int NV, int sl) {
 // Rare path of the fill pass: atoms i and j carry different (or overflowed) winding numbers, so the
 // shift is S = s_loop + w_i - w_j and cell' * S is not the per-cell table entry.  Kept out of line so
 // that none of it is hoisted into the common path.
-template <class T>
-__device__ __noinline__ void slow_shift_and_R(const Geo<T>& g, T xi, T yi, T zi, T xj, T yj, T zj, uint32_t wi, uint32_t wj, int* S012, T* R012) {
+template <class T, class TI>
+__device__ __noinline__ void slow_shift_and_R(const ListArgs<T, TI>* ad, T xi, T yi, T zi, T xj, T yj, T zj, uint32_t wi, uint32_t wj, int* S012,
+                                              T* R012) {
+  const Geo<T>& g = ad->g;
   long long w_i[3], w_j[3];
   int cc[3];
   if (wi & WIND_OVERFLOW) cell_of(g, xi, yi, zi, cc, w_i); else unpack_wind(wi, w_i);
@@ -155,8 +161,8 @@ __device__ __noinline__ void slow_shift_and_R(const Geo<T>& g, T xi, T yi, T zi,
 
 // Generic per-atom route for the atoms [g0, g0 + n) of one cell (out of line: rare).
 template <class T, class TI, int MODE>
-__device__ __noinline__ void generic_cell(long long g0, int n, int lane, const Records<T>& rec, const TI* co, const Geo<T>& g, const Sinks<T, TI>& out) {
-  for (int k = lane; k < n; k += 32) generic_atom<T, TI, MODE>(g0 + k, rec, co, g, out);
+__device__ __noinline__ void generic_cell(const ListArgs<T, TI>* ad, long long g0, int n, int lane) {
+  for (int k = lane; k < n; k += 32) generic_atom<T, TI, MODE>(g0 + k, ad->rec, ad->co, ad->g, ad->out);
 }
 
 // Per-warp candidate tables of one home cell: flat candidate index -> staged slot, hit code.
@@ -249,7 +255,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_list(const ListA
       const int lx = hcell[hc] & 255, ly = (hcell[hc] >> 8) & 255, lz = hcell[hc] >> 16;
       const int vh = ((lz + 1) * VY + (ly + 1)) * VX + (lx + 1);
       const int nh = vstart[vh + 1] - vstart[vh];
-      generic_cell<T, TI, MODE_COUNT>((long long)vgs[vh], nh, lane, a.rec, a.co, g, a.out);
+      generic_cell<T, TI, MODE_COUNT>(a.self, (long long)vgs[vh], nh, lane);
       if (WANT_LIST) for (int k = lane; k < nh; k += 32) a.scount[(long long)vgs[vh] + k] = LIST_NONE;
     }
     return;
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_list(const ListA
     int my_shp, fh;
     const int ncand = build_cell_tables(vstart, vgs, vsh, VX, VY, lx, ly, lz, lane, tab, my_shp, fh);
     if (ncand > MASK_MAXCAND) {  // too many candidates for a 256-bit mask: generic route (the fill pass follows scount)
-      generic_cell<T, TI, MODE_COUNT>(hg0, nh, lane, a.rec, a.co, g, a.out);
+      generic_cell<T, TI, MODE_COUNT>(a.self, hg0, nh, lane);
       if (WANT_LIST) for (int k = lane; k < nh; k += 32) a.scount[hg0 + k] = LIST_NONE;
       continue;
     }
@@ -411,9 +417,9 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_list(const ListA
               const float dx = px - qx, dy = py - qy, dz = pz - qz;
               const float t = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, -mid)));
               hit = valid && t < -hw;
-              if (valid && (cand_bad || ((hbad >> aa) & 1u) || fabsf(t) <= hw)) hit = exact_pair_hit<T>(g, a.rec, hg0 + g0 + aa, gj, shp);
+              if (valid && (cand_bad || ((hbad >> aa) & 1u) || fabsf(t) <= hw)) hit = exact_pair_hit<T, TI>(a.self, hg0 + g0 + aa, gj, shp);
             } else {
-              hit = valid && exact_pair_hit<T>(g, a.rec, hg0 + g0 + aa, gj, shp);
+              hit = valid && exact_pair_hit<T, TI>(a.self, hg0 + g0 + aa, gj, shp);
             }
             const unsigned bal = __ballot_sync(FULL, hit);
             if (lane == 0) mrow[aa] = bal;
@@ -434,9 +440,12 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_list(const ListA
         a.out.counts[a.rec.pidx[hg0 + g0 + lane]] = c;
         if (WANT_LIST) a.scount[hg0 + g0 + lane] = c;
       }
-      // ---- masks -> hit lists, four atoms at a time (lane = 8 * atom + mask word)
+      // ---- masks -> hit lists, four atoms at a time (lane = 8 * atom + mask word).  The codes are compacted into
+      //      shared memory (reusing the slot table and the home-atom buffer, both dead by now) and written coalesced.
       if (WANT_LIST) {
         const int q = lane >> 3, sub = lane & 7;
+        const bool staged = nh <= 32;  // with several home groups the slot table must survive: write straight to global then
+        uint32_t* buf = (q < 2) ? (uint32_t*)tab.cslot + q * 64 : (uint32_t*)hb + (q - 2) * 64;
         for (int a0 = 0; a0 < ng; a0 += 4) {
           const int atom = a0 + q;
           uint32_t word = (atom < ng && sub < nchunk) ? mkT[sub * 34 + atom] : 0u;
@@ -448,15 +457,31 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_list(const ListA
             if (sub >= o) incl += t;
           }
           int pos = incl - pc;
-          uint32_t* dst = a.hits + (hg0 + g0 + atom) * (long long)a.hl;
           const uint32_t* codes = tab.ccode + sub * 32;
+          uint32_t* out = staged ? buf : a.hits + (hg0 + g0 + (atom < ng ? atom : 0)) * (long long)a.hl;
+          const int lim = staged ? 64 : a.hl;
+          __syncwarp();
           while (word) {
             const int bit = __ffs(word) - 1;
             word &= word - 1;
-            if (pos < a.hl) dst[pos] = codes[bit];
+            if (pos < lim) out[pos] = codes[bit];
             pos++;
           }
+          __syncwarp();
+          if (staged) {
+#pragma unroll
+            for (int qq = 0; qq < 4; qq++) {
+              if (a0 + qq < ng) {
+                const int cq = min((int)__shfl_sync(FULL, incl, qq * 8 + 7), min(a.hl, 64));
+                const uint32_t* src = (qq < 2) ? (const uint32_t*)tab.cslot + qq * 64 : (const uint32_t*)hb + (qq - 2) * 64;
+                uint32_t* dst = a.hits + (hg0 + g0 + a0 + qq) * (long long)a.hl;
+                if (lane < cq) dst[lane] = src[lane];
+                if (lane + 32 < cq) dst[lane + 32] = src[lane + 32];
+              }
+            }
+          }
         }
+        __syncwarp();
       }
     }
   }
@@ -480,8 +505,8 @@ template <> __device__ __forceinline__ void load_rec<float>(const RecAoS<float>*
 }
 
 template <class T, class TI>
-__device__ __noinline__ void generic_fill_one(long long s, const Records<T>& rec, const TI* co, const Geo<T>& g, const Sinks<T, TI>& out) {
-  generic_atom<T, TI, MODE_FILL>(s, rec, co, g, out);
+__device__ __noinline__ void generic_fill_one(const ListArgs<T, TI>* ad, long long s) {
+  generic_atom<T, TI, MODE_FILL>(s, ad->rec, ad->co, ad->g, ad->out);
 }
 
 constexpr int FILL_NT = 256;
@@ -505,7 +530,7 @@ __global__ void __launch_bounds__(FILL_NT, NL_FILL_MINB) k_fill_list(const ListA
     const uint32_t io = a.rec.pidx[s];
     if ((long long)io >= a.out.n_rows || cnt == 0) continue;
     if (cnt == LIST_NONE || cnt > (uint32_t)a.hl) {
-      if (lane == 0) generic_fill_one<T, TI>(s, a.rec, a.co, g, a.out);
+      if (lane == 0) generic_fill_one<T, TI>(a.self, s);
       continue;
     }
     const long long base = (long long)a.out.first[io] - 1;
@@ -544,7 +569,7 @@ __global__ void __launch_bounds__(FILL_NT, NL_FILL_MINB) k_fill_list(const ListA
         } else {
           int S3[3] = {S0, S1, S2};
           T R3[3];
-          slow_shift_and_R<T>(g, xi, yi, zi, xj, yj, zj, wi, wj, S3, R3);
+          slow_shift_and_R<T, TI>(a.self, xi, yi, zi, xj, yj, zj, wi, wj, S3, R3);
           S0 = S3[0]; S1 = S3[1]; S2 = S3[2];
           R0 = R3[0]; R1 = R3[1]; R2 = R3[2];
         }
@@ -577,6 +602,7 @@ inline void list_args(ListArgs<T, TI>& a, int64_t n, const TI* co, const Records
   a.tx = ts.tx; a.ty = ts.ty; a.tz = ts.tz;
   a.ntx = (g.nc[0] + ts.tx - 1) / ts.tx; a.nty = (g.nc[1] + ts.ty - 1) / ts.ty; a.ntz = (g.nc[2] + ts.tz - 1) / ts.tz;
   a.mid = a.hw = a.dguard = 0.f;
+  a.self = nullptr;
 }
 
 }  // namespace nl

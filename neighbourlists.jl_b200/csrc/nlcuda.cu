@@ -88,6 +88,7 @@ BuildWs build_ws(void* ws, int64_t N) {
 }
 
 struct PairWs {
+  void* hdr;
   void *px, *py, *pz;
   uint32_t *pidx, *pw, *counts;
   unsigned long long* tsum;
@@ -101,7 +102,7 @@ PairWs pair_ws(void* ws, const nl_params* prm, int64_t N) {
   size_t o = 0;
   auto take = [&](size_t b) { char* r = p ? p + o : nullptr; o += al256(b); return (void*)r; };
   size_t n1 = (size_t)(N > 0 ? N : 1);
-  take(256);  // header, reserved
+  w.hdr = take(4096);  // device copies of kernel argument blocks (rare out-of-line paths read them from here)
   w.px = take(n1 * fsize(prm));
   w.py = take(n1 * fsize(prm));
   w.pz = take(n1 * fsize(prm));
@@ -231,9 +232,14 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
     a.ra = (const RecAoS<T>*)ls.ra; a.pflag = ls.pflag; a.hits = ls.hits; a.scount = ls.scount; a.hl = LIST_HL;
     a.mid = pl.th.mid; a.hw = pl.th.hw; a.dguard = pl.th.dguard;
     const unsigned nblk = (unsigned)((long long)a.ntx * a.nty * a.ntz);
+    static_assert(sizeof(ListArgs<T, TI>) <= 1024, "argument block");
+    a.self = (const ListArgs<T, TI>*)((char*)w.hdr + (MODE == MODE_FILL ? 1024 : (want_mask ? 0 : 2048)));
+    NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
     if (MODE == MODE_FILL) {
-      const unsigned nb = (unsigned)((N + (FILL_NT / 32) - 1) / (FILL_NT / 32));
-      k_fill_list<T, TI><<<nb, FILL_NT, 0, st>>>(a);
+      // persistent grid: each warp walks over many atoms, so the per-thread prologue is paid once
+      long long nb = (N + (FILL_NT / 32) - 1) / (FILL_NT / 32);
+      if (nb > 148 * 4 * 8) nb = 148 * 4 * 8;
+      k_fill_list<T, TI><<<(unsigned)nb, FILL_NT, 0, st>>>(a);
     } else if (want_mask) {
       static bool done = false;
       int rc = set_smem_once(k_count_list<T, TI, true>, CNT_SMEM_BYTES, done);
