@@ -1,18 +1,12 @@
-// nl_mask.cuh -- the fast materialisation path: a counting pass that also records, per atom, the LIST
-// of its neighbours as compact hit codes, and a fill pass that expands the lists into (i, j, S, R)
-// rows without repeating a single distance test or touching the cell structure again.
+// nl_mask.cuh -- the fast materialisation path: a counting pass that records, per atom, a BITMASK
+// of which candidates of its 27-cell stencil are neighbours, and a fill pass that expands the
+// masks into (i, j, S, R) rows without repeating a single distance test.
 //
-// Counting pass (k_count_list).  For a home cell the 27 neighbour cells (dz outer, dy, dx inner) are
-// flattened into one candidate list; lanes run over candidates, home atoms are broadcast from shared
-// memory in pairs, and every (home atom, 32 candidates) ballot lands in a shared-memory bitmask.  At
-// the end of a cell the masks give the per-atom counts and are expanded (four atoms at a time) into
-// hit codes  code = sorted_index_of_j | stencil_cell << 27  stored at hits[sorted_atom * hl + k].
-// Cells with more than 256 candidates, and atoms with more than hl hits, are marked and take the
-// generic per-atom route in the fill pass.
-//
-// Fill pass (k_fill_list): one warp per atom, lanes over hits; j's record is one 32-byte AoS gather,
-// the periodic shift follows from the stencil cell and the home cell's boundary flags, R follows the
-// contract, and each row is transposed through shared memory into contiguous full-sector stores.
+// Candidate numbering.  For a home cell the 27 neighbour cells are visited as 9 x-rows
+// (dz outer, dy inner) of 3 x-adjacent cells; concatenating their atoms in sorted order gives the
+// "flat" candidate list of that cell (independent of tile shape).  Bit f of an atom's mask says
+// whether flat candidate f is within the cutoff.  Cells with more than 256 candidates take the
+// generic per-atom route in both passes.
 //
 // Counting pass, Float64: deciding r2 < rc2 with the contract's Float64 arithmetic for all ~173
 // candidates per atom would make the pass FP64-bound.  Instead every staged atom carries a Float32
@@ -36,6 +30,7 @@ namespace nl {
 
 constexpr int MASK_WORDS = 8;                  // 256 candidates
 constexpr int MASK_MAXCAND = 32 * MASK_WORDS;
+constexpr int CNT_SMEM_BYTES = 48 * 1024;      // count pass: 16 B per staged slot
 
 struct MaskThresholds { float mid, hw, dguard; int ok; };
 
@@ -63,35 +58,24 @@ inline MaskThresholds mask_thresholds(const double cell[9], const int nc[3], con
   return m;
 }
 
-constexpr uint32_t LIST_NONE = 0xffffffffu;   // scount marker: no hit list for this atom (generic route)
-constexpr uint32_t CODE_IDX_MASK = (1u << 27) - 1u;
-constexpr long long LIST_MAX_N = 1ll << 27;     // hit codes carry a 27-bit sorted index
-
-template <class T, class TI> struct ListArgs {
+template <class T, class TI> struct MaskArgs {
   Records<T> rec;
-  const RecAoS<T>* ra;     // AoS records, sorted order
-  const uint8_t* pflag;    // per sorted atom: periodic-boundary flags of its cell (bit 2k: first plane, 2k+1: last plane of axis k)
   const TI* co;
   long long n;
   Geo<T> g;
   Sinks<T, TI> out;
-  uint32_t* hits;          // n * hl hit codes, sorted order
-  uint32_t* scount;        // n: neighbours of each sorted atom, or LIST_NONE
-  int hl;                  // hit-list stride
+  uint32_t* masks;    // n * MASK_WORDS, sorted order
+  uint8_t* cellflag;  // per cell: 1 if the count pass stored masks for its atoms
   int tx, ty, tz, ntx, nty, ntz;
   float mid, hw, dguard;
-  const ListArgs<T, TI>* self;  // this struct in GLOBAL memory: the rare out-of-line paths read their inputs from there, so
-                                // the kernels never materialise parameter copies on the local-memory stack
 };
 
 __device__ __forceinline__ int pack_shift(int s0, int s1, int s2) { return (s0 + 1) | ((s1 + 1) << 2) | ((s2 + 1) << 4); }
 __device__ __forceinline__ void unpack_shift(int p, long long s[3]) { s[0] = (p & 3) - 1; s[1] = ((p >> 2) & 3) - 1; s[2] = ((p >> 4) & 3) - 1; }
 
 // The exact contract for one pair given global sorted indices; returns r2 < cutoff_sq.
-template <class T, class TI>
-__device__ __noinline__ bool exact_pair_hit(const ListArgs<T, TI>* ad, long long gi, long long gj, int shp) {
-  const Geo<T>& g = ad->g;
-  const Records<T>& rec = ad->rec;
+template <class T>
+__device__ __noinline__ bool exact_pair_hit(const Geo<T>& g, const Records<T>& rec, long long gi, long long gj, int shp) {
   const T xi = rec.px[gi], yi = rec.py[gi], zi = rec.pz[gi];
   const T xj = rec.px[gj], yj = rec.py[gj], zj = rec.pz[gj];
   long long wi[3], wj[3], sl[3];
@@ -144,10 +128,8 @@ __device__ __forceinline__ int find_vcell(const int* vstart, int NV, int sl) {
 // Rare path of the fill pass: atoms i and j carry different (or overflowed) winding numbers, so the
 // shift is S = s_loop + w_i - w_j and cell' * S is not the per-cell table entry.  Kept out of line so
 // that none of it is hoisted into the common path.
-template <class T, class TI>
-__device__ __noinline__ void slow_shift_and_R(const ListArgs<T, TI>* ad, T xi, T yi, T zi, T xj, T yj, T zj, uint32_t wi, uint32_t wj, int* S012,
-                                              T* R012) {
-  const Geo<T>& g = ad->g;
+template <class T>
+__device__ __noinline__ void slow_shift_and_R(const Geo<T>& g, T xi, T yi, T zi, T xj, T yj, T zj, uint32_t wi, uint32_t wj, int* S012, T* R012) {
   long long w_i[3], w_j[3];
   int cc[3];
   if (wi & WIND_OVERFLOW) cell_of(g, xi, yi, zi, cc, w_i); else unpack_wind(wi, w_i);
@@ -161,53 +143,50 @@ __device__ __noinline__ void slow_shift_and_R(const ListArgs<T, TI>* ad, T xi, T
 
 // Generic per-atom route for the atoms [g0, g0 + n) of one cell (out of line: rare).
 template <class T, class TI, int MODE>
-__device__ __noinline__ void generic_cell(const ListArgs<T, TI>* ad, long long g0, int n, int lane) {
-  for (int k = lane; k < n; k += 32) generic_atom<T, TI, MODE>(g0 + k, ad->rec, ad->co, ad->g, ad->out);
+__device__ __noinline__ void generic_cell(long long g0, int n, int lane, const Records<T>& rec, const TI* co, const Geo<T>& g, const Sinks<T, TI>& out) {
+  for (int k = lane; k < n; k += 32) generic_atom<T, TI, MODE>(g0 + k, rec, co, g, out);
 }
 
-// Per-warp candidate tables of one home cell: flat candidate index -> staged slot, hit code.
+// Per-warp candidate tables of one home cell: flat candidate index -> staged slot / virtual cell.
 struct CellTables {
   uint16_t* cslot;  // [MASK_MAXCAND]
-  uint32_t* ccode;  // [MASK_MAXCAND] sorted index | stencil cell << 27
+  uint8_t* cv;      // [MASK_MAXCAND] virtual cell id (count pass) or stencil cell index 0..26 (fill pass)
 };
-constexpr int CELLTAB_BYTES = MASK_MAXCAND * 6;
+constexpr int CELLTAB_BYTES = MASK_MAXCAND * 3;
 
 // Builds the tables for home cell (lx, ly, lz) of the tile; returns the number of candidates
 // (tables are valid only if it is <= MASK_MAXCAND).  Lane c < 27 owns neighbour cell
 // c = (dz+1)*9 + (dy+1)*3 + (dx+1); flat order = cell order, then sorted order inside the cell.
-// my_shp (lanes < 27): packed periodic shift of that neighbour cell; fh: flat index of the home cell's first atom.
-__device__ __forceinline__ int build_cell_tables(const int* vstart, const int* vgs, const int* vsh, int VX, int VY, int lx, int ly, int lz,
-                                                 int lane, const CellTables& t, int& my_shp, int& fh) {
-  int st = 0, cn = 0, gs = 0;
-  my_shp = 0;
+template <bool STORE_STENCIL_INDEX>
+__device__ __forceinline__ int build_cell_tables(const int* vstart, int VX, int VY, int lx, int ly, int lz, int lane, const CellTables& t) {
+  int v = 0, st = 0, cn = 0;
   if (lane < 27) {
-    const int v = ((lz + lane / 9) * VY + (ly + (lane / 3) % 3)) * VX + (lx + lane % 3);
+    v = ((lz + lane / 9) * VY + (ly + (lane / 3) % 3)) * VX + (lx + lane % 3);
     st = vstart[v];
     cn = vstart[v + 1] - st;
-    gs = vgs[v];
-    my_shp = vsh[v];
   }
   const int incl = warp_incl_scan(cn, lane);
   const int ncand = __shfl_sync(FULL, incl, 31);
-  fh = __shfl_sync(FULL, incl - cn, 13);
   if (ncand <= MASK_MAXCAND) {
     const int pre = incl - cn;
     const int mx = __reduce_max_sync(FULL, cn);
-    const uint32_t hi = (uint32_t)lane << 27;
     for (int j = 0; j < mx; j++)
-      if (j < cn) { t.cslot[pre + j] = (uint16_t)(st + j); t.ccode[pre + j] = (uint32_t)(gs + j) | hi; }
+      if (j < cn) { t.cslot[pre + j] = (uint16_t)(st + j); t.cv[pre + j] = (uint8_t)(STORE_STENCIL_INDEX ? lane : v); }
   }
   __syncwarp();
   return ncand;
 }
 
+__device__ __forceinline__ long long cell_linear(const int nc[3], int cx, int cy, int cz) {
+  return (long long)cx + (long long)nc[0] * ((long long)cy + (long long)nc[1] * cz);
+}
+
 // ------------------------------------------------------------------------------------------------
-// Counting pass.  WANT_LIST: also store the hit lists for the fill pass.
+// Counting pass.  WANT_MASK: also store the hit masks (and per-cell flags) for the fill pass.
 //
 // Shared memory: tile tables | per-warp {cell tables, chunk-major mask words, home-atom pair buffer} |
 // float4 per staged slot: Float64 -> (q.xyz = Float32 image-relative position, w = 1 if the slot needs
 // the exact path); Float32 -> (absolute x, y, z, packed winding).
-constexpr int CNT_SMEM_BYTES = 56 * 1024;
 constexpr int CNT_WARP_BYTES = CELLTAB_BYTES + MASK_WORDS * 34 * 4 + 16 * 32;
 constexpr int CNT_FIXED_BYTES = 3 * TILE_VPAD * 4 + 64 * 4 + (TILE_NT / 32) * CNT_WARP_BYTES;
 constexpr int CNT_CAP2 = (CNT_SMEM_BYTES - CNT_FIXED_BYTES) / 16 / 8 * 8;
@@ -219,8 +198,8 @@ constexpr float SLOT_FAR = -1.0e18f;  // staged slots that need the exact path: 
 #ifndef NL_CNT_MINB
 #define NL_CNT_MINB 4
 #endif
-template <class T, class TI, bool WANT_LIST>
-__global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_list(const ListArgs<T, TI> a) {
+template <class T, class TI, bool WANT_MASK>
+__global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_mask(const MaskArgs<T, TI> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* vstart = (int*)smem_raw;
   int* vgs = vstart + TILE_VPAD;
@@ -236,9 +215,9 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_list(const ListA
   unsigned char* wb = wbase + wid * CNT_WARP_BYTES;
   CellTables tab;
   tab.cslot = (uint16_t*)wb;
-  tab.ccode = (uint32_t*)(wb + MASK_MAXCAND * 2);
+  tab.cv = (uint8_t*)(wb + MASK_MAXCAND * 2);
   uint32_t* mkT = (uint32_t*)(wb + CELLTAB_BYTES);                          // [MASK_WORDS][34]: word kc of home atom aa at kc*34 + aa
-  float* hb = (float*)(wb + CELLTAB_BYTES + MASK_WORDS * 34 * 4);           // [16 pairs][8]: x0 x1 y0 y1 z0 z1 - -
+  float* hb = (float*)(wb + CELLTAB_BYTES + MASK_WORDS * 34 * 4);           // [16 pairs][8]: x0 x1 y0 y1 z0 z1 f0 f1
 
   const int b = blockIdx.x;
   const int hx0 = (b % a.ntx) * a.tx, hy0 = ((b / a.ntx) % a.nty) * a.ty, hz0 = (b / (a.ntx * a.nty)) * a.tz;
@@ -250,13 +229,13 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_list(const ListA
   if (tid == 0) s_next = 0;
   __syncthreads();
 
-  if (total > CNT_CAP2) {  // denser than the staging capacity: generic route, no lists
+  if (total > CNT_CAP2) {
     for (int hc = wid; hc < nhome; hc += TILE_NT / 32) {
       const int lx = hcell[hc] & 255, ly = (hcell[hc] >> 8) & 255, lz = hcell[hc] >> 16;
       const int vh = ((lz + 1) * VY + (ly + 1)) * VX + (lx + 1);
       const int nh = vstart[vh + 1] - vstart[vh];
-      generic_cell<T, TI, MODE_COUNT>(a.self, (long long)vgs[vh], nh, lane);
-      if (WANT_LIST) for (int k = lane; k < nh; k += 32) a.scount[(long long)vgs[vh] + k] = LIST_NONE;
+      generic_cell<T, TI, MODE_COUNT>((long long)vgs[vh], nh, lane, a.rec, a.co, g, a.out);
+      if (WANT_MASK && lane == 0) a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)] = 0;
     }
     return;
   }
@@ -311,14 +290,24 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_list(const ListA
     const int hstart = vstart[vh], nh = vstart[vh + 1] - hstart;
     if (nh == 0) continue;
     const long long hg0 = vgs[vh];
-    int my_shp, fh;
-    const int ncand = build_cell_tables(vstart, vgs, vsh, VX, VY, lx, ly, lz, lane, tab, my_shp, fh);
-    if (ncand > MASK_MAXCAND) {  // too many candidates for a 256-bit mask: generic route (the fill pass follows scount)
-      generic_cell<T, TI, MODE_COUNT>(a.self, hg0, nh, lane);
-      if (WANT_LIST) for (int k = lane; k < nh; k += 32) a.scount[hg0 + k] = LIST_NONE;
+    const int ncand = build_cell_tables<false>(vstart, VX, VY, lx, ly, lz, lane, tab);
+    if (WANT_MASK && lane == 0) a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)] = ncand <= MASK_MAXCAND ? 1 : 0;
+    if (ncand > MASK_MAXCAND) {  // too many candidates for a 256-bit mask: generic route (the fill pass does the same)
+      generic_cell<T, TI, MODE_COUNT>(hg0, nh, lane, a.rec, a.co, g, a.out);
       continue;
     }
     const int nchunk = (ncand + 31) >> 5;
+    int fh;  // flat index of home atom 0 as a candidate (cell 13 of the stencil): used to drop the self pair
+    {
+      int cn = 0;
+      if (lane < 13) {
+        const int v = ((lz + lane / 9) * VY + (ly + (lane / 3) % 3)) * VX + (lx + lane % 3);
+        cn = vstart[v + 1] - vstart[v];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) cn += __shfl_xor_sync(FULL, cn, o);
+      fh = cn;
+    }
 
     for (int g0 = 0; g0 < nh; g0 += 32) {
       const int ng = min(32, nh - g0);
@@ -346,14 +335,15 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_list(const ListA
       for (int kc = 0; kc < nchunk; kc++) {
         const int f = kc * 32 + lane;
         const bool valid = f < ncand;
-        const uint32_t code = valid ? tab.ccode[f] : 0u;
-        const int gj = (int)(code & CODE_IDX_MASK);
-        const int shp = __shfl_sync(FULL, my_shp, (int)(code >> 27));
+        int gj = 0, shp = 0;
         float qx = CAND_FAR, qy = CAND_FAR, qz = CAND_FAR;
         float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f;
         bool cand_bad = false;
         if (valid) {
-          const float4 q = sq[tab.cslot[f]];
+          const int slot = tab.cslot[f], v = tab.cv[f];
+          gj = vgs[v] + (slot - vstart[v]);
+          shp = vsh[v];
+          const float4 q = sq[slot];
           qx = q.x; qy = q.y; qz = q.z;
           if constexpr (sizeof(T) == 8) {
             cand_bad = q.w != 0.f;
@@ -417,9 +407,9 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_list(const ListA
               const float dx = px - qx, dy = py - qy, dz = pz - qz;
               const float t = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, -mid)));
               hit = valid && t < -hw;
-              if (valid && (cand_bad || ((hbad >> aa) & 1u) || fabsf(t) <= hw)) hit = exact_pair_hit<T, TI>(a.self, hg0 + g0 + aa, gj, shp);
+              if (valid && (cand_bad || ((hbad >> aa) & 1u) || fabsf(t) <= hw)) hit = exact_pair_hit<T>(g, a.rec, hg0 + g0 + aa, gj, shp);
             } else {
-              hit = valid && exact_pair_hit<T, TI>(a.self, hg0 + g0 + aa, gj, shp);
+              hit = valid && exact_pair_hit<T>(g, a.rec, hg0 + g0 + aa, gj, shp);
             }
             const unsigned bal = __ballot_sync(FULL, hit);
             if (lane == 0) mrow[aa] = bal;
@@ -433,176 +423,235 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_list(const ListA
         }
       }
       __syncwarp();
-      // ---- per-atom counts from the masks
-      uint32_t c = 0;
+      // per-atom counts from the masks; masks to global (atom-major, MASK_WORDS per atom)
       if (lane < ng) {
+        uint32_t c = 0;
         for (int k = 0; k < nchunk; k++) c += __popc(mkT[k * 34 + lane]);
         a.out.counts[a.rec.pidx[hg0 + g0 + lane]] = c;
-        if (WANT_LIST) a.scount[hg0 + g0 + lane] = c;
       }
-      // ---- masks -> hit lists, four atoms at a time (lane = 8 * atom + mask word).  The codes are compacted into
-      //      shared memory (reusing the slot table and the home-atom buffer, both dead by now) and written coalesced.
-      if (WANT_LIST) {
-        const int q = lane >> 3, sub = lane & 7;
-        const bool staged = nh <= 32;  // with several home groups the slot table must survive: write straight to global then
-        uint32_t* buf = (q < 2) ? (uint32_t*)tab.cslot + q * 64 : (uint32_t*)hb + (q - 2) * 64;
-        for (int a0 = 0; a0 < ng; a0 += 4) {
-          const int atom = a0 + q;
-          uint32_t word = (atom < ng && sub < nchunk) ? mkT[sub * 34 + atom] : 0u;
-          const int pc = __popc(word);
-          int incl = pc;
-#pragma unroll
-          for (int o = 1; o < 8; o <<= 1) {
-            const int t = __shfl_up_sync(FULL, incl, o, 8);
-            if (sub >= o) incl += t;
-          }
-          int pos = incl - pc;
-          const uint32_t* codes = tab.ccode + sub * 32;
-          uint32_t* out = staged ? buf : a.hits + (hg0 + g0 + (atom < ng ? atom : 0)) * (long long)a.hl;
-          const int lim = staged ? 64 : a.hl;
-          __syncwarp();
-          while (word) {
-            const int bit = __ffs(word) - 1;
-            word &= word - 1;
-            if (pos < lim) out[pos] = codes[bit];
-            pos++;
-          }
-          __syncwarp();
-          if (staged) {
-#pragma unroll
-            for (int qq = 0; qq < 4; qq++) {
-              if (a0 + qq < ng) {
-                const int cq = min((int)__shfl_sync(FULL, incl, qq * 8 + 7), min(a.hl, 64));
-                const uint32_t* src = (qq < 2) ? (const uint32_t*)tab.cslot + qq * 64 : (const uint32_t*)hb + (qq - 2) * 64;
-                uint32_t* dst = a.hits + (hg0 + g0 + a0 + qq) * (long long)a.hl;
-                if (lane < cq) dst[lane] = src[lane];
-                if (lane + 32 < cq) dst[lane + 32] = src[lane + 32];
-              }
-            }
-          }
-        }
-        __syncwarp();
+      if (WANT_MASK) {
+        uint32_t* dst = a.masks + (hg0 + g0) * MASK_WORDS;
+        for (int w = lane; w < ng * MASK_WORDS; w += 32) dst[w] = (w & 7) < nchunk ? mkT[(w & 7) * 34 + (w >> 3)] : 0u;
       }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// Fill pass: one warp per sorted atom, lanes over its hit list.
-template <class T> __device__ __forceinline__ void load_rec(const RecAoS<T>* p, T& x, T& y, T& z, uint32_t& idx, uint32_t& w);
-template <> __device__ __forceinline__ void load_rec<double>(const RecAoS<double>* p, double& x, double& y, double& z, uint32_t& idx, uint32_t& w) {
-  const uint4 lo = __ldg((const uint4*)p), hi = __ldg((const uint4*)p + 1);
-  x = __hiloint2double((int)lo.y, (int)lo.x);
-  y = __hiloint2double((int)lo.w, (int)lo.z);
-  z = __hiloint2double((int)hi.y, (int)hi.x);
-  idx = hi.z; w = hi.w;
-}
-template <> __device__ __forceinline__ void load_rec<float>(const RecAoS<float>* p, float& x, float& y, float& z, uint32_t& idx, uint32_t& w) {
-  const uint4 lo = __ldg((const uint4*)p);
-  x = __uint_as_float(lo.x); y = __uint_as_float(lo.y); z = __uint_as_float(lo.z);
-  idx = lo.w;
-  w = __ldg((const uint32_t*)p + 4);
-}
+// Fill pass: expands the masks.  Stages full records (positions in T, original index, winding).
+// Four atoms' masks are compacted at once (lane = 8*atom + word); each atom's row is then produced
+// by the whole warp, transposed through shared memory and written with contiguous full-sector stores.
+#ifndef NL_FILL_SMEM_KB
+#define NL_FILL_SMEM_KB 100
+#endif
+constexpr int FILL_SMEM_BYTES = NL_FILL_SMEM_KB * 1024;
+constexpr int FILL_WARP_BYTES = CELLTAB_BYTES + 4 * MASK_MAXCAND + 32 * 3 * 4 + 32 * 3 * 8 + 28 * 3 * 8;  // tables | 4 hit lists | S stage | R stage | cs table
+constexpr int FILL_FIXED_BYTES = 3 * TILE_VPAD * 4 + 64 * 4 + (TILE_NT / 32) * FILL_WARP_BYTES;
+template <class T> __host__ __device__ constexpr int fill_cap() { return (FILL_SMEM_BYTES - FILL_FIXED_BYTES) / TileRecBytes<T>::value / 8 * 8; }
+static_assert(FILL_WARP_BYTES % 16 == 0 && FILL_FIXED_BYTES % 16 == 0, "alignment");
 
-template <class T, class TI>
-__device__ __noinline__ void generic_fill_one(const ListArgs<T, TI>* ad, long long s) {
-  generic_atom<T, TI, MODE_FILL>(s, ad->rec, ad->co, ad->g, ad->out);
-}
-
-constexpr int FILL_NT = 256;
 #ifndef NL_FILL_MINB
-#define NL_FILL_MINB 4
+#define NL_FILL_MINB 2
 #endif
 template <class T, class TI>
-__global__ void __launch_bounds__(FILL_NT, NL_FILL_MINB) k_fill_list(const ListArgs<T, TI> a) {
-  __shared__ int stS_all[FILL_NT / 32][96];
-  __shared__ T stR_all[FILL_NT / 32][96];
-  const Geo<T>& g = a.g;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  int* stS = stS_all[wid];
-  T* stR = stR_all[wid];
-  T cz0, cz1, cz2;  // cell' * (0,0,0) under the contract (keeps the sign-of-zero behaviour of the reference expression)
-  mtv(g.cell, (T)0, (T)0, (T)0, cz0, cz1, cz2);
-  const long long nwarps = (long long)gridDim.x * (FILL_NT / 32);
+__global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskArgs<T, TI> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int CAP = fill_cap<T>();
+  int* vstart = (int*)smem_raw;
+  int* vgs = vstart + TILE_VPAD;
+  int* vsh = vgs + TILE_VPAD;
+  int* hcell = vsh + TILE_VPAD;
+  unsigned char* wbase = (unsigned char*)(hcell + 64);
+  T* sx = (T*)(wbase + (TILE_NT / 32) * FILL_WARP_BYTES);
+  T* sy = sx + CAP;
+  T* sz = sy + CAP;
+  uint32_t* sidx = (uint32_t*)(sz + CAP);
+  uint32_t* sw = sidx + CAP;
+  __shared__ int scan_sm[33];
+  __shared__ int s_next;
 
-  for (long long s = (long long)blockIdx.x * (FILL_NT / 32) + wid; s < a.n; s += nwarps) {
-    const uint32_t cnt = a.scount[s];
-    const uint32_t io = a.rec.pidx[s];
-    if ((long long)io >= a.out.n_rows || cnt == 0) continue;
-    if (cnt == LIST_NONE || cnt > (uint32_t)a.hl) {
-      if (lane == 0) generic_fill_one<T, TI>(a.self, s);
+  const Geo<T>& g = a.g;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int grp = lane >> 3, sub = lane & 7;
+  unsigned char* wb = wbase + wid * FILL_WARP_BYTES;
+  CellTables tab;
+  tab.cslot = (uint16_t*)wb;
+  tab.cv = (uint8_t*)(wb + MASK_MAXCAND * 2);
+  uint8_t* lists = wb + CELLTAB_BYTES;                                        // [4][MASK_MAXCAND]
+  int* stS = (int*)(wb + CELLTAB_BYTES + 4 * MASK_MAXCAND);                   // [32][3] shifts of the current row segment
+  T* stR = (T*)(wb + CELLTAB_BYTES + 4 * MASK_MAXCAND + 32 * 3 * 4);          // [32][3] R of the current row segment
+  T* cst = (T*)(wb + CELLTAB_BYTES + 4 * MASK_MAXCAND + 32 * 3 * 4 + 32 * 3 * 8);  // [27][3] cell' * s_loop per stencil cell
+
+  const int b = blockIdx.x;
+  const int hx0 = (b % a.ntx) * a.tx, hy0 = ((b / a.ntx) % a.nty) * a.ty, hz0 = (b / (a.ntx * a.nty)) * a.tz;
+  const int hxn = min(a.tx, g.nc[0] - hx0), hyn = min(a.ty, g.nc[1] - hy0), hzn = min(a.tz, g.nc[2] - hz0);
+  const int VX = hxn + 2, VY = hyn + 2, VZ = hzn + 2, NV = VX * VY * VZ;
+  const int total = tile_table<T, TI>(g, a.co, hx0, hy0, hz0, VX, VY, NV, vstart, vgs, vsh, scan_sm);
+  const int nhome = hxn * hyn * hzn;
+  if (tid < nhome) hcell[tid] = (tid % hxn) | (((tid / hxn) % hyn) << 8) | ((tid / (hxn * hyn)) << 16);
+  if (tid == 0) s_next = 0;
+  __syncthreads();
+
+  if (total > CAP) {
+    // denser than the staging capacity: the generic route needs no masks
+    for (int hc = wid; hc < nhome; hc += TILE_NT / 32) {
+      const int lx = hcell[hc] & 255, ly = (hcell[hc] >> 8) & 255, lz = hcell[hc] >> 16;
+      const int vh = ((lz + 1) * VY + (ly + 1)) * VX + (lx + 1);
+      const int nh = vstart[vh + 1] - vstart[vh];
+      generic_cell<T, TI, MODE_FILL>((long long)vgs[vh], nh, lane, a.rec, a.co, g, a.out);
+    }
+    return;
+  }
+  for (int sl = tid; sl < total; sl += TILE_NT) {
+    const int v = find_vcell(vstart, NV, sl);
+    const long long src = (long long)vgs[v] + (sl - vstart[v]);
+    sx[sl] = a.rec.px[src];
+    sy[sl] = a.rec.py[src];
+    sz[sl] = a.rec.pz[src];
+    sidx[sl] = a.rec.pidx[src];
+    sw[sl] = a.rec.pw[src];
+  }
+  __syncthreads();
+
+  while (true) {
+    int hc = 0;
+    if (lane == 0) hc = atomicAdd(&s_next, 1);
+    hc = __shfl_sync(FULL, hc, 0);
+    if (hc >= nhome) break;
+    const int lx = hcell[hc] & 255, ly = (hcell[hc] >> 8) & 255, lz = hcell[hc] >> 16;
+    const int vh = ((lz + 1) * VY + (ly + 1)) * VX + (lx + 1);
+    const int hstart = vstart[vh], nh = vstart[vh + 1] - hstart;
+    if (nh == 0) continue;
+    const long long hg0 = vgs[vh];
+    if (!a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)]) {
+      generic_cell<T, TI, MODE_FILL>(hg0, nh, lane, a.rec, a.co, g, a.out);
       continue;
     }
-    const long long base = (long long)a.out.first[io] - 1;
-    const int fl = a.pflag[s];
-    T xi, yi, zi;
-    uint32_t ii, wi;
-    load_rec<T>(a.ra + s, xi, yi, zi, ii, wi);
-    const TI io_out = out_index(a.out, io);
-    TI* const io_row = a.out.io + base;
-    TI* const jo_row = a.out.jo + base;
-    TI* const So_row = a.out.So + 3 * base;
-    T* const Ro_row = a.out.Ro ? a.out.Ro + 3 * base : nullptr;
-    const uint32_t* L = a.hits + s * (long long)a.hl;
+    build_cell_tables<true>(vstart, VX, VY, lx, ly, lz, lane, tab);
+    // lane c < 27: packed periodic shift of stencil cell c and its shift vector cs = cell' * s_loop (contract arithmetic)
+    int my_shp = 0;
+    if (lane < 27) {
+      const int v = ((lz + lane / 9) * VY + (ly + (lane / 3) % 3)) * VX + (lx + lane % 3);
+      my_shp = vsh[v];
+      T c0, c1, c2;
+      mtv(g.cell, (T)((my_shp & 3) - 1), (T)(((my_shp >> 2) & 3) - 1), (T)(((my_shp >> 4) & 3) - 1), c0, c1, c2);
+      cst[3 * lane] = c0; cst[3 * lane + 1] = c1; cst[3 * lane + 2] = c2;
+    }
+    __syncwarp();
 
-    for (int r0 = 0; r0 < (int)cnt; r0 += 32) {
-      const int r = r0 + lane;
-      const int nr = min(32, (int)cnt - r0);
-      if (r < (int)cnt) {
-        const uint32_t code = L[r];
-        const int c = (int)(code >> 27);
-        T xj, yj, zj;
-        uint32_t jo, wj;
-        load_rec<T>(a.ra + (code & CODE_IDX_MASK), xj, yj, zj, jo, wj);
-        // stencil cell c = (dz+1)*9 + (dy+1)*3 + (dx+1); the shift is non-zero only across a periodic face
-        const int dz = (c * 57) >> 9, rem = c - dz * 9, dy = (rem * 171) >> 9, dx = rem - dy * 3;  // each in {0,1,2}
-        int S0 = (dx == 0 && (fl & 1)) ? -1 : ((dx == 2 && (fl & 2)) ? 1 : 0);
-        int S1 = (dy == 0 && (fl & 4)) ? -1 : ((dy == 2 && (fl & 8)) ? 1 : 0);
-        int S2 = (dz == 0 && (fl & 16)) ? -1 : ((dz == 2 && (fl & 32)) ? 1 : 0);
-        T R0, R1, R2;
-        if (wi == wj && !(wi & WIND_OVERFLOW)) {
-          T c0 = cz0, c1 = cz1, c2 = cz2;
-          if ((S0 | S1 | S2) != 0) mtv(g.cell, (T)S0, (T)S1, (T)S2, c0, c1, c2);
-          R0 = add_rn(sub_rn(xj, xi), c0);
-          R1 = add_rn(sub_rn(yj, yi), c1);
-          R2 = add_rn(sub_rn(zj, zi), c2);
-        } else {
-          int S3[3] = {S0, S1, S2};
-          T R3[3];
-          slow_shift_and_R<T, TI>(a.self, xi, yi, zi, xj, yj, zj, wi, wj, S3, R3);
-          S0 = S3[0]; S1 = S3[1]; S2 = S3[2];
-          R0 = R3[0]; R1 = R3[1]; R2 = R3[2];
-        }
-        stS[3 * lane] = S0; stS[3 * lane + 1] = S1; stS[3 * lane + 2] = S2;
-        if (Ro_row) { stR[3 * lane] = R0; stR[3 * lane + 1] = R1; stR[3 * lane + 2] = R2; }
-        io_row[r] = io_out;
-        jo_row[r] = out_index(a.out, jo);
+    // prefetch of the first pass
+    uint32_t nx_word = 0, nx_io = 0;
+    long long nx_base = 0;
+    if (grp < nh) {
+      nx_io = sidx[hstart + grp];
+      if ((long long)nx_io < a.out.n_rows) {  // atoms without a row (halo atoms of a shard) expand to nothing
+        nx_word = a.masks[(hg0 + grp) * MASK_WORDS + sub];
+        nx_base = (long long)a.out.first[nx_io] - 1;
       }
-      __syncwarp();
-      // transposed, contiguous stores of the row segment [r0, r0 + nr): 3 nr words of S, 3 nr of R
-      const int nw = 3 * nr;
+    }
+
+    for (int a0 = 0; a0 < nh; a0 += 4) {
+      // ---- four atoms at once: lane = 8 * atom + mask word
+      uint32_t word = nx_word;
+      const uint32_t my_io = nx_io;
+      const long long my_base = nx_base;
+      nx_word = 0;
+      if (a0 + 4 + grp < nh) {  // next pass in flight while this one is expanded
+        nx_io = sidx[hstart + a0 + 4 + grp];
+        if ((long long)nx_io < a.out.n_rows) {
+          nx_word = a.masks[(hg0 + a0 + 4 + grp) * MASK_WORDS + sub];
+          nx_base = (long long)a.out.first[nx_io] - 1;
+        }
+      }
+      const int pc = __popc(word);
+      int incl = pc;
 #pragma unroll
-      for (int m = 0; m < 3; m++) {
-        const int w = m * 32 + lane;
-        if (w < nw) {
-          So_row[3 * r0 + w] = (TI)stS[w];
-          if (Ro_row) Ro_row[3 * r0 + w] = stR[w];
+      for (int o = 1; o < 8; o <<= 1) {
+        const int t = __shfl_up_sync(FULL, incl, o, 8);
+        if (sub >= o) incl += t;
+      }
+      const int my_nhit = __shfl_sync(FULL, incl, 7, 8);
+      __syncwarp();
+      {
+        uint8_t* L = lists + grp * MASK_MAXCAND + (incl - pc);
+        const int fb = sub * 32;
+        while (word) {
+          const int bit = __ffs(word) - 1;
+          word &= word - 1;
+          *L++ = (uint8_t)(fb + bit);
         }
       }
       __syncwarp();
+
+      const int na = min(4, nh - a0);
+      for (int q = 0; q < na; q++) {
+        const int hs = hstart + a0 + q;
+        const int nhit = __shfl_sync(FULL, my_nhit, q * 8);
+        if (nhit == 0) continue;
+        const uint32_t io = __shfl_sync(FULL, my_io, q * 8);
+        const long long base = __shfl_sync(FULL, my_base, q * 8);
+        const TI io_out = out_index(a.out, io);
+        const T xi = sx[hs], yi = sy[hs], zi = sz[hs];
+        const uint32_t wi = sw[hs];
+        const uint8_t* L = lists + q * MASK_MAXCAND;
+        TI* const io_row = a.out.io + base;
+        TI* const jo_row = a.out.jo + base;
+        TI* const So_row = a.out.So + 3 * base;
+        T* const Ro_row = a.out.Ro ? a.out.Ro + 3 * base : nullptr;
+
+        for (int r0 = 0; r0 < nhit; r0 += 32) {
+          const int r = r0 + lane;
+          const int nr = min(32, nhit - r0);
+          const bool act = r < nhit;
+          const int f = act ? (int)L[r] : 0;
+          const int slot = tab.cslot[f], c = tab.cv[f];  // c: stencil cell index (dz+1)*9 + (dy+1)*3 + (dx+1)
+          const int shp = __shfl_sync(FULL, my_shp, c);
+          if (act) {
+            const T xj = sx[slot], yj = sy[slot], zj = sz[slot];
+            const uint32_t wj = sw[slot];
+            int S0 = (shp & 3) - 1, S1 = ((shp >> 2) & 3) - 1, S2 = ((shp >> 4) & 3) - 1;
+            T R0, R1, R2;
+            if (wi == wj && !(wi & WIND_OVERFLOW)) {
+              R0 = add_rn(sub_rn(xj, xi), cst[3 * c]);
+              R1 = add_rn(sub_rn(yj, yi), cst[3 * c + 1]);
+              R2 = add_rn(sub_rn(zj, zi), cst[3 * c + 2]);
+            } else {
+              int S3[3] = {S0, S1, S2};
+              T R3[3];
+              slow_shift_and_R<T>(g, xi, yi, zi, xj, yj, zj, wi, wj, S3, R3);
+              S0 = S3[0]; S1 = S3[1]; S2 = S3[2];
+              R0 = R3[0]; R1 = R3[1]; R2 = R3[2];
+            }
+            stS[3 * lane] = S0; stS[3 * lane + 1] = S1; stS[3 * lane + 2] = S2;
+            if (Ro_row) { stR[3 * lane] = R0; stR[3 * lane + 1] = R1; stR[3 * lane + 2] = R2; }
+            io_row[r] = io_out;
+            jo_row[r] = out_index(a.out, sidx[slot]);
+          }
+          __syncwarp();
+          // transposed, contiguous stores of the row segment [r0, r0 + nr): 3 nr words of S, 3 nr of R
+          const int nw = 3 * nr;
+#pragma unroll
+          for (int m = 0; m < 3; m++) {
+            const int w = m * 32 + lane;
+            if (w < nw) {
+              So_row[3 * r0 + w] = (TI)stS[w];
+              if (Ro_row) Ro_row[3 * r0 + w] = stR[w];
+            }
+          }
+          __syncwarp();
+        }
+      }
     }
   }
 }
 
 template <class T, class TI>
-inline void list_args(ListArgs<T, TI>& a, int64_t n, const TI* co, const Records<T>& rec, const Geo<T>& g, const Sinks<T, TI>& sk,
-                      const TileShape& ts) {
-  a.rec = rec; a.co = co; a.n = n; a.g = g; a.out = sk;
-  a.ra = nullptr; a.pflag = nullptr; a.hits = nullptr; a.scount = nullptr; a.hl = 64;
+inline void mask_args(MaskArgs<T, TI>& a, int64_t n, const TI* co, const Records<T>& rec, const Geo<T>& g, const Sinks<T, TI>& sk,
+                      const TileShape& ts, uint32_t* masks) {
+  a.rec = rec; a.co = co; a.n = n; a.g = g; a.out = sk; a.masks = masks; a.cellflag = nullptr;
   a.tx = ts.tx; a.ty = ts.ty; a.tz = ts.tz;
   a.ntx = (g.nc[0] + ts.tx - 1) / ts.tx; a.nty = (g.nc[1] + ts.ty - 1) / ts.ty; a.ntz = (g.nc[2] + ts.tz - 1) / ts.tz;
   a.mid = a.hw = a.dguard = 0.f;
-  a.self = nullptr;
 }
 
 }  // namespace nl

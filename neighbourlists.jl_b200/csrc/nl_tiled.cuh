@@ -61,20 +61,10 @@ template <class T> inline bool pick_tile(const Geo<T>& g, long long n, int cap, 
   return best_home > 0;
 }
 
-// Whether the hit-list path can serve (params, N) at all (the exact conditions are in make_plan, nlcuda.cu).
-inline bool list_path_possible(const nl_params* p, int64_t n) {
-  if (p->nxyz[0] != 1 || p->nxyz[1] != 1 || p->nxyz[2] != 1 || n <= 0 || n >= (1ll << 27)) return false;
-  const double nct = (double)p->ncells[0] * p->ncells[1] * p->ncells[2];
-  return 27.0 * (double)n / nct <= 200.0;
-}
-constexpr int LIST_HL = 64;  // hit-list stride (entries per atom)
-
-// list-path scratch: AoS records (32 B), boundary flags (1 B), hit lists (LIST_HL * 4 B), counts (4 B) per atom
+// hit masks (8 words per atom) + one flag byte per cell
 inline size_t tiled_scratch_bytes(const nl_params* p, int64_t n) {
-  if (!list_path_possible(p, n)) return 256;
-  const size_t n1 = (size_t)n;
-  auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-  return 256 + al(n1 * 32) + al(n1) + al(n1 * LIST_HL * 4) + al(n1 * 4);
+  const size_t nct = (size_t)p->ncells[0] * p->ncells[1] * p->ncells[2];
+  return 512 + (((size_t)(n > 0 ? n : 1) * 32 + 255) & ~(size_t)255) + nct;
 }
 
 template <class T> inline bool tiled_applicable(const nl_params* p, const Geo<T>& g, long long n, int cap, TileShape& ts) {

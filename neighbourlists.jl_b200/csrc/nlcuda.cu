@@ -88,7 +88,6 @@ BuildWs build_ws(void* ws, int64_t N) {
 }
 
 struct PairWs {
-  void* hdr;
   void *px, *py, *pz;
   uint32_t *pidx, *pw, *counts;
   unsigned long long* tsum;
@@ -102,7 +101,7 @@ PairWs pair_ws(void* ws, const nl_params* prm, int64_t N) {
   size_t o = 0;
   auto take = [&](size_t b) { char* r = p ? p + o : nullptr; o += al256(b); return (void*)r; };
   size_t n1 = (size_t)(N > 0 ? N : 1);
-  w.hdr = take(4096);  // device copies of kernel argument blocks (rare out-of-line paths read them from here)
+  take(256);  // header, reserved
   w.px = take(n1 * fsize(prm));
   w.py = take(n1 * fsize(prm));
   w.pz = take(n1 * fsize(prm));
@@ -114,19 +113,6 @@ PairWs pair_ws(void* ws, const nl_params* prm, int64_t N) {
   w.tiled = take(tiled_scratch_bytes(prm, N));
   w.total_bytes = o;
   return w;
-}
-
-struct ListScratch { void* ra; uint8_t* pflag; uint32_t* hits; uint32_t* scount; };
-ListScratch list_scratch(void* base, const nl_params* p, int64_t N) {
-  ListScratch t = {nullptr, nullptr, nullptr, nullptr};
-  if (!list_path_possible(p, N)) return t;
-  char* c = (char*)base + 256;
-  const size_t n1 = (size_t)N;
-  t.ra = c; c += al256(n1 * 32);
-  t.pflag = (uint8_t*)c; c += al256(n1);
-  t.hits = (uint32_t*)c; c += al256(n1 * LIST_HL * 4);
-  t.scount = (uint32_t*)c;
-  return t;
 }
 
 // ---------------------------------------------------------------- stage implementations
@@ -168,9 +154,8 @@ int cell_ids_impl(const nl_params* p, const void* X, int64_t N, void* out, cudaS
 template <class T, class TI>
 int prep_impl(const nl_params* p, const void* Xs, int64_t N, const void* perm, PairWs& w, Geo<T>& g, cudaStream_t st) {
   if (N > 0) {
-    ListScratch ls = list_scratch(w.tiled, p, N);
     k_prep_records<T, TI><<<(unsigned)((N + 255) / 256), 256, 0, st>>>((const T*)Xs, (const TI*)perm, N, g, (T*)w.px, (T*)w.py, (T*)w.pz,
-                                                                      w.pidx, w.pw, (RecAoS<T>*)ls.ra, ls.pflag);
+                                                                      w.pidx, w.pw);
     NL_LAUNCHED(1);
     NL_LAUNCH_CHECK();
   }
@@ -185,7 +170,7 @@ template <class T> Records<T> records_of(const PairWs& w) {
 
 // Which traversal serves this problem.  A pure function of (params, N): nl_count_pairs and
 // nl_fill_pairs must reach the same verdict.
-enum { PATH_GENERIC = 0, PATH_TILED = 1, PATH_LIST = 2 };
+enum { PATH_GENERIC = 0, PATH_TILED = 1, PATH_MASK = 2 };
 template <class T> struct Plan {
   int path;
   TileShape ts_exact, ts_count, ts_fill;
@@ -198,14 +183,14 @@ template <class T> Plan<T> make_plan(const nl_params* p, const Geo<T>& g, int64_
   if (N <= 0) return pl;
   if (!tiled_applicable<T>(p, g, N, tile_cap<T>(), pl.ts_exact)) return pl;
   pl.path = PATH_TILED;
-  if (!list_path_possible(p, N)) return pl;  // dense cells would overflow the 256-candidate masks, or N >= 2^27
-  if (!pick_tile<T>(g, N, CNT_CAP2, pl.ts_count)) return pl;
-  pl.ts_fill = pl.ts_count;
+  const double dens = (double)N / (double)g.nct;
+  if (27.0 * dens > 200.0) return pl;  // candidate lists would overflow the 256-bit masks too often
+  if (!pick_tile<T>(g, N, CNT_CAP2, pl.ts_count) || !pick_tile<T>(g, N, fill_cap<T>(), pl.ts_fill)) return pl;
   if (sizeof(T) == 8) {
     pl.th = mask_thresholds(p->cell, p->ncells, pl.ts_count, (double)g.cutoff_sq);
     if (!pl.th.ok) return pl;
   }
-  pl.path = PATH_LIST;
+  pl.path = PATH_MASK;
   return pl;
 }
 
@@ -218,6 +203,14 @@ template <class F> int set_smem_once(F* fn, int bytes, bool& done) {
   return NL_OK;
 }
 
+struct TiledScratch { uint32_t* masks; uint8_t* cellflag; };
+TiledScratch tiled_scratch(void* base, int64_t N) {
+  TiledScratch t;
+  t.masks = (uint32_t*)((char*)base + 256);
+  t.cellflag = (uint8_t*)((char*)base + 256 + al256((size_t)(N > 0 ? N : 1) * 32));
+  return t;
+}
+
 // MODE_COUNT with want_mask (materialisation) or without (lazy count), MODE_FILL, MODE_LJ.
 template <class T, class TI, int MODE>
 int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, const Geo<T>& g, const Sinks<T, TI>& sk, bool want_mask,
@@ -225,31 +218,28 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
   if (N <= 0) return NL_OK;
   Records<T> rec = records_of<T>(w);
   const Plan<T> pl = make_plan<T>(p, g, N);
-  if (pl.path == PATH_LIST && MODE != MODE_LJ) {
-    ListScratch ls = list_scratch(w.tiled, p, N);
-    ListArgs<T, TI> a;
-    list_args<T, TI>(a, N, (const TI*)co, rec, g, sk, pl.ts_count);
-    a.ra = (const RecAoS<T>*)ls.ra; a.pflag = ls.pflag; a.hits = ls.hits; a.scount = ls.scount; a.hl = LIST_HL;
+  if (pl.path == PATH_MASK && MODE != MODE_LJ) {
+    TiledScratch tsx = tiled_scratch(w.tiled, N);
+    MaskArgs<T, TI> a;
+    mask_args<T, TI>(a, N, (const TI*)co, rec, g, sk, MODE == MODE_FILL ? pl.ts_fill : pl.ts_count, tsx.masks);
+    a.cellflag = tsx.cellflag;
     a.mid = pl.th.mid; a.hw = pl.th.hw; a.dguard = pl.th.dguard;
     const unsigned nblk = (unsigned)((long long)a.ntx * a.nty * a.ntz);
-    static_assert(sizeof(ListArgs<T, TI>) <= 1024, "argument block");
-    a.self = (const ListArgs<T, TI>*)((char*)w.hdr + (MODE == MODE_FILL ? 1024 : (want_mask ? 0 : 2048)));
-    NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
     if (MODE == MODE_FILL) {
-      // persistent grid: each warp walks over many atoms, so the per-thread prologue is paid once
-      long long nb = (N + (FILL_NT / 32) - 1) / (FILL_NT / 32);
-      if (nb > 148 * 4 * 8) nb = 148 * 4 * 8;
-      k_fill_list<T, TI><<<(unsigned)nb, FILL_NT, 0, st>>>(a);
+      static bool done = false;
+      int rc = set_smem_once(k_fill_mask<T, TI>, FILL_SMEM_BYTES, done);
+      if (rc) return rc;
+      k_fill_mask<T, TI><<<nblk, TILE_NT, FILL_SMEM_BYTES, st>>>(a);
     } else if (want_mask) {
       static bool done = false;
-      int rc = set_smem_once(k_count_list<T, TI, true>, CNT_SMEM_BYTES, done);
+      int rc = set_smem_once(k_count_mask<T, TI, true>, CNT_SMEM_BYTES, done);
       if (rc) return rc;
-      k_count_list<T, TI, true><<<nblk, TILE_NT, CNT_SMEM_BYTES, st>>>(a);
+      k_count_mask<T, TI, true><<<nblk, TILE_NT, CNT_SMEM_BYTES, st>>>(a);
     } else {
       static bool done = false;
-      int rc = set_smem_once(k_count_list<T, TI, false>, CNT_SMEM_BYTES, done);
+      int rc = set_smem_once(k_count_mask<T, TI, false>, CNT_SMEM_BYTES, done);
       if (rc) return rc;
-      k_count_list<T, TI, false><<<nblk, TILE_NT, CNT_SMEM_BYTES, st>>>(a);
+      k_count_mask<T, TI, false><<<nblk, TILE_NT, CNT_SMEM_BYTES, st>>>(a);
     }
     NL_LAUNCHED(1);
   } else if (pl.path != PATH_GENERIC) {
