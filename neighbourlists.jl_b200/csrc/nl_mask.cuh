@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_mask(const MaskA
 constexpr int FILL_SMEM_BYTES = NL_FILL_SMEM_KB * 1024;
 constexpr int FILL_WARP_BYTES = CELLTAB_BYTES + 4 * MASK_MAXCAND + 32 * 3 * 4 + 32 * 3 * 8 + 28 * 3 * 8;  // tables | 4 hit lists | S stage | R stage | cs table
 constexpr int FILL_FIXED_BYTES = 3 * TILE_VPAD * 4 + 64 * 4 + (TILE_NT / 32) * FILL_WARP_BYTES;
-template <class T> __host__ __device__ constexpr int fill_cap() { return (FILL_SMEM_BYTES - FILL_FIXED_BYTES) / TileRecBytes<T>::value / 8 * 8; }
+template <class T> __host__ __device__ constexpr int fill_cap() { return (FILL_SMEM_BYTES - FILL_FIXED_BYTES) / (TileRecBytes<T>::value + 4) / 8 * 8; }
 static_assert(FILL_WARP_BYTES % 16 == 0 && FILL_FIXED_BYTES % 16 == 0, "alignment");
 
 #ifndef NL_FILL_MINB
@@ -467,6 +467,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
   T* sz = sy + CAP;
   uint32_t* sidx = (uint32_t*)(sz + CAP);
   uint32_t* sw = sidx + CAP;
+  uint32_t* sgid = sw + CAP;  // shard mode: global index - 1 of each staged atom
   __shared__ int scan_sm[33];
   __shared__ int s_next;
 
@@ -510,8 +511,10 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
     sz[sl] = a.rec.pz[src];
     sidx[sl] = a.rec.pidx[src];
     sw[sl] = a.rec.pw[src];
+    if (a.out.pgid0) sgid[sl] = a.out.pgid0[src];
   }
   __syncthreads();
+  const bool use_gid = a.out.pgid0 != nullptr;
 
   while (true) {
     int hc = 0;
@@ -590,7 +593,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
         if (nhit == 0) continue;
         const uint32_t io = __shfl_sync(FULL, my_io, q * 8);
         const long long base = __shfl_sync(FULL, my_base, q * 8);
-        const TI io_out = out_index(a.out, io);
+        const TI io_out = use_gid ? (TI)sgid[hs] + 1 : (TI)io + 1;
         const T xi = sx[hs], yi = sy[hs], zi = sz[hs];
         const uint32_t wi = sw[hs];
         const uint8_t* L = lists + q * MASK_MAXCAND;
@@ -625,7 +628,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
             stS[3 * lane] = S0; stS[3 * lane + 1] = S1; stS[3 * lane + 2] = S2;
             if (Ro_row) { stR[3 * lane] = R0; stR[3 * lane + 1] = R1; stR[3 * lane + 2] = R2; }
             io_row[r] = io_out;
-            jo_row[r] = out_index(a.out, sidx[slot]);
+            jo_row[r] = use_gid ? (TI)sgid[slot] + 1 : (TI)sidx[slot] + 1;
           }
           __syncwarp();
           // transposed, contiguous stores of the row segment [r0, r0 + nr): 3 nr words of S, 3 nr of R

@@ -31,6 +31,7 @@ template <class T, class TI> struct Sinks {
   T* Ro;                 //            may be null
   long long n_rows;      //            only atoms with original index < n_rows get a row (sharding: owned atoms first)
   const TI* gmap;        //            may be null; else i/j are written as gmap[original index] (global, 1-based)
+  const uint32_t* pgid0; //            with gmap: gmap[pidx[s]] - 1 per SORTED atom (one gather per atom instead of one per pair)
   double* energy;        // MODE_LJ: device scalar
   double lj_eps, lj_sigma2;
 };
@@ -54,6 +55,13 @@ __global__ void __launch_bounds__(256) k_prep_records(const T* __restrict__ Xs, 
   pz[s] = z;
   pidx[s] = (uint32_t)(perm[s] - 1);
   pw[s] = pack_wind(w);
+}
+
+template <class TI>
+__global__ void __launch_bounds__(256) k_make_pgid(const uint32_t* __restrict__ pidx, const TI* __restrict__ gmap, long long n,
+                                                   uint32_t* __restrict__ pgid0) {
+  long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < n) pgid0[s] = (uint32_t)(gmap[pidx[s]] - 1);
 }
 
 // Generic traversal of ONE atom (sorted slot s): any nxyz >= 1, any ncells >= 1, any density.

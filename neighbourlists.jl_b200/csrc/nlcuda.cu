@@ -89,7 +89,7 @@ BuildWs build_ws(void* ws, int64_t N) {
 
 struct PairWs {
   void *px, *py, *pz;
-  uint32_t *pidx, *pw, *counts;
+  uint32_t *pidx, *pw, *counts, *pgid0;
   unsigned long long* tsum;
   unsigned long long* total;
   void* tiled;  // tiled-kernel scratch (tile table, hit masks)
@@ -108,6 +108,7 @@ PairWs pair_ws(void* ws, const nl_params* prm, int64_t N) {
   w.pidx = (uint32_t*)take(n1 * 4);
   w.pw = (uint32_t*)take(n1 * 4);
   w.counts = (uint32_t*)take(n1 * 4);
+  w.pgid0 = (uint32_t*)take(n1 * 4);
   w.tsum = (unsigned long long*)take((size_t)(scan_tiles((long long)n1) + 1) * 8);
   w.total = (unsigned long long*)take(256);
   w.tiled = take(tiled_scratch_bytes(prm, N));
@@ -288,6 +289,12 @@ int fill_pairs_impl(const nl_params* p, int64_t N, const void* co, const void* f
   sk.first = (const TI*)first;
   sk.io = (TI*)io; sk.jo = (TI*)jo; sk.So = (TI*)So; sk.Ro = (T*)Ro;
   sk.n_rows = n_rows; sk.gmap = (const TI*)gmap;
+  if (gmap && N > 0) {
+    k_make_pgid<TI><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(w.pidx, (const TI*)gmap, N, w.pgid0);
+    NL_LAUNCHED(1);
+    NL_LAUNCH_CHECK();
+    sk.pgid0 = w.pgid0;
+  }
   return traverse<T, TI, MODE_FILL>(p, N, co, w, g, sk, true, st);
 }
 

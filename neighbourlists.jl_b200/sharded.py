@@ -19,6 +19,7 @@ single-device CSR (tests/test_sharded_*).
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Optional
 
@@ -27,6 +28,27 @@ import torch
 import torch.distributed as dist
 
 from .cellmath import CellGeometry, geometry
+
+_PROFILE = bool(os.environ.get("NL_SHARD_PROFILE"))
+
+
+class _Phases:
+    """Optional per-phase device timing (NL_SHARD_PROFILE=1): CUDA events between the phases of one call."""
+
+    def __init__(self, on):
+        self.on, self.marks = on, []
+
+    def mark(self, name):
+        if self.on and torch.cuda.is_available():
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.marks.append((name, e))
+
+    def report(self, rank):
+        if self.on and self.marks and rank == 0:
+            torch.cuda.synchronize()
+            print("[shard phases ms] " + " ".join(f"{n}={a.elapsed_time(b):.2f}" for (_, a), (n, b) in zip(self.marks[:-1], self.marks[1:])),
+                  flush=True)
 
 
 @dataclass
@@ -104,6 +126,8 @@ def neighbour_list_sharded(X_local, gidx_local, cutoff, cell, pbc, *, group=None
     with redistribute=False the caller guarantees they already lie in this rank's slab of `plan_slabs`.
     """
     engine = engine or CudaEngine()
+    ph = _Phases(_PROFILE)
+    ph.mark("start")
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     dev = engine.device
@@ -125,7 +149,9 @@ def neighbour_list_sharded(X_local, gidx_local, cutoff, cell, pbc, *, group=None
     hist = torch.bincount(planes, minlength=nc[axis]).long()
     if world > 1:
         dist.all_reduce(hist, group=group)
+    ph.mark("bin+hist")
     plan = plan_slabs(hist.cpu().numpy(), world, halo, bool(geo.pbc[axis]), axis)
+    ph.mark("plan")
     bounds_t = torch.as_tensor(plan.bounds, device=dev)
 
     # ---- step 0: all-to-all-v to the owners
@@ -144,6 +170,7 @@ def neighbour_list_sharded(X_local, gidx_local, cutoff, cell, pbc, *, group=None
         gidx = torch.cat([gidx[stay], _a2a(gidx[order], sc, rc, group)])
         planes = torch.cat([planes[stay], _a2a(planes[order], sc, rc, group)])
     n_owned = int(X.shape[0])
+    ph.mark("redistribute")
 
     # ---- step 1: halo exchange with ranks r-1 / r+1
     halos_X, halos_g = [], []
@@ -190,8 +217,11 @@ def neighbour_list_sharded(X_local, gidx_local, cutoff, cell, pbc, *, group=None
     X_all = torch.cat([X] + halos_X) if halos_X else X
     g_all = torch.cat([gidx] + halos_g) if halos_g else gidx
     n_halo = int(X_all.shape[0]) - n_owned
+    ph.mark("halo")
 
     # ---- step 2: the unchanged single-GPU pipeline on owned + halo atoms, global geometry
     res = engine.build(X_all, n_owned, g_all, cutoff, cell, pbc, int_type, with_R)
+    ph.mark("local build")
+    ph.report(rank)
     return ShardedPairList(owned_index=gidx, X_owned=X, first=res["first"], i=res["i"], j=res["j"], S=res["S"], R=res["R"],
                            n_halo=n_halo, plan=plan)
