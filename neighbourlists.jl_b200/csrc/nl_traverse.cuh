@@ -40,21 +40,33 @@ template <class T, class TI> __device__ __forceinline__ TI out_index(const Sinks
   return out.gmap ? out.gmap[orig] : (TI)orig + 1;
 }
 
+// AoS twin of the records: one 32-byte sector per atom (x, y, z, index to publish, packed winding).
+template <class T> struct RecAoS;
+template <> struct alignas(32) RecAoS<double> { double x, y, z; uint32_t idx, w; };
+template <> struct alignas(32) RecAoS<float> { float x, y, z; uint32_t idx, w, pad0, pad1, pad2; };
+static_assert(sizeof(RecAoS<double>) == 32 && sizeof(RecAoS<float>) == 32, "one sector per record");
+
 template <class T, class TI>
 __global__ void __launch_bounds__(256) k_prep_records(const T* __restrict__ Xs, const TI* __restrict__ perm, long long n, Geo<T> g,
                                                       T* __restrict__ px, T* __restrict__ py, T* __restrict__ pz,
-                                                      uint32_t* __restrict__ pidx, uint32_t* __restrict__ pw) {
+                                                      uint32_t* __restrict__ pidx, uint32_t* __restrict__ pw,
+                                                      RecAoS<T>* __restrict__ ra, uint32_t* __restrict__ pkey) {
   long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   T x = Xs[3 * s], y = Xs[3 * s + 1], z = Xs[3 * s + 2];
   int c[3];
   long long w[3];
   cell_of(g, x, y, z, c, w);
+  const uint32_t idx = (uint32_t)(perm[s] - 1), pwv = pack_wind(w);
   px[s] = x;
   py[s] = y;
   pz[s] = z;
-  pidx[s] = (uint32_t)(perm[s] - 1);
-  pw[s] = pack_wind(w);
+  pidx[s] = idx;
+  pw[s] = pwv;
+  RecAoS<T> r;
+  r.x = x; r.y = y; r.z = z; r.idx = idx; r.w = pwv;
+  ra[s] = r;
+  pkey[s] = (uint32_t)c[0] + (uint32_t)g.nc[0] * ((uint32_t)c[1] + (uint32_t)g.nc[1] * (uint32_t)c[2]);
 }
 
 template <class TI>

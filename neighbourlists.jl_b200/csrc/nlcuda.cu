@@ -2,12 +2,15 @@
 // Host-side stage orchestration only; kernels live in the .cuh files next to this one.
 #include "../../include/nlcuda.h"
 
+#include <cstdlib>
+
 #include "nl_build.cuh"
 #include "nl_common.cuh"
 #include "nl_scan_sort.cuh"
 #include "nl_traverse.cuh"
 #include "nl_tiled.cuh"
 #include "nl_mask.cuh"
+#include "nl_fillrows.cuh"
 
 namespace {
 
@@ -88,8 +91,10 @@ BuildWs build_ws(void* ws, int64_t N) {
 }
 
 struct PairWs {
+  void* hdr;
   void *px, *py, *pz;
-  uint32_t *pidx, *pw, *counts, *pgid0;
+  uint32_t *pidx, *pw, *counts, *pgid0, *pkey, *sorted_of;
+  void* ra;
   unsigned long long* tsum;
   unsigned long long* total;
   void* tiled;  // tiled-kernel scratch (tile table, hit masks)
@@ -101,7 +106,7 @@ PairWs pair_ws(void* ws, const nl_params* prm, int64_t N) {
   size_t o = 0;
   auto take = [&](size_t b) { char* r = p ? p + o : nullptr; o += al256(b); return (void*)r; };
   size_t n1 = (size_t)(N > 0 ? N : 1);
-  take(256);  // header, reserved
+  w.hdr = take(4096);  // device copies of kernel argument blocks (rare out-of-line paths read them from here)
   w.px = take(n1 * fsize(prm));
   w.py = take(n1 * fsize(prm));
   w.pz = take(n1 * fsize(prm));
@@ -109,6 +114,9 @@ PairWs pair_ws(void* ws, const nl_params* prm, int64_t N) {
   w.pw = (uint32_t*)take(n1 * 4);
   w.counts = (uint32_t*)take(n1 * 4);
   w.pgid0 = (uint32_t*)take(n1 * 4);
+  w.pkey = (uint32_t*)take(n1 * 4);
+  w.sorted_of = (uint32_t*)take(n1 * 4);
+  w.ra = take(n1 * 32);
   w.tsum = (unsigned long long*)take((size_t)(scan_tiles((long long)n1) + 1) * 8);
   w.total = (unsigned long long*)take(256);
   w.tiled = take(tiled_scratch_bytes(prm, N));
@@ -156,7 +164,7 @@ template <class T, class TI>
 int prep_impl(const nl_params* p, const void* Xs, int64_t N, const void* perm, PairWs& w, Geo<T>& g, cudaStream_t st) {
   if (N > 0) {
     k_prep_records<T, TI><<<(unsigned)((N + 255) / 256), 256, 0, st>>>((const T*)Xs, (const TI*)perm, N, g, (T*)w.px, (T*)w.py, (T*)w.pz,
-                                                                      w.pidx, w.pw);
+                                                                      w.pidx, w.pw, (RecAoS<T>*)w.ra, w.pkey);
     NL_LAUNCHED(1);
     NL_LAUNCH_CHECK();
   }
@@ -195,6 +203,13 @@ template <class T> Plan<T> make_plan(const nl_params* p, const Geo<T>& g, int64_
   return pl;
 }
 
+// NL_FILL_TILED=1 selects the older sorted-order, tile-staged fill kernel (k_fill_mask) for A/B measurements.
+inline bool fill_tiled_requested() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NL_FILL_TILED"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
 template <class F> int set_smem_once(F* fn, int bytes, bool& done) {
   if (!done) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -226,7 +241,23 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
     a.cellflag = tsx.cellflag;
     a.mid = pl.th.mid; a.hw = pl.th.hw; a.dguard = pl.th.dguard;
     const unsigned nblk = (unsigned)((long long)a.ntx * a.nty * a.ntz);
-    if (MODE == MODE_FILL) {
+    if (MODE == MODE_FILL && !fill_tiled_requested()) {
+      // original-order, thread-per-pair fill (nl_fillrows.cuh)
+      k_fillrows_prologue<T, TI><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(w.pidx, sk.gmap, N, w.sorted_of, (RecAoS<T>*)w.ra);
+      NL_LAUNCHED(1);
+      FillRowsArgs<T, TI> fa;
+      fa.ra = (const RecAoS<T>*)w.ra; fa.pkey = w.pkey; fa.sorted_of = w.sorted_of; fa.masks = tsx.masks; fa.cellflag = tsx.cellflag;
+      fa.co = (const TI*)co; fa.rec = rec; fa.g = g; fa.out = sk; fa.n = N;
+      static_assert(sizeof(FillRowsArgs<T, TI>) <= 1024, "argument block");
+      fa.self = (const FillRowsArgs<T, TI>*)((char*)w.hdr + 1024);
+      NL_CUDA(cudaMemcpyAsync((void*)fa.self, &fa, sizeof(fa), cudaMemcpyHostToDevice, st));
+      if (sk.n_rows > 0) {
+        k_fill_rows<T, TI><<<(unsigned)((sk.n_rows + FR_RB - 1) / FR_RB), FR_NT, 0, st>>>(fa);
+        NL_LAUNCHED(1);
+      }
+      NL_LAUNCH_CHECK();
+      return NL_OK;
+    } else if (MODE == MODE_FILL) {
       static bool done = false;
       int rc = set_smem_once(k_fill_mask<T, TI>, FILL_SMEM_BYTES, done);
       if (rc) return rc;
