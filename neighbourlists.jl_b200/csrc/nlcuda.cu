@@ -203,10 +203,12 @@ template <class T> Plan<T> make_plan(const nl_params* p, const Geo<T>& g, int64_
   return pl;
 }
 
-// NL_FILL_TILED=1 selects the older sorted-order, tile-staged fill kernel (k_fill_mask) for A/B measurements.
+// Two fill kernels exist: the sorted-order, tile-staged k_fill_mask (default: 8.3 ms at the headline
+// size, bound by randomly placed row writes) and the original-order, thread-per-pair k_fill_rows (10.8 ms, bound by
+// random record gathers).  NL_FILL_ROWS=1 selects the latter for A/B measurements.
 inline bool fill_tiled_requested() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("NL_FILL_TILED"); v = (e && e[0] == '1') ? 1 : 0; }
+  if (v < 0) { const char* e = getenv("NL_FILL_ROWS"); v = (e && e[0] == '1') ? 0 : 1; }
   return v == 1;
 }
 
@@ -261,6 +263,12 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
       static bool done = false;
       int rc = set_smem_once(k_fill_mask<T, TI>, FILL_SMEM_BYTES, done);
       if (rc) return rc;
+      // `i` as a separate unit-stride stream; the generic route inside k_fill_mask still writes its own i (same values)
+      if (sk.n_rows > 0) {
+        k_fill_i<TI><<<(unsigned)((sk.n_rows + FI_ROWS - 1) / FI_ROWS), 256, 0, st>>>(sk.first, sk.n_rows, sk.gmap, sk.io);
+        NL_LAUNCHED(1);
+      }
+      a.skip_i = 1;
       k_fill_mask<T, TI><<<nblk, TILE_NT, FILL_SMEM_BYTES, st>>>(a);
     } else if (want_mask) {
       static bool done = false;

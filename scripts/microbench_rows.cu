@@ -8,6 +8,22 @@
 #include <cuda_runtime.h>
 #define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(1); } } while (0)
 
+template <int POL> __device__ __forceinline__ void st(int* p, int v) { if (POL == 0) *p = v; else if (POL == 1) __stcs(p, v); else if (POL == 2) __stwt(p, v); else __stcg(p, v); }
+template <int POL> __device__ __forceinline__ void st(double* p, double v) { if (POL == 0) *p = v; else if (POL == 1) __stcs(p, v); else if (POL == 2) __stwt(p, v); else __stcg(p, v); }
+
+template <bool WITH_R, int POL>
+__global__ void write_rows_pol(const int* __restrict__ first, const int* __restrict__ order, int n, int* io, int* jo, int* So, double* Ro) {
+  const int lane = threadIdx.x & 31;
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n; w += nw) {
+    const int row = order ? order[w] : (int)w;
+    const long long b = first[row], e = first[row + 1];
+    const int cnt = (int)(e - b);
+    for (int r = lane; r < cnt; r += 32) { st<POL>(io + b + r, row); st<POL>(jo + b + r, r); }
+    for (int x = lane; x < 3 * cnt; x += 32) { st<POL>(So + 3 * b + x, x); if (WITH_R) st<POL>(Ro + 3 * b + x, (double)x); }
+  }
+}
+
 template <bool WITH_R>
 __global__ void write_rows(const int* __restrict__ first, const int* __restrict__ order, int n, int* io, int* jo, int* So, double* Ro) {
   const int lane = threadIdx.x & 31;
@@ -51,6 +67,25 @@ int main() {
       printf("rows %s, %s: %.3f ms  (%.0f GB/s of payload, P=%lld)\n", mode ? "RANDOM order" : "sequential", with_r ? "i,j,S,R" : "i,j,S", best,
              bytes / best / 1e6, P);
     }
+  for (int pol = 1; pol <= 3; pol++) {
+    float best = 1e9;
+    for (int it = 0; it < 5; it++) {
+      cudaEventRecord(e0);
+      if (pol == 1) write_rows_pol<true, 1><<<148 * 8, 256>>>(d_first, d_perm, n, io, jo, So, Ro);
+      if (pol == 2) write_rows_pol<true, 2><<<148 * 8, 256>>>(d_first, d_perm, n, io, jo, So, Ro);
+      if (pol == 3) write_rows_pol<true, 3><<<148 * 8, 256>>>(d_first, d_perm, n, io, jo, So, Ro);
+      cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+      float ms; cudaEventElapsedTime(&ms, e0, e1); best = std::min(best, ms);
+    }
+    printf("rows RANDOM order, i,j,S,R, store policy %s: %.3f ms (%.0f GB/s)\n", pol == 1 ? "st.cs (streaming)" : pol == 2 ? "st.wt (write-through)" : "st.cg", best, (double)P * 44 / best / 1e6);
+  }
+  // more warps in flight: 148*32 blocks
+  {
+    float best = 1e9;
+    for (int it = 0; it < 5; it++) { cudaEventRecord(e0); write_rows<true><<<148 * 32, 256>>>(d_first, d_perm, n, io, jo, So, Ro); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+      float ms; cudaEventElapsedTime(&ms, e0, e1); best = std::min(best, ms); }
+    printf("rows RANDOM order, i,j,S,R, grid 148*32: %.3f ms\n", best);
+  }
   // reference: plain streaming memset-like write of the same volume
   {
     float best = 1e9;
