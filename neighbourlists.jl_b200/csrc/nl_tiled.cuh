@@ -108,6 +108,14 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_tiled(const TiledArgs<T, TI> a) 
   const int hx0 = (b % a.ntx) * a.tx, hy0 = ((b / a.ntx) % a.nty) * a.ty, hz0 = (b / (a.ntx * a.nty)) * a.tz;
   const int hxn = min(a.tx, g.nc[0] - hx0), hyn = min(a.ty, g.nc[1] - hy0), hzn = min(a.tz, g.nc[2] - hz0);
   const int VX = hxn + 2, VY = hyn + 2, VZ = hzn + 2, NV = VX * VY * VZ;
+  {  // quick reject: tiles without a single home atom (a slab shard sees the global grid, mostly empty) cost two loads per row
+    int nonempty = 0;
+    if (tid < hyn * hzn) {
+      const long long c0 = (long long)hx0 + (long long)g.nc[0] * ((long long)(hy0 + tid % hyn) + (long long)g.nc[1] * (hz0 + tid / hyn));
+      nonempty = (long long)a.co[c0 + hxn] > (long long)a.co[c0];
+    }
+    if (!__syncthreads_or(nonempty)) return;
+  }
 
   // ---- 1. virtual cell table
   int cnt = 0, gs = 0;
