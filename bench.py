@@ -162,14 +162,14 @@ def run_ours(args):
         gidx = None
     else:
         # weak scaling: ONE global box of world * n_atoms atoms; rank r generates the atoms of its own
-        # equal-width slab along the slab axis (x).  neighbour_list_sharded still bins, balances the slabs
+        # equal-width slab along the slab axis (z).  neighbour_list_sharded still bins, balances the slabs
         # by atom count, moves boundary atoms to their owners (all-to-all-v) and exchanges the halos.
         n_total = n_atoms * world
         L = (n_total / DENSITY) ** (1.0 / 3.0)
         C = np.eye(3) * L
         rng = np.random.Generator(np.random.PCG64(SEED + rank))
         X = rng.random((n_atoms, 3))
-        X[:, 0] = (X[:, 0] + rank) / world
+        X[:, 2] = (X[:, 2] + rank) / world
         X *= L
         gidx = torch.arange(rank * n_atoms + 1, (rank + 1) * n_atoms + 1, dtype=torch.int64)
     X_host = torch.from_numpy(X).pin_memory()
@@ -284,7 +284,7 @@ def run_ours(args):
             "config": {"workload": f"{n_atoms} atoms per GPU, random cubic box rho={DENSITY} A^-3, rc={CUTOFF} A, pbc TTT, Float64/Int32, "
                                    f"seed {SEED}+rank; output (i,j,S,R) = 44 B/pair",
                        "pairs_per_gpu": P, "parallelism": "single GPU" if world == 1 else
-                       f"{world} spatial slabs along x of one {n_atoms * world}-atom box, all-to-all-v + cutoff-wide halo exchange (NCCL)",
+                       f"{world} spatial slabs along z of one {n_atoms * world}-atom box, all-to-all-v + cutoff-wide halo exchange (NCCL)",
                        "l2": "inputs (240 MB) and outputs (>11 GB) exceed the 126 MB L2; no explicit flush",
                        "stage_ms": {"count_stage": count_mean, "fill_kernel": fill_mean},
                        "step_roofline": {"bytes": step_bytes, "formula": "24 N + 48 P", "gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,

@@ -1,7 +1,7 @@
 """Multi-GPU neighbour lists: 1-D spatial slabs with a cutoff-wide halo.
 
 One process per GPU (torch.distributed, NCCL over NVLink; gloo on CPU in the tests).  The box is cut
-into slabs of whole cell PLANES along the axis with the most cells; rank r owns planes
+into slabs of whole cell PLANES along the axis with the most cells (ties: z, the slowest key axis); rank r owns planes
 [bounds[r], bounds[r+1]) balanced by atom count.  Three exchanges, all plain point-to-point data
 movement (no reduction on the data path):
 
@@ -136,7 +136,8 @@ def neighbour_list_sharded(X_local, gidx_local, cutoff, cell, pbc, *, group=None
     fdt = np.float64 if X.dtype == torch.float64 else np.float32
     geo: CellGeometry = geometry(cell, cutoff, pbc, fdt)
     nc = [int(v) for v in geo.ncells]
-    axis = int(np.argmax(nc))                        # most planes (ties: lowest axis) -- the longest cell axis
+    axis = 2 - int(np.argmax(nc[::-1]))              # most planes; ties go to the SLOWEST key axis (z), so that a slab is one
+                                                     # contiguous range of cell keys / sorted atoms
     halo = int(geo.nxyz[axis])
     stride = [1, nc[0], nc[0] * nc[1]][axis]
 
