@@ -69,14 +69,19 @@ template <class T, class TI> struct MaskArgs {
   int skip_i;         // fill pass: the i array is written by k_fill_i instead
   int tx, ty, tz, ntx, nty, ntz;
   float mid, hw, dguard;
+  const MaskArgs<T, TI>* self;  // this struct in GLOBAL memory: the rare out-of-line paths read their inputs from there, so the
+                                // kernels never copy their parameters onto the local-memory stack (measured: that copy cost
+                                // 77 KB of local stores per CTA, 9 GB per launch on a slab of an 8x larger global grid)
 };
 
 __device__ __forceinline__ int pack_shift(int s0, int s1, int s2) { return (s0 + 1) | ((s1 + 1) << 2) | ((s2 + 1) << 4); }
 __device__ __forceinline__ void unpack_shift(int p, long long s[3]) { s[0] = (p & 3) - 1; s[1] = ((p >> 2) & 3) - 1; s[2] = ((p >> 4) & 3) - 1; }
 
 // The exact contract for one pair given global sorted indices; returns r2 < cutoff_sq.
-template <class T>
-__device__ __noinline__ bool exact_pair_hit(const Geo<T>& g, const Records<T>& rec, long long gi, long long gj, int shp) {
+template <class T, class TI>
+__device__ __noinline__ bool exact_pair_hit(const MaskArgs<T, TI>* ad, long long gi, long long gj, int shp) {
+  const Geo<T>& g = ad->g;
+  const Records<T>& rec = ad->rec;
   const T xi = rec.px[gi], yi = rec.py[gi], zi = rec.pz[gi];
   const T xj = rec.px[gj], yj = rec.py[gj], zj = rec.pz[gj];
   long long wi[3], wj[3], sl[3];
@@ -129,8 +134,10 @@ __device__ __forceinline__ int find_vcell(const int* vstart, int NV, int sl) {
 // Rare path of the fill pass: atoms i and j carry different (or overflowed) winding numbers, so the
 // shift is S = s_loop + w_i - w_j and cell' * S is not the per-cell table entry.  Kept out of line so
 // that none of it is hoisted into the common path.
-template <class T>
-__device__ __noinline__ void slow_shift_and_R(const Geo<T>& g, T xi, T yi, T zi, T xj, T yj, T zj, uint32_t wi, uint32_t wj, int* S012, T* R012) {
+template <class T, class TI>
+__device__ __noinline__ void slow_shift_and_R(const MaskArgs<T, TI>* ad, T xi, T yi, T zi, T xj, T yj, T zj, uint32_t wi, uint32_t wj, int* S012,
+                                              T* R012) {
+  const Geo<T>& g = ad->g;
   long long w_i[3], w_j[3];
   int cc[3];
   if (wi & WIND_OVERFLOW) cell_of(g, xi, yi, zi, cc, w_i); else unpack_wind(wi, w_i);
@@ -144,8 +151,8 @@ __device__ __noinline__ void slow_shift_and_R(const Geo<T>& g, T xi, T yi, T zi,
 
 // Generic per-atom route for the atoms [g0, g0 + n) of one cell (out of line: rare).
 template <class T, class TI, int MODE>
-__device__ __noinline__ void generic_cell(long long g0, int n, int lane, const Records<T>& rec, const TI* co, const Geo<T>& g, const Sinks<T, TI>& out) {
-  for (int k = lane; k < n; k += 32) generic_atom<T, TI, MODE>(g0 + k, rec, co, g, out);
+__device__ __noinline__ void generic_cell(const MaskArgs<T, TI>* ad, long long g0, int n, int lane) {
+  for (int k = lane; k < n; k += 32) generic_atom<T, TI, MODE>(g0 + k, ad->rec, ad->co, ad->g, ad->out);
 }
 
 // Per-warp candidate tables of one home cell: flat candidate index -> staged slot / virtual cell.
@@ -243,7 +250,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_mask(const MaskA
       const int lx = hcell[hc] & 255, ly = (hcell[hc] >> 8) & 255, lz = hcell[hc] >> 16;
       const int vh = ((lz + 1) * VY + (ly + 1)) * VX + (lx + 1);
       const int nh = vstart[vh + 1] - vstart[vh];
-      generic_cell<T, TI, MODE_COUNT>((long long)vgs[vh], nh, lane, a.rec, a.co, g, a.out);
+      generic_cell<T, TI, MODE_COUNT>(a.self, (long long)vgs[vh], nh, lane);
       if (WANT_MASK && lane == 0) a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)] = 0;
     }
     return;
@@ -302,7 +309,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_mask(const MaskA
     const int ncand = build_cell_tables<false>(vstart, VX, VY, lx, ly, lz, lane, tab);
     if (WANT_MASK && lane == 0) a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)] = ncand <= MASK_MAXCAND ? 1 : 0;
     if (ncand > MASK_MAXCAND) {  // too many candidates for a 256-bit mask: generic route (the fill pass does the same)
-      generic_cell<T, TI, MODE_COUNT>(hg0, nh, lane, a.rec, a.co, g, a.out);
+      generic_cell<T, TI, MODE_COUNT>(a.self, hg0, nh, lane);
       continue;
     }
     const int nchunk = (ncand + 31) >> 5;
@@ -416,9 +423,9 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_mask(const MaskA
               const float dx = px - qx, dy = py - qy, dz = pz - qz;
               const float t = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, -mid)));
               hit = valid && t < -hw;
-              if (valid && (cand_bad || ((hbad >> aa) & 1u) || fabsf(t) <= hw)) hit = exact_pair_hit<T>(g, a.rec, hg0 + g0 + aa, gj, shp);
+              if (valid && (cand_bad || ((hbad >> aa) & 1u) || fabsf(t) <= hw)) hit = exact_pair_hit<T, TI>(a.self, hg0 + g0 + aa, gj, shp);
             } else {
-              hit = valid && exact_pair_hit<T>(g, a.rec, hg0 + g0 + aa, gj, shp);
+              hit = valid && exact_pair_hit<T, TI>(a.self, hg0 + g0 + aa, gj, shp);
             }
             const unsigned bal = __ballot_sync(FULL, hit);
             if (lane == 0) mrow[aa] = bal;
@@ -516,7 +523,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
       const int lx = hcell[hc] & 255, ly = (hcell[hc] >> 8) & 255, lz = hcell[hc] >> 16;
       const int vh = ((lz + 1) * VY + (ly + 1)) * VX + (lx + 1);
       const int nh = vstart[vh + 1] - vstart[vh];
-      generic_cell<T, TI, MODE_FILL>((long long)vgs[vh], nh, lane, a.rec, a.co, g, a.out);
+      generic_cell<T, TI, MODE_FILL>(a.self, (long long)vgs[vh], nh, lane);
     }
     return;
   }
@@ -544,7 +551,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
     if (nh == 0) continue;
     const long long hg0 = vgs[vh];
     if (!a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)]) {
-      generic_cell<T, TI, MODE_FILL>(hg0, nh, lane, a.rec, a.co, g, a.out);
+      generic_cell<T, TI, MODE_FILL>(a.self, hg0, nh, lane);
       continue;
     }
     build_cell_tables<true>(vstart, VX, VY, lx, ly, lz, lane, tab);
@@ -638,7 +645,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
             } else {
               int S3[3] = {S0, S1, S2};
               T R3[3];
-              slow_shift_and_R<T>(g, xi, yi, zi, xj, yj, zj, wi, wj, S3, R3);
+              slow_shift_and_R<T, TI>(a.self, xi, yi, zi, xj, yj, zj, wi, wj, S3, R3);
               S0 = S3[0]; S1 = S3[1]; S2 = S3[2];
               R0 = R3[0]; R1 = R3[1]; R2 = R3[2];
             }
@@ -668,7 +675,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
 template <class T, class TI>
 inline void mask_args(MaskArgs<T, TI>& a, int64_t n, const TI* co, const Records<T>& rec, const Geo<T>& g, const Sinks<T, TI>& sk,
                       const TileShape& ts, uint32_t* masks) {
-  a.rec = rec; a.co = co; a.n = n; a.g = g; a.out = sk; a.masks = masks; a.cellflag = nullptr; a.skip_i = 0;
+  a.rec = rec; a.co = co; a.n = n; a.g = g; a.out = sk; a.masks = masks; a.cellflag = nullptr; a.skip_i = 0; a.self = nullptr;
   a.tx = ts.tx; a.ty = ts.ty; a.tz = ts.tz;
   a.ntx = (g.nc[0] + ts.tx - 1) / ts.tx; a.nty = (g.nc[1] + ts.ty - 1) / ts.ty; a.ntz = (g.nc[2] + ts.tz - 1) / ts.tz;
   a.mid = a.hw = a.dguard = 0.f;

@@ -243,6 +243,8 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
     a.cellflag = tsx.cellflag;
     a.mid = pl.th.mid; a.hw = pl.th.hw; a.dguard = pl.th.dguard;
     const unsigned nblk = (unsigned)((long long)a.ntx * a.nty * a.ntz);
+    static_assert(sizeof(MaskArgs<T, TI>) <= 1024, "argument block");
+    a.self = (const MaskArgs<T, TI>*)((char*)w.hdr + (MODE == MODE_FILL ? 2048 : (want_mask ? 0 : 3072)));
     if (MODE == MODE_FILL && !fill_tiled_requested()) {
       // original-order, thread-per-pair fill (nl_fillrows.cuh)
       k_fillrows_prologue<T, TI><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(w.pidx, sk.gmap, N, w.sorted_of, (RecAoS<T>*)w.ra);
@@ -269,16 +271,19 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
         NL_LAUNCHED(1);
         a.skip_i = 1;
       }
+      NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
       k_fill_mask<T, TI><<<nblk, TILE_NT, FILL_SMEM_BYTES, st>>>(a);
     } else if (want_mask) {
       static bool done = false;
       int rc = set_smem_once(k_count_mask<T, TI, true>, CNT_SMEM_BYTES, done);
       if (rc) return rc;
+      NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
       k_count_mask<T, TI, true><<<nblk, TILE_NT, CNT_SMEM_BYTES, st>>>(a);
     } else {
       static bool done = false;
       int rc = set_smem_once(k_count_mask<T, TI, false>, CNT_SMEM_BYTES, done);
       if (rc) return rc;
+      NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
       k_count_mask<T, TI, false><<<nblk, TILE_NT, CNT_SMEM_BYTES, st>>>(a);
     }
     NL_LAUNCHED(1);
