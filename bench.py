@@ -51,6 +51,16 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback"
 
 
+def fill_traffic(n_atoms):
+    """dram__bytes_read + dram__bytes_write of one fill launch, from the committed ncu capture (10 M-atom workload only)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_fill_traffic.json")) as f:
+            t = json.load(f)
+        return t["traffic_bytes_per_launch"] if n_atoms == 10_000_000 else None
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -289,8 +299,8 @@ def run_ours(args):
                        "stage_ms": {"count_stage": count_mean, "fill_kernel": fill_mean},
                        "step_roofline": {"bytes": step_bytes, "formula": "24 N + 48 P", "gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,
                                          "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak}},
-            "roofline": {"bound": "hbm", "kernel": "pair fill (nl_fill_pairs)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": which,
+            "roofline": {"bound": "hbm", "kernel": "pair fill (nl_fill_pairs: k_fill_mask)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": fill_traffic(n_atoms), "peak_source": which,
                          "bytes_per_launch": fill_bytes, "formula": "44 P + 36 N"},
             "e2e": {"value": P_total / (e2e_ms * 1e-3), "unit": "pairs/s",
                     "h2d_bytes_per_step": int(X_host.numel() * 8 + (0 if world == 1 else n_atoms * 8)),
