@@ -23,6 +23,7 @@
 // share one winding number, and fall back to exact_pair_hit otherwise.
 #pragma once
 #include <cmath>
+#include <type_traits>
 
 #include "nl_tiled.cuh"
 
@@ -463,7 +464,9 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_mask(const MaskA
 constexpr int FILL_SMEM_BYTES = NL_FILL_SMEM_KB * 1024;
 constexpr int FILL_WARP_BYTES = CELLTAB_BYTES + 4 * MASK_MAXCAND + 32 * 3 * 4 + 32 * 3 * 8 + 28 * 3 * 8;  // tables | 4 hit lists | S stage | R stage | cs table
 constexpr int FILL_FIXED_BYTES = 3 * TILE_VPAD * 4 + 64 * 4 + (TILE_NT / 32) * FILL_WARP_BYTES;
-template <class T> __host__ __device__ constexpr int fill_cap() { return (FILL_SMEM_BYTES - FILL_FIXED_BYTES) / (TileRecBytes<T>::value + 4) / 8 * 8; }
+template <class T, class TI> __host__ __device__ constexpr int fill_cap() {
+  return (FILL_SMEM_BYTES - FILL_FIXED_BYTES) / (TileRecBytes<T>::value + 4 + (int)sizeof(TI)) / 8 * 8;
+}
 static_assert(FILL_WARP_BYTES % 16 == 0 && FILL_FIXED_BYTES % 16 == 0, "alignment");
 
 #ifndef NL_FILL_MINB
@@ -472,7 +475,7 @@ static_assert(FILL_WARP_BYTES % 16 == 0 && FILL_FIXED_BYTES % 16 == 0, "alignmen
 template <class T, class TI>
 __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskArgs<T, TI> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  constexpr int CAP = fill_cap<T>();
+  constexpr int CAP = fill_cap<T, TI>();
   int* vstart = (int*)smem_raw;
   int* vgs = vstart + TILE_VPAD;
   int* vsh = vgs + TILE_VPAD;
@@ -484,6 +487,8 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
   uint32_t* sidx = (uint32_t*)(sz + CAP);
   uint32_t* sw = sidx + CAP;
   uint32_t* sgid = sw + CAP;  // shard mode: global index - 1 of each staged atom
+  typedef typename std::conditional<sizeof(TI) == 4, uint32_t, unsigned long long>::type BaseT;
+  BaseT* sbase = (BaseT*)(sgid + CAP);  // home slots: 0-based start of the atom's row (all ones: no row); gathered once per tile
   __shared__ int scan_sm[33];
   __shared__ int s_next;
 
@@ -536,6 +541,17 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
     sidx[sl] = a.rec.pidx[src];
     sw[sl] = a.rec.pw[src];
     if (a.out.pgid0) sgid[sl] = a.out.pgid0[src];
+    {  // row starts of the HOME atoms (interior virtual cells): one random gather per atom, all in flight together here
+      const int vx = v % VX, vy = (v / VX) % VY, vz = v / (VX * VY);
+      if (vx >= 1 && vx <= VX - 2 && vy >= 1 && vy <= VY - 2 && vz >= 1 && vz <= VZ - 2) {
+        const uint32_t io = sidx[sl];
+        sbase[sl] = (long long)io < a.out.n_rows ? (BaseT)(a.out.first[io] - 1) : ~(BaseT)0;
+      }
+    }
+  }
+  if (tid < nhome) {  // per-cell "masks valid" flags, fetched once per tile
+    const int lx = hcell[tid] & 255, ly = (hcell[tid] >> 8) & 255, lz = (hcell[tid] >> 16) & 255;
+    if (a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)]) hcell[tid] |= 1 << 24;
   }
   __syncthreads();
   const bool use_gid = a.out.pgid0 != nullptr;
@@ -545,12 +561,12 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
     if (lane == 0) hc = atomicAdd(&s_next, 1);
     hc = __shfl_sync(FULL, hc, 0);
     if (hc >= nhome) break;
-    const int lx = hcell[hc] & 255, ly = (hcell[hc] >> 8) & 255, lz = hcell[hc] >> 16;
+    const int lx = hcell[hc] & 255, ly = (hcell[hc] >> 8) & 255, lz = (hcell[hc] >> 16) & 255;
     const int vh = ((lz + 1) * VY + (ly + 1)) * VX + (lx + 1);
     const int hstart = vstart[vh], nh = vstart[vh + 1] - hstart;
     if (nh == 0) continue;
     const long long hg0 = vgs[vh];
-    if (!a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)]) {
+    if (!(hcell[hc] >> 24)) {
       generic_cell<T, TI, MODE_FILL>(a.self, hg0, nh, lane);
       continue;
     }
@@ -566,30 +582,22 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
     }
     __syncwarp();
 
-    // prefetch of the first pass
-    uint32_t nx_word = 0, nx_io = 0;
-    long long nx_base = 0;
-    if (grp < nh) {
-      nx_io = sidx[hstart + grp];
-      if ((long long)nx_io < a.out.n_rows) {  // atoms without a row (halo atoms of a shard) expand to nothing
-        nx_word = a.masks[(hg0 + grp) * MASK_WORDS + sub];
-        nx_base = (long long)a.out.first[nx_io] - 1;
-      }
-    }
+    // prefetch of the first pass (mask words only: row starts and indices are already in shared memory)
+    uint32_t nx_word = 0;
+    if (grp < nh && sbase[hstart + grp] != ~(BaseT)0) nx_word = a.masks[(hg0 + grp) * MASK_WORDS + sub];
 
     for (int a0 = 0; a0 < nh; a0 += 4) {
       // ---- four atoms at once: lane = 8 * atom + mask word
       uint32_t word = nx_word;
-      const uint32_t my_io = nx_io;
-      const long long my_base = nx_base;
-      nx_word = 0;
-      if (a0 + 4 + grp < nh) {  // next pass in flight while this one is expanded
-        nx_io = sidx[hstart + a0 + 4 + grp];
-        if ((long long)nx_io < a.out.n_rows) {
-          nx_word = a.masks[(hg0 + a0 + 4 + grp) * MASK_WORDS + sub];
-          nx_base = (long long)a.out.first[nx_io] - 1;
-        }
+      uint32_t my_io = 0;
+      long long my_base = 0;
+      if (a0 + grp < nh) {
+        my_io = sidx[hstart + a0 + grp];
+        my_base = (long long)sbase[hstart + a0 + grp];   // all ones (no row) comes with word == 0
       }
+      nx_word = 0;
+      if (a0 + 4 + grp < nh && sbase[hstart + a0 + 4 + grp] != ~(BaseT)0)  // next pass in flight while this one is expanded
+        nx_word = a.masks[(hg0 + a0 + 4 + grp) * MASK_WORDS + sub];
       const int pc = __popc(word);
       int incl = pc;
 #pragma unroll

@@ -185,7 +185,7 @@ template <class T> struct Plan {
   TileShape ts_exact, ts_count, ts_fill;
   MaskThresholds th;
 };
-template <class T> Plan<T> make_plan(const nl_params* p, const Geo<T>& g, int64_t N) {
+template <class T, class TI> Plan<T> make_plan(const nl_params* p, const Geo<T>& g, int64_t N) {
   Plan<T> pl;
   pl.path = PATH_GENERIC;
   pl.th = MaskThresholds{0.f, 0.f, 0.f, 0};
@@ -194,7 +194,7 @@ template <class T> Plan<T> make_plan(const nl_params* p, const Geo<T>& g, int64_
   pl.path = PATH_TILED;
   const double dens = (double)N / (double)g.nct;
   if (27.0 * dens > 200.0) return pl;  // candidate lists would overflow the 256-bit masks too often
-  if (!pick_tile<T>(g, N, CNT_CAP2, pl.ts_count) || !pick_tile<T>(g, N, fill_cap<T>(), pl.ts_fill)) return pl;
+  if (!pick_tile<T>(g, N, CNT_CAP2, pl.ts_count) || !pick_tile<T>(g, N, fill_cap<T, TI>(), pl.ts_fill)) return pl;
   if (sizeof(T) == 8) {
     pl.th = mask_thresholds(p->cell, p->ncells, pl.ts_count, (double)g.cutoff_sq);
     if (!pl.th.ok) return pl;
@@ -235,7 +235,7 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
              cudaStream_t st) {
   if (N <= 0) return NL_OK;
   Records<T> rec = records_of<T>(w);
-  const Plan<T> pl = make_plan<T>(p, g, N);
+  const Plan<T> pl = make_plan<T, TI>(p, g, N);
   if (pl.path == PATH_MASK && MODE != MODE_LJ) {
     TiledScratch tsx = tiled_scratch(w.tiled, N);
     MaskArgs<T, TI> a;
