@@ -31,7 +31,6 @@ namespace nl {
 
 constexpr int MASK_WORDS = 8;                  // 256 candidates
 constexpr int MASK_MAXCAND = 32 * MASK_WORDS;
-constexpr int CNT_SMEM_BYTES = 48 * 1024;      // count pass: 16 B per staged slot
 
 struct MaskThresholds { float mid, hw, dguard; int ok; };
 
@@ -80,7 +79,7 @@ __device__ __forceinline__ void unpack_shift(int p, long long s[3]) { s[0] = (p 
 
 // The exact contract for one pair given global sorted indices; returns r2 < cutoff_sq.
 template <class T, class TI>
-__device__ __noinline__ bool exact_pair_hit(const MaskArgs<T, TI>* ad, long long gi, long long gj, int shp) {
+__device__ __noinline__ bool exact_pair_hit(const MaskArgs<T, TI>* ad, long long gi, long long gj, int shp, T* r2_out = nullptr) {
   const Geo<T>& g = ad->g;
   const Records<T>& rec = ad->rec;
   const T xi = rec.px[gi], yi = rec.py[gi], zi = rec.pz[gi];
@@ -93,7 +92,9 @@ __device__ __noinline__ bool exact_pair_hit(const MaskArgs<T, TI>* ad, long long
   unpack_shift(shp, sl);
   const long long S[3] = {sl[0] + wi[0] - wj[0], sl[1] + wi[1] - wj[1], sl[2] + wi[2] - wj[2]};
   T R[3];
-  return pair_r2(g, xi, yi, zi, xj, yj, zj, S, R) < g.cutoff_sq;
+  const T r2 = pair_r2(g, xi, yi, zi, xj, yj, zj, S, R);
+  if (r2_out) *r2_out = r2;
+  return r2 < g.cutoff_sq;
 }
 
 // Shared tile prologue: virtual cell table (slot starts, global starts, packed shifts).
@@ -152,8 +153,10 @@ __device__ __noinline__ void slow_shift_and_R(const MaskArgs<T, TI>* ad, T xi, T
 
 // Generic per-atom route for the atoms [g0, g0 + n) of one cell (out of line: rare).
 template <class T, class TI, int MODE>
-__device__ __noinline__ void generic_cell(const MaskArgs<T, TI>* ad, long long g0, int n, int lane) {
-  for (int k = lane; k < n; k += 32) generic_atom<T, TI, MODE>(g0 + k, ad->rec, ad->co, ad->g, ad->out);
+__device__ __noinline__ double generic_cell(const MaskArgs<T, TI>* ad, long long g0, int n, int lane) {
+  double e = 0.0;
+  for (int k = lane; k < n; k += 32) e += generic_atom<T, TI, MODE>(g0 + k, ad->rec, ad->co, ad->g, ad->out);
+  return e;
 }
 
 // Per-warp candidate tables of one home cell: flat candidate index -> staged slot / virtual cell.
@@ -167,7 +170,8 @@ constexpr int CELLTAB_BYTES = MASK_MAXCAND * 3;
 // (tables are valid only if it is <= MASK_MAXCAND).  Lane c < 27 owns neighbour cell
 // c = (dz+1)*9 + (dy+1)*3 + (dx+1); flat order = cell order, then sorted order inside the cell.
 template <bool STORE_STENCIL_INDEX>
-__device__ __forceinline__ int build_cell_tables(const int* vstart, int VX, int VY, int lx, int ly, int lz, int lane, const CellTables& t) {
+__device__ __forceinline__ int build_cell_tables(const int* vstart, int VX, int VY, int lx, int ly, int lz, int lane, const CellTables& t,
+                                                 int cap = MASK_MAXCAND) {
   int v = 0, st = 0, cn = 0;
   if (lane < 27) {
     v = ((lz + lane / 9) * VY + (ly + (lane / 3) % 3)) * VX + (lx + lane % 3);
@@ -176,7 +180,7 @@ __device__ __forceinline__ int build_cell_tables(const int* vstart, int VX, int 
   }
   const int incl = warp_incl_scan(cn, lane);
   const int ncand = __shfl_sync(FULL, incl, 31);
-  if (ncand <= MASK_MAXCAND) {
+  if (ncand <= cap) {
     const int pre = incl - cn;
     const int mx = __reduce_max_sync(FULL, cn);
     for (int j = 0; j < mx; j++)
@@ -191,15 +195,22 @@ __device__ __forceinline__ long long cell_linear(const int nc[3], int cx, int cy
 }
 
 // ------------------------------------------------------------------------------------------------
-// Counting pass.  WANT_MASK: also store the hit masks (and per-cell flags) for the fill pass.
+// Counting pass, three sinks (CM):
+//   CM_MASK  counts + hit masks + per-cell flags for the fill pass (candidate lists up to 256)
+//   CM_COUNT counts only: the lazy count_neighbours sink (candidate lists up to 512, so denser systems stay on this path)
+//   CM_LJ    fused Lennard-Jones energy over the hits, Float32 positions (BASELINE config 5); no counts, no masks
+enum { CM_MASK = 0, CM_COUNT = 1, CM_LJ = 2 };
+__host__ __device__ constexpr int cm_tabcap(int cm) { return cm == CM_MASK ? MASK_MAXCAND : 2 * MASK_MAXCAND; }
+__host__ __device__ constexpr int cm_smem_bytes(int cm) { return cm == CM_MASK ? 48 * 1024 : 64 * 1024; }
+__host__ __device__ constexpr int cm_warp_bytes(int cm) { return cm_tabcap(cm) * 3 + MASK_WORDS * 34 * 4 + 16 * 32; }
+__host__ __device__ constexpr int cm_fixed_bytes(int cm) { return 3 * TILE_VPAD * 4 + 64 * 4 + (TILE_NT / 32) * cm_warp_bytes(cm); }
+__host__ __device__ constexpr int cm_cap(int cm) { return (cm_smem_bytes(cm) - cm_fixed_bytes(cm)) / 16 / 8 * 8; }
+static_assert(cm_warp_bytes(CM_MASK) % 16 == 0 && cm_fixed_bytes(CM_MASK) % 16 == 0 && cm_warp_bytes(CM_COUNT) % 16 == 0, "alignment");
 //
 // Shared memory: tile tables | per-warp {cell tables, chunk-major mask words, home-atom pair buffer} |
 // float4 per staged slot: Float64 -> (q.xyz = Float32 image-relative position, w = 1 if the slot needs
 // the exact path); Float32 -> (absolute x, y, z, packed winding).
-constexpr int CNT_WARP_BYTES = CELLTAB_BYTES + MASK_WORDS * 34 * 4 + 16 * 32;
-constexpr int CNT_FIXED_BYTES = 3 * TILE_VPAD * 4 + 64 * 4 + (TILE_NT / 32) * CNT_WARP_BYTES;
-constexpr int CNT_CAP2 = (CNT_SMEM_BYTES - CNT_FIXED_BYTES) / 16 / 8 * 8;
-static_assert(CNT_WARP_BYTES % 16 == 0 && CNT_FIXED_BYTES % 16 == 0, "alignment");
+constexpr int CNT_CAP2 = cm_cap(CM_MASK);
 
 constexpr float CAND_FAR = 1.0e18f;   // lanes beyond the candidate list: finite "nowhere" (squares stay finite in Float32)
 constexpr float SLOT_FAR = -1.0e18f;  // staged slots that need the exact path: far from everything, including CAND_FAR
@@ -207,8 +218,13 @@ constexpr float SLOT_FAR = -1.0e18f;  // staged slots that need the exact path: 
 #ifndef NL_CNT_MINB
 #define NL_CNT_MINB 4
 #endif
-template <class T, class TI, bool WANT_MASK>
-__global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_mask(const MaskArgs<T, TI> a) {
+template <class T, class TI, int CM>
+__global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : 3) k_count_mask(const MaskArgs<T, TI> a) {
+  constexpr bool WANT_MASK = CM == CM_MASK;
+  constexpr int TABCAP = cm_tabcap(CM);
+  constexpr int CNT_WARP_BYTES = cm_warp_bytes(CM);
+  constexpr int CAPSLOTS = cm_cap(CM);
+  static_assert(CM != CM_LJ || sizeof(T) == 4, "the fused LJ sink of this kernel is Float32 only");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* vstart = (int*)smem_raw;
   int* vgs = vstart + TILE_VPAD;
@@ -224,9 +240,10 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_mask(const MaskA
   unsigned char* wb = wbase + wid * CNT_WARP_BYTES;
   CellTables tab;
   tab.cslot = (uint16_t*)wb;
-  tab.cv = (uint8_t*)(wb + MASK_MAXCAND * 2);
-  uint32_t* mkT = (uint32_t*)(wb + CELLTAB_BYTES);                          // [MASK_WORDS][34]: word kc of home atom aa at kc*34 + aa
-  float* hb = (float*)(wb + CELLTAB_BYTES + MASK_WORDS * 34 * 4);           // [16 pairs][8]: x0 x1 y0 y1 z0 z1 f0 f1
+  tab.cv = (uint8_t*)(wb + TABCAP * 2);
+  uint32_t* mkT = (uint32_t*)(wb + TABCAP * 3);                             // [MASK_WORDS][34]: word (kc & 7) of home atom aa at (kc & 7)*34 + aa
+  float* hb = (float*)(wb + TABCAP * 3 + MASK_WORDS * 34 * 4);              // [16 pairs][8]: x0 x1 y0 y1 z0 z1 f0 f1
+  double e_acc = 0.0;                                                       // CM_LJ: this lane's share of the energy
 
   const int b = blockIdx.x;
   const int hx0 = (b % a.ntx) * a.tx, hy0 = ((b / a.ntx) % a.nty) * a.ty, hz0 = (b / (a.ntx * a.nty)) * a.tz;
@@ -246,16 +263,18 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_mask(const MaskA
   if (tid == 0) s_next = 0;
   __syncthreads();
 
-  if (total > CNT_CAP2) {
+  constexpr int GMODE = CM == CM_LJ ? MODE_LJ : MODE_COUNT;
+  const bool tile_generic = total > CAPSLOTS;   // denser than the staging capacity: the whole tile takes the generic route
+  if (tile_generic) {
     for (int hc = wid; hc < nhome; hc += TILE_NT / 32) {
       const int lx = hcell[hc] & 255, ly = (hcell[hc] >> 8) & 255, lz = hcell[hc] >> 16;
       const int vh = ((lz + 1) * VY + (ly + 1)) * VX + (lx + 1);
       const int nh = vstart[vh + 1] - vstart[vh];
-      generic_cell<T, TI, MODE_COUNT>(a.self, (long long)vgs[vh], nh, lane);
+      e_acc += generic_cell<T, TI, GMODE>(a.self, (long long)vgs[vh], nh, lane);
       if (WANT_MASK && lane == 0) a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)] = 0;
     }
-    return;
   }
+  if (!tile_generic) {
 
   // ---- stage
   if constexpr (sizeof(T) == 8) {
@@ -307,10 +326,10 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_mask(const MaskA
     const int hstart = vstart[vh], nh = vstart[vh + 1] - hstart;
     if (nh == 0) continue;
     const long long hg0 = vgs[vh];
-    const int ncand = build_cell_tables<false>(vstart, VX, VY, lx, ly, lz, lane, tab);
-    if (WANT_MASK && lane == 0) a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)] = ncand <= MASK_MAXCAND ? 1 : 0;
-    if (ncand > MASK_MAXCAND) {  // too many candidates for a 256-bit mask: generic route (the fill pass does the same)
-      generic_cell<T, TI, MODE_COUNT>(a.self, hg0, nh, lane);
+    const int ncand = build_cell_tables<false>(vstart, VX, VY, lx, ly, lz, lane, tab, TABCAP);
+    if (WANT_MASK && lane == 0) a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)] = ncand <= TABCAP ? 1 : 0;
+    if (ncand > TABCAP) {  // too many candidates for the tables / the 256-bit masks: generic route (the fill pass does the same)
+      e_acc += generic_cell<T, TI, GMODE>(a.self, hg0, nh, lane);
       continue;
     }
     const int nchunk = (ncand + 31) >> 5;
@@ -347,6 +366,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_mask(const MaskA
         slow_group = __any_sync(FULL, lane < ng && (my_w != W0 || (my_w & WIND_OVERFLOW)));
       }
       const unsigned hbad = (sizeof(T) == 8) ? __ballot_sync(FULL, my_bad) : 0u;
+      uint32_t cnt_acc = 0;  // lane aa < ng: neighbours of home atom aa so far
       __syncwarp();
 
       for (int kc = 0; kc < nchunk; kc++) {
@@ -375,7 +395,8 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_mask(const MaskA
           }
         }
         float bmin = 3.0e38f;  // min |t| over this lane's pairs: <= hw means some pair fell in the uncertainty band
-        uint32_t* mrow = mkT + kc * 34;
+        uint32_t* mrow = mkT + (kc & (MASK_WORDS - 1)) * 34;
+        const int self_aa = valid ? (int)tab.cslot[f] - (hstart + g0) : -1;  // the home atom this candidate IS under zero shift (CM_LJ)
 
         if constexpr (sizeof(T) == 8) {
           const float2 nqx = make_float2(-qx, -qx), nqy = make_float2(-qy, -qy), nqz = make_float2(-qz, -qz);
@@ -409,9 +430,22 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_mask(const MaskA
             // explicit .rn and -fmad=false (verified in SASS), which would break the unfused contract
             const float2 p0 = mul2_rn(R0, R0), p1 = mul2_rn(R1, R1), p2 = mul2_rn(R2, R2);
             const float r2x = __fadd_rn(__fadd_rn(p0.x, p1.x), p2.x), r2y = __fadd_rn(__fadd_rn(p0.y, p1.y), p2.y);
-            const unsigned b0 = __ballot_sync(FULL, valid && r2x < csqf);
-            const unsigned b1 = __ballot_sync(FULL, valid && r2y < csqf);
-            *(uint2*)(mrow + 2 * pr) = make_uint2(b0, b1);
+            if (CM == CM_LJ) {
+              if (!slow_group && !cand_bad) {  // otherwise the exact pass below accumulates this chunk
+                if (valid && r2x < csqf && 2 * pr != self_aa) {
+                  const double s2 = a.out.lj_sigma2 / (double)r2x, s6 = s2 * s2 * s2;
+                  e_acc += 4.0 * a.out.lj_eps * (s6 * s6 - s6);
+                }
+                if (valid && r2y < csqf && 2 * pr + 1 != self_aa && 2 * pr + 1 < ng) {
+                  const double s2 = a.out.lj_sigma2 / (double)r2y, s6 = s2 * s2 * s2;
+                  e_acc += 4.0 * a.out.lj_eps * (s6 * s6 - s6);
+                }
+              }
+            } else {
+              const unsigned b0 = __ballot_sync(FULL, valid && r2x < csqf);
+              const unsigned b1 = __ballot_sync(FULL, valid && r2y < csqf);
+              *(uint2*)(mrow + 2 * pr) = make_uint2(b0, b1);
+            }
           }
         }
         __syncwarp();
@@ -425,31 +459,53 @@ __global__ void __launch_bounds__(TILE_NT, NL_CNT_MINB) k_count_mask(const MaskA
               const float t = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, -mid)));
               hit = valid && t < -hw;
               if (valid && (cand_bad || ((hbad >> aa) & 1u) || fabsf(t) <= hw)) hit = exact_pair_hit<T, TI>(a.self, hg0 + g0 + aa, gj, shp);
+            } else if (CM == CM_LJ) {
+              hit = false;
+              if (valid && (slow_group || cand_bad) && aa != self_aa) {  // exactly the pairs the fast loop skipped
+                T r2e;
+                if (exact_pair_hit<T, TI>(a.self, hg0 + g0 + aa, gj, shp, &r2e)) {
+                  const double s2 = a.out.lj_sigma2 / (double)r2e, s6 = s2 * s2 * s2;
+                  e_acc += 4.0 * a.out.lj_eps * (s6 * s6 - s6);
+                }
+              }
             } else {
               hit = valid && exact_pair_hit<T, TI>(a.self, hg0 + g0 + aa, gj, shp);
             }
-            const unsigned bal = __ballot_sync(FULL, hit);
-            if (lane == 0) mrow[aa] = bal;
+            if (CM != CM_LJ) {
+              const unsigned bal = __ballot_sync(FULL, hit);
+              if (lane == 0) mrow[aa] = bal;
+            }
           }
           __syncwarp();
         }
-        // drop the self pair (same atom, zero shift): flat index fh + g0 + aa of home atom aa
-        if (lane < ng) {
+        // drop the self pair (same atom, zero shift): flat index fh + g0 + aa of home atom aa; accumulate the counts
+        if (CM != CM_LJ && lane < ng) {
           const int fs = fh + g0 + lane;
           if ((fs >> 5) == kc) mrow[lane] &= ~(1u << (fs & 31));
+          cnt_acc += __popc(mrow[lane]);
         }
+        if (CM != CM_MASK) __syncwarp();  // the mask rows are a ring of MASK_WORDS chunks
       }
       __syncwarp();
-      // per-atom counts from the masks; masks to global (atom-major, MASK_WORDS per atom)
-      if (lane < ng) {
-        uint32_t c = 0;
-        for (int k = 0; k < nchunk; k++) c += __popc(mkT[k * 34 + lane]);
-        a.out.counts[a.rec.pidx[hg0 + g0 + lane]] = c;
-      }
+      // per-atom counts; masks to global (atom-major, MASK_WORDS per atom)
+      if (CM != CM_LJ && lane < ng) a.out.counts[a.rec.pidx[hg0 + g0 + lane]] = cnt_acc;
       if (WANT_MASK) {
         uint32_t* dst = a.masks + (hg0 + g0) * MASK_WORDS;
         for (int w = lane; w < ng * MASK_WORDS; w += 32) dst[w] = (w & 7) < nchunk ? mkT[(w & 7) * 34 + (w >> 3)] : 0u;
       }
+    }
+  }
+  }  // !tile_generic
+  if (CM == CM_LJ) {
+    __shared__ double s_energy[TILE_NT / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e_acc += __shfl_xor_sync(FULL, e_acc, o);
+    if (lane == 0) s_energy[wid] = e_acc;
+    __syncthreads();
+    if (tid == 0) {
+      double e = 0.0;
+      for (int w = 0; w < TILE_NT / 32; w++) e += s_energy[w];
+      if (e != 0.0) atomicAdd(a.out.energy, e);
     }
   }
 }

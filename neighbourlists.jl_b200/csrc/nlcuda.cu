@@ -184,15 +184,27 @@ template <class T> struct Plan {
   int path;
   TileShape ts_exact, ts_count, ts_fill;
   MaskThresholds th;
+  int lazy_ok;          // the packed counting kernel can serve the lazy sinks (count; LJ for Float32)
+  TileShape ts_lazy;
+  MaskThresholds th_lazy;
 };
 template <class T, class TI> Plan<T> make_plan(const nl_params* p, const Geo<T>& g, int64_t N) {
   Plan<T> pl;
   pl.path = PATH_GENERIC;
   pl.th = MaskThresholds{0.f, 0.f, 0.f, 0};
+  pl.th_lazy = pl.th;
+  pl.lazy_ok = 0;
   if (N <= 0) return pl;
   if (!tiled_applicable<T>(p, g, N, tile_cap<T>(), pl.ts_exact)) return pl;
   pl.path = PATH_TILED;
   const double dens = (double)N / (double)g.nct;
+  if (27.0 * dens <= 400.0 && pick_tile<T>(g, N, cm_cap(CM_COUNT), pl.ts_lazy)) {  // candidate tables hold 512 entries
+    pl.lazy_ok = 1;
+    if (sizeof(T) == 8) {
+      pl.th_lazy = mask_thresholds(p->cell, p->ncells, pl.ts_lazy, (double)g.cutoff_sq);
+      pl.lazy_ok = pl.th_lazy.ok;
+    }
+  }
   if (27.0 * dens > 200.0) return pl;  // candidate lists would overflow the 256-bit masks too often
   if (!pick_tile<T>(g, N, CNT_CAP2, pl.ts_count) || !pick_tile<T>(g, N, fill_cap<T, TI>(), pl.ts_fill)) return pl;
   if (sizeof(T) == 8) {
@@ -236,7 +248,24 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
   if (N <= 0) return NL_OK;
   Records<T> rec = records_of<T>(w);
   const Plan<T> pl = make_plan<T, TI>(p, g, N);
-  if (pl.path == PATH_MASK && MODE != MODE_LJ) {
+  constexpr bool LJ_FAST = MODE == MODE_LJ && sizeof(T) == 4;
+  if (pl.lazy_ok && ((MODE == MODE_COUNT && !want_mask) || LJ_FAST)) {
+    // lazy sinks on the packed counting kernel: no masks, candidate lists up to 512
+    constexpr int CM = MODE == MODE_LJ ? CM_LJ : CM_COUNT;
+    MaskArgs<T, TI> a;
+    mask_args<T, TI>(a, N, (const TI*)co, rec, g, sk, pl.ts_lazy, nullptr);
+    a.mid = pl.th_lazy.mid; a.hw = pl.th_lazy.hw; a.dguard = pl.th_lazy.dguard;
+    a.self = (const MaskArgs<T, TI>*)((char*)w.hdr + 3072);
+    NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
+    const unsigned nblk = (unsigned)((long long)a.ntx * a.nty * a.ntz);
+    if constexpr (CM == CM_COUNT || LJ_FAST) {
+      static bool done = false;
+      int rc = set_smem_once(k_count_mask<T, TI, CM>, cm_smem_bytes(CM), done);
+      if (rc) return rc;
+      k_count_mask<T, TI, CM><<<nblk, TILE_NT, cm_smem_bytes(CM), st>>>(a);
+    }
+    NL_LAUNCHED(1);
+  } else if (pl.path == PATH_MASK && MODE != MODE_LJ) {
     TiledScratch tsx = tiled_scratch(w.tiled, N);
     MaskArgs<T, TI> a;
     mask_args<T, TI>(a, N, (const TI*)co, rec, g, sk, MODE == MODE_FILL ? pl.ts_fill : pl.ts_count, tsx.masks);
@@ -273,18 +302,13 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
       }
       NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
       k_fill_mask<T, TI><<<nblk, TILE_NT, FILL_SMEM_BYTES, st>>>(a);
-    } else if (want_mask) {
-      static bool done = false;
-      int rc = set_smem_once(k_count_mask<T, TI, true>, CNT_SMEM_BYTES, done);
-      if (rc) return rc;
-      NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
-      k_count_mask<T, TI, true><<<nblk, TILE_NT, CNT_SMEM_BYTES, st>>>(a);
     } else {
+      // MODE_COUNT: with masks for the fill pass, or (lazy count on a problem the lazy plan rejected) without
       static bool done = false;
-      int rc = set_smem_once(k_count_mask<T, TI, false>, CNT_SMEM_BYTES, done);
+      int rc = set_smem_once(k_count_mask<T, TI, CM_MASK>, cm_smem_bytes(CM_MASK), done);
       if (rc) return rc;
       NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
-      k_count_mask<T, TI, false><<<nblk, TILE_NT, CNT_SMEM_BYTES, st>>>(a);
+      k_count_mask<T, TI, CM_MASK><<<nblk, TILE_NT, cm_smem_bytes(CM_MASK), st>>>(a);
     }
     NL_LAUNCHED(1);
   } else if (pl.path != PATH_GENERIC) {
