@@ -167,9 +167,13 @@ def neighbour_list_sharded(X_local, gidx_local, cutoff, cell, pbc, *, group=None
         recv_counts = torch.empty_like(send_counts)
         dist.all_to_all_single(recv_counts, send_counts, group=group)
         sc, rc = send_counts.cpu().tolist(), recv_counts.cpu().tolist()
-        X = torch.cat([X[stay], _a2a(X[order], sc, rc, group)])
-        gidx = torch.cat([gidx[stay], _a2a(gidx[order], sc, rc, group)])
-        planes = torch.cat([planes[stay], _a2a(planes[order], sc, rc, group)])
+        # the exchanges are collective: every rank takes part even with nothing to send or receive
+        rX, rg, rp = _a2a(X[order], sc, rc, group), _a2a(gidx[order], sc, rc, group), _a2a(planes[order], sc, rc, group)
+        if leave.numel() > 0:                          # compact only if something left; one index for the three arrays
+            keep = stay.nonzero().flatten()
+            X, gidx, planes = X.index_select(0, keep), gidx.index_select(0, keep), planes.index_select(0, keep)
+        if rX.shape[0] > 0:
+            X, gidx, planes = torch.cat([X, rX]), torch.cat([gidx, rg]), torch.cat([planes, rp])
     n_owned = int(X.shape[0])
     ph.mark("redistribute")
 
