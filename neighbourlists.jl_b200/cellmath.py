@@ -74,7 +74,25 @@ def analyze_cell(cell, cutoff, dtype) -> tuple:
     return inv, ncells, lens, nxyz
 
 
+_GEO_CACHE: dict = {}
+
+
 def geometry(cell, cutoff, pbc, dtype) -> CellGeometry:
+    """analyze_cell + nxyz for (cell, cutoff, pbc) in `dtype`; memoised (the scalar numpy arithmetic costs ~0.1 ms,
+    which matters for the 10k-atom case where the whole list takes 0.4 ms)."""
+    dt = np.dtype(dtype)
+    key = (np.asarray(cell, dtype=dt).tobytes(), float(dt.type(cutoff)), tuple(bool(b) for b in pbc), dt.str)
+    hit = _GEO_CACHE.get(key)
+    if hit is not None:
+        return hit
+    if len(_GEO_CACHE) > 256:
+        _GEO_CACHE.clear()
+    geo = _geometry_uncached(cell, cutoff, pbc, dt)
+    _GEO_CACHE[key] = geo
+    return geo
+
+
+def _geometry_uncached(cell, cutoff, pbc, dtype) -> CellGeometry:
     dt = np.dtype(dtype)
     inv, ncells, lens, nxyz = analyze_cell(cell, cutoff, dt)
     return CellGeometry(dtype=dt, cell=np.asarray(cell, dtype=dt).reshape(3, 3).copy(), inv_cell=inv, lens=lens, ncells=ncells,
