@@ -96,28 +96,6 @@ __device__ __forceinline__ int select_bit(uint32_t w, int r) {
   return pos;
 }
 
-// The `i` array alone, as a pure unit-stride stream: i[p] = (published index of) the row that contains p.
-// Taking it out of the sorted-order fill removes one short (~100 B) randomly placed segment per row.
-constexpr int FI_ROWS = 1024;
-template <class TI>
-__global__ void __launch_bounds__(256) k_fill_i(const TI* __restrict__ first, long long n_rows, const TI* __restrict__ gmap, TI* __restrict__ io) {
-  __shared__ int s_first[FI_ROWS + 1];
-  const long long r0 = (long long)blockIdx.x * FI_ROWS;
-  const int nrow = (int)min((long long)FI_ROWS, n_rows - r0);
-  const long long p0 = (long long)first[r0] - 1;
-  for (int t = threadIdx.x; t <= nrow; t += 256) s_first[t] = (int)((long long)first[r0 + t] - 1 - p0);
-  __syncthreads();
-  const int total = s_first[nrow];
-  for (int pl = threadIdx.x; pl < total; pl += 256) {
-    int lo = 0, hi = nrow;  // last row with s_first[row] <= pl
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (s_first[mid] <= pl) lo = mid; else hi = mid;
-    }
-    io[p0 + pl] = gmap ? gmap[r0 + lo] : (TI)(r0 + lo + 1);
-  }
-}
-
 template <class T, class TI>
 __global__ void __launch_bounds__(FR_NT, 3) k_fill_rows(const FillRowsArgs<T, TI> a) {
   __shared__ int s_first[FR_RB + 1];      // row starts relative to the block's first pair

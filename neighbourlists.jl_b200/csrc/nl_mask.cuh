@@ -66,7 +66,6 @@ template <class T, class TI> struct MaskArgs {
   Sinks<T, TI> out;
   uint32_t* masks;    // n * MASK_WORDS, sorted order
   uint8_t* cellflag;  // per cell: 1 if the count pass stored masks for its atoms
-  int skip_i;         // fill pass: the i array is written by k_fill_i instead
   int tx, ty, tz, ntx, nty, ntz;
   float mid, hw, dguard;
   const MaskArgs<T, TI>* self;  // this struct in GLOBAL memory: the rare out-of-line paths read their inputs from there, so the
@@ -719,7 +718,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
             }
             stS[3 * lane] = S0; stS[3 * lane + 1] = S1; stS[3 * lane + 2] = S2;
             if (Ro_row) { stR[3 * lane] = R0; stR[3 * lane + 1] = R1; stR[3 * lane + 2] = R2; }
-            if (!a.skip_i) io_row[r] = io_out;
+            io_row[r] = io_out;
             jo_row[r] = use_gid ? (TI)sgid[slot] + 1 : (TI)sidx[slot] + 1;
           }
           __syncwarp();
@@ -743,7 +742,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
 template <class T, class TI>
 inline void mask_args(MaskArgs<T, TI>& a, int64_t n, const TI* co, const Records<T>& rec, const Geo<T>& g, const Sinks<T, TI>& sk,
                       const TileShape& ts, uint32_t* masks) {
-  a.rec = rec; a.co = co; a.n = n; a.g = g; a.out = sk; a.masks = masks; a.cellflag = nullptr; a.skip_i = 0; a.self = nullptr;
+  a.rec = rec; a.co = co; a.n = n; a.g = g; a.out = sk; a.masks = masks; a.cellflag = nullptr; a.self = nullptr;
   a.tx = ts.tx; a.ty = ts.ty; a.tz = ts.tz;
   a.ntx = (g.nc[0] + ts.tx - 1) / ts.tx; a.nty = (g.nc[1] + ts.ty - 1) / ts.ty; a.ntz = (g.nc[2] + ts.tz - 1) / ts.tz;
   a.mid = a.hw = a.dguard = 0.f;

@@ -294,12 +294,6 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
       static bool done = false;
       int rc = set_smem_once(k_fill_mask<T, TI>, FILL_SMEM_BYTES, done);
       if (rc) return rc;
-      // (k_fill_i can write `i` as a separate unit-stride stream -- measured: no gain, 8.9 vs 8.3 ms -- so it stays off)
-      if (false && sk.n_rows > 0) {
-        k_fill_i<TI><<<(unsigned)((sk.n_rows + FI_ROWS - 1) / FI_ROWS), 256, 0, st>>>(sk.first, sk.n_rows, sk.gmap, sk.io);
-        NL_LAUNCHED(1);
-        a.skip_i = 1;
-      }
       NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
       k_fill_mask<T, TI><<<nblk, TILE_NT, FILL_SMEM_BYTES, st>>>(a);
     } else {

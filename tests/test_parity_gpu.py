@@ -298,3 +298,30 @@ def test_near_threshold_decisions(nl, dtype):
     e = pl.cpu()
     dimer = int((np.abs(e["i"].astype(np.int64) - e["j"].astype(np.int64)) == n_d).sum()) / (2 * n_d)
     assert 0.2 < dimer < 0.8, dimer
+
+
+def test_original_order_fill_variant():
+    """The alternative fill kernel (k_fill_rows: original atom order, one thread per pair; selected with
+    NL_FILL_ROWS=1, read once per process) must produce the same lists.  Runs in a subprocess."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, torch, sys
+sys.path.insert(0, %r)
+import neighbourlists_jl_b200 as nl
+from oracle import nl_oracle as O
+from tests import util as U
+for dtype, pbc, cell, N, rc in ((np.float64, (True, True, True), None, 20000, 5.0), (np.float32, (True, False, True), U.TRICLINIC * 3, 4000, 3.0)):
+    if cell is None:
+        X, cell, _ = U.rand_config(N, seed=5, dtype=dtype)
+    else:
+        X = U.displace_by_lattice(U.rand_in_cell(N, cell, seed=6, dtype=dtype), cell, pbc)
+    pl = nl.neighbour_list(torch.from_numpy(X).cuda(), rc, cell.astype(dtype), pbc, with_R=True)
+    orc = O.sortbased(X, rc, cell.astype(dtype), pbc, dtype=dtype)
+    U.assert_engine_matches_oracle(pl.cpu(), orc, 1e-12 if dtype == np.float64 else 1e-5, msg="fill_rows")
+print("OK")
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, NL_FILL_ROWS="1")
+    out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
