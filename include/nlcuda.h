@@ -123,6 +123,12 @@ NL_API int nl_fill_pairs_rows(const nl_params* params, const void* X_sorted, int
  * (replaces _compute_cell_ids, src/gpu_kernels.jl:244-255,378).  The slab sharding bins atoms with it. */
 NL_API int nl_cell_ids(const nl_params* params, const void* X, int64_t N, void* cell_id_out, void* stream);
 
+/* Slab plan for multi-GPU sharding (host-only, no CUDA call): cuts the `nplanes` cell planes of the slab axis into
+ * `nranks` slabs balanced by atom count.  plane_hist[nplanes] = atoms per plane (already summed over ranks);
+ * halo = nxyz of the slab axis; every slab gets at least 2*halo+1 planes (1 if nranks == 1).
+ * bounds_out[nranks+1]: rank r owns planes [bounds[r], bounds[r+1]).  NL_ERR_BAD_ARG if the planes do not suffice. */
+NL_API int nl_shard_plan(const int64_t* plane_hist, int32_t nplanes, int32_t nranks, int32_t halo, int64_t* bounds_out);
+
 /* Lazy mode: fused for_each_neighbour traversals (src/cell_list.jl:779-801) with fixed sinks.
  * nl_lazy_count: counts_out[m] (N TI, original order) = count_neighbours(clist, m) (:808-814).
  * nl_lazy_lj_energy: *energy_out (DEVICE double) = sum over ordered pairs of

@@ -45,7 +45,7 @@ class NlError(RuntimeError):
 _lib = None
 
 EXPORTS = ("nl_version", "nl_strerror", "nl_last_cuda_error", "nl_launch_count", "nl_workspace_bytes", "nl_build_cells", "nl_count_pairs",
-           "nl_fill_pairs", "nl_fill_pairs_rows", "nl_cell_ids", "nl_lazy_count", "nl_lazy_lj_energy")
+           "nl_fill_pairs", "nl_fill_pairs_rows", "nl_cell_ids", "nl_shard_plan", "nl_lazy_count", "nl_lazy_lj_energy")
 
 
 def lib():
@@ -69,9 +69,11 @@ def lib():
         L.nl_fill_pairs.argtypes = [pp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
         L.nl_fill_pairs_rows.argtypes = [pp, vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, sz, vp]
         L.nl_cell_ids.argtypes = [pp, vp, i64, vp, vp]
+        L.nl_shard_plan.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp]
+        L.nl_shard_plan.restype = C.c_int
         L.nl_lazy_count.argtypes = [pp, vp, i64, vp, vp, vp, vp, sz, vp]
         L.nl_lazy_lj_energy.argtypes = [pp, vp, i64, vp, vp, C.c_double, C.c_double, vp, vp, sz, vp]
-        for n in ("nl_build_cells", "nl_count_pairs", "nl_fill_pairs", "nl_fill_pairs_rows", "nl_cell_ids", "nl_lazy_count", "nl_lazy_lj_energy"):
+        for n in ("nl_build_cells", "nl_count_pairs", "nl_fill_pairs", "nl_fill_pairs_rows", "nl_cell_ids", "nl_shard_plan", "nl_lazy_count", "nl_lazy_lj_energy"):
             getattr(L, n).restype = C.c_int
         _lib = L
     return _lib

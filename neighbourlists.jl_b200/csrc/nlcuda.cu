@@ -485,6 +485,29 @@ int nl_fill_pairs_rows(const nl_params* params, const void* X_sorted, int64_t N,
                      (cudaStream_t)stream);
 }
 
+int nl_shard_plan(const int64_t* plane_hist, int32_t nplanes, int32_t nranks, int32_t halo, int64_t* bounds_out) {
+  if (!plane_hist || !bounds_out || nplanes < 1 || nranks < 1 || halo < 0) return NL_ERR_BAD_ARG;
+  const long long minw = nranks > 1 ? 2ll * halo + 1 : 1;
+  if ((long long)nranks * minw > nplanes) return NL_ERR_BAD_ARG;
+  long long total = 0;
+  for (int p = 0; p < nplanes; p++) total += plane_hist[p];
+  bounds_out[0] = 0;
+  long long cum = 0;  // atoms in planes [0, b)
+  int b = 0;
+  for (int r = 1; r < nranks; r++) {
+    // smallest b with cum(b) >= total * r / nranks   (exact rational comparison: cum * nranks >= total * r)
+    while (b < nplanes && (__int128)cum * nranks < (__int128)total * r) cum += plane_hist[b++];
+    long long bb = b;
+    if (bb < bounds_out[r - 1] + minw) bb = bounds_out[r - 1] + minw;              // this slab wide enough
+    if (bb > nplanes - (long long)(nranks - r) * minw) bb = nplanes - (long long)(nranks - r) * minw;  // room for the rest
+    while (b < bb) cum += plane_hist[b++];
+    while (b > bb) cum -= plane_hist[--b];
+    bounds_out[r] = bb;
+  }
+  bounds_out[nranks] = nplanes;
+  return NL_OK;
+}
+
 int nl_cell_ids(const nl_params* params, const void* X, int64_t N, void* cell_id_out, void* stream) {
   int rc = check_params(params, N);
   if (rc) return rc;

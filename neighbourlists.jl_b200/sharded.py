@@ -70,8 +70,8 @@ def plan_slabs(plane_hist: np.ndarray, world: int, halo: int, periodic: bool, ax
     total = int(cum[-1])
     bounds = [0]
     for r in range(1, world):
-        target = total * r / world
-        b = int(np.searchsorted(cum, target, side="left"))
+        # smallest b with cum[b] >= total * r / world, compared exactly (same rule as nl_shard_plan in the library)
+        b = int(np.searchsorted(cum * world, total * r, side="left"))
         b = max(b, bounds[-1] + minw)            # this slab wide enough
         b = min(b, n - (world - r) * minw)       # room for the remaining slabs
         bounds.append(b)

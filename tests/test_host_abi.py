@@ -91,3 +91,30 @@ def test_no_cpu_fallback():
         pytest.skip("GPU present")
     with pytest.raises(nl.NlError):
         nl.neighbour_list(np.zeros((4, 3)), 1.0, np.eye(3) * 5, (True, True, True))
+
+
+def test_shard_plan_matches_host_logic():
+    """nl_shard_plan (C, for the Julia driver) == sharded.plan_slabs (Python driver) on random histograms."""
+    from importlib import import_module
+    sh = import_module("neighbourlists_jl_b200.sharded")
+    L = nl._lib.lib()
+    rng = np.random.default_rng(4)
+    for t in range(300):
+        nplanes = int(rng.integers(1, 200))
+        world = int(rng.integers(1, 9))
+        halo = int(rng.integers(0, 3))
+        hist = rng.integers(0, 1000, nplanes).astype(np.int64)
+        if t % 7 == 0:
+            hist[rng.integers(0, nplanes)] += 10 ** 6  # one very dense plane
+        out = np.zeros(world + 1, np.int64)
+        rc = L.nl_shard_plan(hist.ctypes.data_as(C.c_void_p), nplanes, world, halo, out.ctypes.data_as(C.c_void_p))
+        minw = 2 * halo + 1 if world > 1 else 1
+        if world * minw > nplanes:
+            assert rc == nl._lib.NL_ERR_BAD_ARG
+            with pytest.raises(ValueError):
+                sh.plan_slabs(hist, world, halo, True, 0)
+            continue
+        assert rc == 0
+        ref = sh.plan_slabs(hist, world, halo, True, 0).bounds
+        assert np.array_equal(out, ref), (hist, world, halo, out, ref)
+        assert out[0] == 0 and out[-1] == nplanes and np.all(np.diff(out) >= minw)
