@@ -14,7 +14,7 @@
 // /root/reference).
 //
 // Every function cites the reference file:line it follows (paths relative to /root/reference).
-// Build: see oracle/Makefile (g++ -O2 -ffp-contract=off -fopenmp; no fast-math: the arithmetic
+// Build: see oracle/Makefile (g++ -O3 -ffp-contract=off -fopenmp; no fast-math: the arithmetic
 // contract below forbids FMA contraction and reassociation).
 //
 // Conventions: matrices are 3x3 in Julia column-major order, m[r + 3*c] = M[r+1, c+1]; ROWS of
