@@ -139,6 +139,47 @@ NL_API int nl_lazy_lj_energy(const nl_params* params, const void* X_sorted, int6
                       const void* cell_offsets, double eps, double sigma, double* energy_out, void* ws,
                       size_t ws_bytes, void* stream);
 
+/* ---- The callers either side of the hot path: device-side PairList accessors, the IsolatedCell
+ * bounding box of the AtomsBase adapter, and the displacement check of a skin (Verlet) list. ------------------- */
+
+/* _getR for a range of pairs without scalar indexing (src/cell_list.jl:525-531 as looped by neigss!, :583-592):
+ *   R_out[p - p_lo] = (X[j[p]] - X[i[p]]) + cell' * S[p]   for p in [p_lo, p_hi)   (0-based, half-open)
+ * X is the caller's ORIGINAL-order position array (PairList.X), N atoms; i, j, S are the PairList arrays.
+ * Same expression and association as the fill pass, so R is bit-identical to nl_fill_pairs' R_out.  Passing NEW
+ * positions refreshes R for an unchanged pair topology (skin list).                                            */
+NL_API int nl_pairs_R(const nl_params* params, const void* X, int64_t N, const void* i, const void* j, const void* S,
+                      int64_t p_lo, int64_t p_hi, void* R_out, void* stream);
+
+/* maxneigs(nlist) (src/cell_list.jl:513) as a device reduction: *max_out (DEVICE int64) = max_n first[n+1]-first[n].
+ * N == 0 is NL_ERR_BAD_ARG (the reference's maximum over an empty collection throws).                          */
+NL_API int nl_max_neighbours(const nl_params* params, const void* first, int64_t N, int64_t* max_out, void* stream);
+
+/* Neighbourhoods of a SET of atoms at once (the sites() loop, src/iterators.jl:27-40, over neigss!,
+ * src/cell_list.jl:583-592) as fixed-width padded blocks:
+ *   rows   in   n_sel TI            atoms (1-based)
+ *   n_out  out  n_sel TI            nneigs(nlist, rows[s]) (src/cell_list.jl:523) -- the FULL count even if > width
+ *   j_out  out  n_sel x width TI    neighbours, 0 in the padding
+ *   S_out  out  n_sel x width x 3 TI   (may be NULL)
+ *   R_out  out  n_sel x width x 3 T    (may be NULL) computed like nl_pairs_R                                */
+NL_API int nl_rows_padded(const nl_params* params, const void* X, int64_t N, const void* first, const void* j,
+                          const void* S, const void* rows, int64_t n_sel, int32_t width, void* n_out, void* j_out,
+                          void* S_out, void* R_out, void* stream);
+
+/* Scratch for the two reductions below (256-byte aligned device memory). */
+#define NL_REDUCE_WS_BYTES 32768
+
+/* Bounding box of the positions: minmax_out (DEVICE, 6 T) = (min x, min y, min z, max x, max y, max z).  The
+ * IsolatedCell branch of _get_cell_matrix (ext/NeighbourListsAtomsBaseExt.jl:17-31) builds its cell as
+ * diag(max - min + 1) from these.  N >= 1.                                                                     */
+NL_API int nl_bounding_box(int32_t float_type, const void* X, int64_t N, void* minmax_out, void* ws, size_t ws_bytes,
+                           void* stream);
+
+/* d2_out (DEVICE, 1 T) = max_n |X[n] - X_ref[n]|^2, evaluated in T as (dx dx + dy dy) + dz dz.  A list built with
+ * cutoff + skin stays complete for `cutoff` while sqrt(d2) < skin / 2 (absent in the reference, which rebuilds on
+ * every call, src/cell_list.jl:906-916).                                                                       */
+NL_API int nl_max_displacement2(int32_t float_type, const void* X, const void* X_ref, int64_t N, void* d2_out, void* ws,
+                                size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

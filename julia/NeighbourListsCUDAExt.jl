@@ -102,4 +102,63 @@ function lj_energy(clist::SortedCellList{T,TI,<:CuVector}, eps, sigma) where {T,
     return e
 end
 
+# ---- PairList accessors without scalar indexing (src/cell_list.jl:513-606, src/iterators.jl) ------------------
+const DevPairList{T,TI} = PairList{T,TI,<:CuVector}
+
+# nl_params of a PairList: only the element types and the cell are read by the accessor kernels
+_params(nl::PairList{T,TI}) where {T,TI} =
+    NlParams(_ftag(T), _itag(TI), Tuple(Float64.(nl.C)), Tuple(Float64.(inv(nl.C))), Float64(nl.cutoff),
+             (Int32(1), Int32(1), Int32(1)), (Int32(1), Int32(1), Int32(1)), (0x00, 0x00, 0x00), ntuple(_ -> 0x00, 5))
+
+"R for the pairs lo:hi (1-based, inclusive) -- the _getR loop of neigss!, on the device; X defaults to nl.X"
+function pairs_R(nl::DevPairList{T,TI}, lo::Integer = 1, hi::Integer = length(nl.i); X = nl.X) where {T,TI}
+    R = CuVector{SVec{T}}(undef, hi - lo + 1)
+    _check(ccall((:nl_pairs_R, libnlcuda), Cint,
+                 (Ref{NlParams}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, Int64, CuPtr{Cvoid}, Ptr{Cvoid}),
+                 _params(nl), X, length(X), nl.i, nl.j, nl.S, lo - 1, hi, R, _stream()))
+    return R
+end
+
+function NeighbourLists.neigss(nl::DevPairList, i0::Integer)
+    n1, n2 = CUDA.@allowscalar(nl.first[i0]), CUDA.@allowscalar(nl.first[i0+1]) - 1
+    return (@view nl.j[n1:n2]), pairs_R(nl, n1, n2), (@view nl.S[n1:n2])
+end
+
+function NeighbourLists.maxneigs(nl::DevPairList)
+    out = CUDA.zeros(Int64, 1)
+    _check(ccall((:nl_max_neighbours, libnlcuda), Cint, (Ref{NlParams}, CuPtr{Cvoid}, Int64, CuPtr{Int64}, Ptr{Cvoid}),
+                 _params(nl), nl.first, length(nl.first) - 1, out, _stream()))
+    return Array(out)[1]
+end
+
+"neighbourhoods of the atoms `rows` as padded blocks: (n, j, R, S) with j :: width x n_sel etc."
+function sites_padded(nl::DevPairList{T,TI}, rows::CuVector{TI}, width::Integer = maxneigs(nl)) where {T,TI}
+    ns = length(rows)
+    n = CuVector{TI}(undef, ns); j = CuMatrix{TI}(undef, width, ns)
+    S = CuMatrix{SVec{TI}}(undef, width, ns); R = CuMatrix{SVec{T}}(undef, width, ns)
+    _check(ccall((:nl_rows_padded, libnlcuda), Cint,
+                 (Ref{NlParams}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, Int32,
+                  CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{Cvoid}),
+                 _params(nl), nl.X, length(nl.X), nl.first, nl.j, nl.S, rows, ns, width, n, j, S, R, _stream()))
+    return n, j, R, S
+end
+
+# ---- AtomsBase extension with device positions: the IsolatedCell bounding box (ext/NeighbourListsAtomsBaseExt.jl:17-31)
+function bounding_cell(X::CuVector{SVec{T}}) where {T}
+    mm = CuVector{T}(undef, 6); ws = CUDA.zeros(UInt8, 32768)
+    _check(ccall((:nl_bounding_box, libnlcuda), Cint, (Int32, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                 _ftag(T), X, length(X), mm, ws, length(ws), _stream()))
+    m = Array(mm)
+    return SMat{T}(m[4] - m[1] + 1, 0, 0, 0, m[5] - m[2] + 1, 0, 0, 0, m[6] - m[3] + 1)
+end
+
+# ---- skin list: max squared displacement since the list was built
+function max_displacement2(X::CuVector{SVec{T}}, Xref::CuVector{SVec{T}}) where {T}
+    d2 = CuVector{T}(undef, 1); ws = CUDA.zeros(UInt8, 32768)
+    _check(ccall((:nl_max_displacement2, libnlcuda), Cint,
+                 (Int32, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                 _ftag(T), X, Xref, length(X), d2, ws, length(ws), _stream()))
+    return Array(d2)[1]
+end
+
 end # module

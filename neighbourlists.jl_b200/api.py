@@ -98,6 +98,7 @@ class PairList:
     S: torch.Tensor       # (P,3) TI
     first: torch.Tensor   # (N+1,) TI, 1-based
     R: Optional[torch.Tensor] = None
+    params: object = field(repr=False, default=None)  # host-side extra: nl_params of the list (types, cell)
 
     def cpu(self):
         """Device -> host copies of every array (numpy), for inspection and tests."""
@@ -115,8 +116,12 @@ def _pairs_workspace(clist: SortedCellList) -> torch.Tensor:
     return clist._ws
 
 
-def build_cell_list(X, cutoff, cell, pbc, *, int_type=np.int32, device=None) -> SortedCellList:
-    """build_cell_list(X, cutoff, cell, pbc; int_type) -> SortedCellList  (src/cell_list.jl:632-679)."""
+def build_cell_list(X, cutoff, cell=None, pbc=None, *, int_type=np.int32, device=None) -> SortedCellList:
+    """build_cell_list(X, cutoff, cell, pbc; int_type) -> SortedCellList  (src/cell_list.jl:632-679);
+    build_cell_list(system, cutoff) for AtomsBase-style systems (atoms.py)."""
+    if cell is None and pbc is None and hasattr(X, "positions"):
+        from . import atoms
+        return atoms.build_cell_list(X, cutoff, int_type=int_type, device=device)
     Xd = _as_device_positions(X, device)
     it = _int_dtype(int_type)
     fdt = np.dtype(_T2N[Xd.dtype])
@@ -195,7 +200,7 @@ def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers:
         if timers is not None:
             ev[3].record()
             timers.setdefault("events", []).append(ev)
-    return PairList(X=clist.X_orig, C=clist.cell, cutoff=clist.cutoff, i=i, j=j, S=S, first=first, R=R)
+    return PairList(X=clist.X_orig, C=clist.cell, cutoff=clist.cutoff, i=i, j=j, S=S, first=first, R=R, params=clist.params)
 
 
 def cell_ids(X, cutoff, cell, pbc, *, int_type=np.int32, device=None) -> torch.Tensor:
@@ -211,8 +216,12 @@ def cell_ids(X, cutoff, cell, pbc, *, int_type=np.int32, device=None) -> torch.T
     return out
 
 
-def neighbour_list(X, cutoff, cell, pbc, *, lazy: bool = False, int_type=np.int32, with_R: bool = False, device=None):
-    """neighbour_list(X, cutoff, cell, pbc; lazy, int_type)  (src/cell_list.jl:897-916)."""
+def neighbour_list(X, cutoff, cell=None, pbc=None, *, lazy: bool = False, int_type=np.int32, with_R: bool = False, device=None):
+    """neighbour_list(X, cutoff, cell, pbc; lazy, int_type)  (src/cell_list.jl:897-916);
+    neighbour_list(system, cutoff; lazy, int_type) for AtomsBase-style systems (atoms.py)."""
+    if cell is None and pbc is None and hasattr(X, "positions"):
+        from . import atoms
+        return atoms.neighbour_list(X, cutoff, lazy=lazy, int_type=int_type, with_R=with_R, device=device)
     clist = build_cell_list(X, cutoff, cell, pbc, int_type=int_type, device=device)
     if lazy:
         return clist
@@ -240,24 +249,52 @@ def nneigs(nlist: PairList, i0: int) -> int:
 
 
 def maxneigs(nlist: PairList) -> int:
-    if nsites(nlist) == 0:
+    """maxneigs(nlist) (src/cell_list.jl:513) as one device reduction (nl_max_neighbours)."""
+    N = nsites(nlist)
+    if N == 0:
         raise ValueError("maxneigs of an empty list")  # reference: maximum over an empty collection throws
-    return int((nlist.first[1:] - nlist.first[:-1]).max().item())
+    dev = nlist.first.device
+    with torch.cuda.device(dev):
+        out = torch.empty(1, dtype=torch.int64, device=dev)
+        _lib.check(_lib.lib().nl_max_neighbours(_list_params(nlist), _ptr(nlist.first), N, _ptr(out), _stream(dev)))
+    return int(out.item())
 
 
 max_neighbours = maxneigs
 max_neigs = maxneigs
 
 
+def _list_params(nlist: PairList):
+    """nl_params of a PairList (built by materialize_pairlist; rebuilt from C/cutoff for hand-made lists)."""
+    if nlist.params is None:
+        fdt = np.dtype(_T2N[nlist.X.dtype])
+        geo = geometry(nlist.C, nlist.cutoff, (False, False, False), fdt)
+        nlist.params = _lib.make_params(geo, fdt, _T2N[nlist.first.dtype])
+    return nlist.params
+
+
+def pairs_R(nlist: PairList, lo: int = 0, hi: Optional[int] = None, X: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """R[n] = (X[j] - X[i]) + C' * S[n] for the pairs [lo, hi) (0-based) with the reference's association
+    (_getR, src/cell_list.jl:525-531), in one kernel (nl_pairs_R) instead of scalar indexing.  `X` overrides
+    the stored positions (same atoms, moved: the skin-list refresh)."""
+    P = npairs(nlist)
+    hi = P if hi is None else hi
+    if not 0 <= lo <= hi <= P:
+        raise IndexError("pair range out of bounds")
+    Xp = nlist.X if X is None else X
+    if Xp.dtype != nlist.X.dtype or Xp.shape != nlist.X.shape or Xp.device != nlist.X.device:
+        raise ValueError("X must match the list's positions in dtype, shape and device")
+    Xp = Xp.contiguous()
+    dev = Xp.device
+    with torch.cuda.device(dev):
+        R = torch.empty((hi - lo, 3), dtype=Xp.dtype, device=dev)
+        _lib.check(_lib.lib().nl_pairs_R(_list_params(nlist), _ptr(Xp), Xp.shape[0], _ptr(nlist.i), _ptr(nlist.j), _ptr(nlist.S),
+                                         lo, hi, _ptr(R), _stream(dev)))
+    return R
+
+
 def _getR(nlist: PairList, lo: int, hi: int) -> torch.Tensor:
-    """R[n] = (X[j] - X[i]) + C' * S[n] with the reference's association (src/cell_list.jl:525-531)."""
-    j = nlist.j[lo:hi].long() - 1
-    i = nlist.i[lo:hi].long() - 1
-    d = nlist.X[j] - nlist.X[i]
-    S = nlist.S[lo:hi].to(nlist.X.dtype)
-    Cm = torch.as_tensor(nlist.C, dtype=nlist.X.dtype, device=nlist.X.device)
-    cs = torch.stack([(Cm[0, k] * S[:, 0] + Cm[1, k] * S[:, 1]) + Cm[2, k] * S[:, 2] for k in range(3)], dim=1)
-    return d + cs
+    return pairs_R(nlist, lo, hi)
 
 
 def neigss(nlist: PairList, i0: int):
@@ -265,6 +302,64 @@ def neigss(nlist: PairList, i0: int):
     f = nlist.first[i0 - 1:i0 + 1].tolist()
     lo, hi = int(f[0]) - 1, int(f[1]) - 1
     return nlist.j[lo:hi], _getR(nlist, lo, hi), nlist.S[lo:hi]
+
+
+def sites_padded(nlist: PairList, rows=None, width: Optional[int] = None, with_R: bool = True, with_S: bool = True):
+    """Neighbourhoods of many atoms at once: the sites() loop of src/iterators.jl:27-40 over neigss!
+    (src/cell_list.jl:583-592) as fixed-width device blocks (nl_rows_padded).
+
+    rows: 1-based atom indices (default: all atoms); width: block width (default: maxneigs of the list).
+    Returns (n, j, R, S): n[s] = nneigs(rows[s]); j (n_sel, width) with 0 padding; R (n_sel, width, 3) or None;
+    S (n_sel, width, 3) or None.  Rows longer than `width` are truncated (n still holds the full count)."""
+    N = nsites(nlist)
+    dev = nlist.first.device
+    it = nlist.first.dtype
+    if rows is None:
+        rows_t = torch.arange(1, N + 1, dtype=it, device=dev)
+    else:
+        rows_t = torch.as_tensor(rows, device=dev).to(it).contiguous().reshape(-1)
+        if rows_t.numel() and (int(rows_t.min()) < 1 or int(rows_t.max()) > N):
+            raise IndexError("atom index out of range")  # BoundsError in the reference
+    n_sel = int(rows_t.numel())
+    if width is None:
+        width = maxneigs(nlist) if N > 0 else 0
+    with torch.cuda.device(dev):
+        n_out = torch.empty(n_sel, dtype=it, device=dev)
+        j_out = torch.empty((n_sel, width), dtype=it, device=dev)
+        S_out = torch.empty((n_sel, width, 3), dtype=it, device=dev) if with_S else None
+        R_out = torch.empty((n_sel, width, 3), dtype=nlist.X.dtype, device=dev) if with_R else None
+        if n_sel > 0:
+            _lib.check(_lib.lib().nl_rows_padded(_list_params(nlist), _ptr(nlist.X), nlist.X.shape[0], _ptr(nlist.first), _ptr(nlist.j),
+                                                 _ptr(nlist.S), _ptr(rows_t), n_sel, width, _ptr(n_out), _ptr(j_out), _ptr(S_out),
+                                                 _ptr(R_out), _stream(dev)))
+    return n_out, j_out, R_out, S_out
+
+
+def pairs(nlist: PairList, chunk: int = 1 << 20):
+    """pairs(nlist) (src/iterators.jl:12-25): iterates (i, j, R) over all pairs; R comes from nl_pairs_R in
+    chunks, so the host loop never indexes device memory element by element."""
+    P = npairs(nlist)
+    for lo in range(0, P, chunk):
+        hi = min(P, lo + chunk)
+        ii, jj = nlist.i[lo:hi].tolist(), nlist.j[lo:hi].tolist()
+        RR = pairs_R(nlist, lo, hi).tolist()
+        for n in range(hi - lo):
+            yield ii[n], jj[n], RR[n]
+
+
+def sites(nlist: PairList, chunk: int = 1 << 14):
+    """sites(nlist) (src/iterators.jl:27-40): iterates (i, j, R) with j, R the neighbourhood of atom i, gathered
+    chunk rows at a time on the device (nl_rows_padded)."""
+    N = nsites(nlist)
+    if N == 0:
+        return
+    width = maxneigs(nlist)
+    for lo in range(0, N, chunk):
+        hi = min(N, lo + chunk)
+        n, j, R, _ = sites_padded(nlist, torch.arange(lo + 1, hi + 1, device=nlist.first.device), width, with_R=True, with_S=False)
+        n, j, R = n.tolist(), j.cpu().numpy(), R.cpu().numpy()
+        for s in range(hi - lo):
+            yield lo + s + 1, j[s, :n[s]], R[s, :n[s]]
 
 
 def neigs(nlist: PairList, i0: int):

@@ -2,6 +2,7 @@
 // Host-side stage orchestration only; kernels live in the .cuh files next to this one.
 #include "../../include/nlcuda.h"
 
+#include <algorithm>
 #include <cstdlib>
 
 #include "nl_build.cuh"
@@ -11,6 +12,7 @@
 #include "nl_tiled.cuh"
 #include "nl_mask.cuh"
 #include "nl_fillrows.cuh"
+#include "nl_access.cuh"
 
 namespace {
 
@@ -399,6 +401,48 @@ int lazy_lj_impl(const nl_params* p, const void* Xs, int64_t N, const void* perm
   return traverse<T, TI, MODE_LJ>(p, N, co, w, g, sk, false, st);
 }
 
+// ---------------------------------------------------------------- accessors / adapters (nl_access.cuh)
+template <class T, class TI>
+int pairs_R_impl(const nl_params* p, const void* X, const void* i, const void* j, const void* S, int64_t p_lo, int64_t p_hi, void* R,
+                 cudaStream_t st) {
+  const long long np = p_hi - p_lo;
+  if (np <= 0) return NL_OK;
+  Geo<T> g = make_geo<T>(p);
+  k_pairs_R<T, TI><<<(unsigned)((np + 255) / 256), 256, 0, st>>>((const T*)X, (const TI*)i, (const TI*)j, (const TI*)S, p_lo, np, g, (T*)R);
+  NL_LAUNCHED(1);
+  NL_LAUNCH_CHECK();
+  return NL_OK;
+}
+
+template <class T, class TI>
+int rows_padded_impl(const nl_params* p, const void* X, const void* first, const void* j, const void* S, const void* rows, int64_t n_sel,
+                     int32_t width, void* n_out, void* j_out, void* S_out, void* R_out, cudaStream_t st) {
+  Geo<T> g = make_geo<T>(p);
+  k_rows_padded<T, TI><<<(unsigned)((n_sel + 7) / 8), 256, 0, st>>>((const T*)X, (const TI*)first, (const TI*)j, (const TI*)S, (const TI*)rows,
+                                                                     n_sel, width, g, (TI*)n_out, (TI*)j_out, (TI*)S_out, (T*)R_out);
+  NL_LAUNCHED(1);
+  NL_LAUNCH_CHECK();
+  return NL_OK;
+}
+
+template <class T> int bbox_impl(const void* X, int64_t N, void* out, void* ws, cudaStream_t st) {
+  const int nb = (int)std::min<long long>(RED_BLOCKS, (N + 255) / 256);
+  k_bbox_partial<T><<<nb, 256, 0, st>>>((const T*)X, N, (T*)ws);
+  k_bbox_final<T><<<1, 256, 0, st>>>((const T*)ws, nb, (T*)out);
+  NL_LAUNCHED(2);
+  NL_LAUNCH_CHECK();
+  return NL_OK;
+}
+
+template <class T> int maxdisp_impl(const void* X, const void* Y, int64_t N, void* out, void* ws, cudaStream_t st) {
+  const int nb = (int)std::max<long long>(1, std::min<long long>(RED_BLOCKS, (N + 255) / 256));
+  k_maxdisp_partial<T><<<nb, 256, 0, st>>>((const T*)X, (const T*)Y, N, (T*)ws);
+  k_max_final<T><<<1, 256, 0, st>>>((const T*)ws, nb, (T*)out);
+  NL_LAUNCHED(2);
+  NL_LAUNCH_CHECK();
+  return NL_OK;
+}
+
 #define NL_DISPATCH(p, FN, ...)                                                              \
   ((p)->float_type == NL_F64                                                                 \
        ? ((p)->int_type == NL_I64 ? FN<double, int64_t>(__VA_ARGS__) : FN<double, int32_t>(__VA_ARGS__)) \
@@ -535,6 +579,59 @@ int nl_lazy_lj_energy(const nl_params* params, const void* X_sorted, int64_t N, 
   rc = check_ws(ws, ws_bytes, pair_ws(nullptr, params, N).total_bytes);
   if (rc) return rc;
   return NL_DISPATCH(params, lazy_lj_impl, params, X_sorted, N, perm, cell_offsets, eps, sigma, energy_out, ws, (cudaStream_t)stream);
+}
+
+int nl_pairs_R(const nl_params* params, const void* X, int64_t N, const void* i, const void* j, const void* S, int64_t p_lo, int64_t p_hi,
+               void* R_out, void* stream) {
+  int rc = check_params(params, N);
+  if (rc) return rc;
+  if (p_lo < 0 || p_hi < p_lo) return NL_ERR_BAD_ARG;
+  if (p_hi == p_lo) return NL_OK;
+  if (!X || !i || !j || !S || !R_out) return NL_ERR_BAD_ARG;
+  return NL_DISPATCH(params, pairs_R_impl, params, X, i, j, S, p_lo, p_hi, R_out, (cudaStream_t)stream);
+}
+
+int nl_max_neighbours(const nl_params* params, const void* first, int64_t N, int64_t* max_out, void* stream) {
+  int rc = check_params(params, N);
+  if (rc) return rc;
+  if (N == 0 || !first || !max_out) return NL_ERR_BAD_ARG;  // reference: maximum over an empty collection throws
+  cudaStream_t st = (cudaStream_t)stream;
+  NL_CUDA(cudaMemsetAsync(max_out, 0, sizeof(int64_t), st));
+  const unsigned nb = (unsigned)std::min<long long>(RED_BLOCKS, (N + 255) / 256);
+  if (params->int_type == NL_I64) k_max_neighbours<int64_t><<<nb, 256, 0, st>>>((const int64_t*)first, N, (unsigned long long*)max_out);
+  else k_max_neighbours<int32_t><<<nb, 256, 0, st>>>((const int32_t*)first, N, (unsigned long long*)max_out);
+  NL_LAUNCHED(1);
+  NL_LAUNCH_CHECK();
+  return NL_OK;
+}
+
+int nl_rows_padded(const nl_params* params, const void* X, int64_t N, const void* first, const void* j, const void* S, const void* rows,
+                   int64_t n_sel, int32_t width, void* n_out, void* j_out, void* S_out, void* R_out, void* stream) {
+  int rc = check_params(params, N);
+  if (rc) return rc;
+  if (n_sel < 0 || width < 0) return NL_ERR_BAD_ARG;
+  if (n_sel == 0) return NL_OK;
+  if (!X || !first || !rows || !n_out || (width > 0 && (!j || !S || !j_out))) return NL_ERR_BAD_ARG;
+  return NL_DISPATCH(params, rows_padded_impl, params, X, first, j, S, rows, n_sel, width, n_out, j_out, S_out, R_out, (cudaStream_t)stream);
+}
+
+int nl_bounding_box(int32_t float_type, const void* X, int64_t N, void* minmax_out, void* ws, size_t ws_bytes, void* stream) {
+  if (float_type != NL_F32 && float_type != NL_F64) return NL_ERR_BAD_ARG;
+  if (N < 1 || !X || !minmax_out) return NL_ERR_BAD_ARG;  // reference: maximum over an empty collection throws
+  int rc = check_ws(ws, ws_bytes, NL_REDUCE_WS_BYTES);
+  if (rc) return rc;
+  return float_type == NL_F64 ? bbox_impl<double>(X, N, minmax_out, ws, (cudaStream_t)stream)
+                              : bbox_impl<float>(X, N, minmax_out, ws, (cudaStream_t)stream);
+}
+
+int nl_max_displacement2(int32_t float_type, const void* X, const void* X_ref, int64_t N, void* d2_out, void* ws, size_t ws_bytes,
+                         void* stream) {
+  if (float_type != NL_F32 && float_type != NL_F64) return NL_ERR_BAD_ARG;
+  if (N < 0 || !d2_out || (N > 0 && (!X || !X_ref))) return NL_ERR_BAD_ARG;
+  int rc = check_ws(ws, ws_bytes, NL_REDUCE_WS_BYTES);
+  if (rc) return rc;
+  return float_type == NL_F64 ? maxdisp_impl<double>(X, X_ref, N, d2_out, ws, (cudaStream_t)stream)
+                              : maxdisp_impl<float>(X, X_ref, N, d2_out, ws, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -180,3 +180,61 @@ def canonical(i, j, S, R=None):
     if R is not None:
         out.append(np.asarray(R).reshape(-1, 3)[order])
     return tuple(out)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# numpy restatements of the reference's accessors / adapter pieces.  numpy evaluates every
+# elementwise operation separately in the array dtype, i.e. unfused and in the written association.
+
+def pairs_R(X, i, j, S, cell, dtype=np.float64):
+    """_getR for all pairs: R = (X[j] - X[i]) + C' * S (/root/reference/src/cell_list.jl:525-531)."""
+    T = np.dtype(dtype).type
+    X = np.asarray(X, dtype=T)
+    C_ = np.asarray(cell, dtype=T)
+    i0, j0 = np.asarray(i, dtype=np.int64) - 1, np.asarray(j, dtype=np.int64) - 1
+    Sf = np.asarray(S).astype(T)
+    d = X[j0] - X[i0]
+    cs = np.stack([(C_[0, k] * Sf[:, 0] + C_[1, k] * Sf[:, 1]) + C_[2, k] * Sf[:, 2] for k in range(3)], axis=1)
+    return (d + cs).astype(T)
+
+
+def maxneigs(first):
+    """maximum(nneigs(nlist, n) for n = 1:nsites) (/root/reference/src/cell_list.jl:513,523)."""
+    f = np.asarray(first, dtype=np.int64)
+    if f.shape[0] < 2:
+        raise ValueError("maximum over an empty collection")
+    return int((f[1:] - f[:-1]).max())
+
+
+def rows_padded(X, first, j, S, cell, rows, width, dtype=np.float64):
+    """neigss(nlist, i) (/root/reference/src/cell_list.jl:583-597) for every i in rows, padded to `width`."""
+    T = np.dtype(dtype).type
+    f = np.asarray(first, dtype=np.int64)
+    rows = np.asarray(rows, dtype=np.int64)
+    n = np.zeros(len(rows), dtype=np.int64)
+    jo = np.zeros((len(rows), width), dtype=np.asarray(j).dtype)
+    So = np.zeros((len(rows), width, 3), dtype=np.asarray(S).dtype)
+    Ro = np.zeros((len(rows), width, 3), dtype=T)
+    for s, r in enumerate(rows):
+        lo, hi = f[r - 1] - 1, f[r] - 1
+        n[s] = hi - lo
+        m = min(hi - lo, width)
+        jo[s, :m] = j[lo:lo + m]
+        So[s, :m] = S[lo:lo + m]
+        Ro[s, :m] = pairs_R(X, np.full(m, r), j[lo:lo + m], S[lo:lo + m], cell, dtype)
+    return n, jo, So, Ro
+
+
+def bounding_cell(X, dtype=np.float64):
+    """IsolatedCell branch of _get_cell_matrix (/root/reference/ext/NeighbourListsAtomsBaseExt.jl:17-31):
+    diag(max - min + 1) per axis, in the positions' element type."""
+    T = np.dtype(dtype).type
+    X = np.asarray(X, dtype=T)
+    return np.diag((X.max(axis=0) - X.min(axis=0)) + T(1)).astype(T)
+
+
+def max_displacement2(X, X_ref, dtype=np.float64):
+    T = np.dtype(dtype).type
+    d = np.asarray(X, dtype=T) - np.asarray(X_ref, dtype=T)
+    d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
+    return T(d2.max()) if d2.size else T(0)

@@ -1,0 +1,177 @@
+"""SURVEY 8f rows on the GPU: device-side PairList accessors (f2), the AtomsBase-style adapter with the device
+bounding box (f1) and the skin list (f3), each against the numpy restatement of the reference (oracle/nl_oracle.py).
+Integer outputs and R must be BIT-exact: the kernels evaluate the same expression in the same association."""
+import numpy as np
+import pytest
+
+from oracle import nl_oracle as O
+from tests import util as U
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nl():
+    import torch
+    assert torch.cuda.is_available()
+    import neighbourlists_jl_b200 as nl
+    nl._lib.lib()
+    return nl
+
+
+@pytest.mark.parametrize("dtype,int_type", [(np.float64, np.int32), (np.float32, np.int32), (np.float64, np.int64), (np.float32, np.int64)])
+def test_pairs_R_bit_exact(nl, dtype, int_type):
+    # _getR (src/cell_list.jl:525-531) for every pair, triclinic cell, atoms displaced by lattice vectors
+    import torch
+    pbc = (True, True, False)
+    C = (U.TRICLINIC * 2.0).astype(dtype)
+    X = U.displace_by_lattice(U.rand_in_cell(3000, C, seed=71, dtype=dtype), C, pbc)
+    Xd = torch.from_numpy(X).cuda()
+    pl = nl.neighbour_list(Xd, 3.0, C, pbc, int_type=int_type, with_R=True)
+    h = pl.cpu()
+    want = O.pairs_R(X, h["i"], h["j"], h["S"], C, dtype)
+    got = nl.pairs_R(pl).cpu().numpy()
+    assert got.dtype == np.dtype(dtype) and np.array_equal(got, want)
+    assert np.array_equal(got, h["R"]), "accessor R == fill-pass R (same expression, SURVEY 8a13)"
+    lo, hi = 1234, 1234 + 777
+    assert np.array_equal(nl.pairs_R(pl, lo, hi).cpu().numpy(), want[lo:hi])
+    assert nl.pairs_R(pl, 5, 5).shape == (0, 3)
+    with pytest.raises(IndexError):
+        nl.pairs_R(pl, 0, nl.npairs(pl) + 1)
+
+
+def test_maxneigs_and_rows_padded(nl):
+    import torch
+    X, C, L = U.rand_config(5000, seed=72)
+    rng = np.random.default_rng(5)
+    X[:40] = X[0] + rng.normal(scale=0.7, size=(40, 3))  # a cluster: one long row
+    Xd = torch.from_numpy(X).cuda()
+    pl = nl.neighbour_list(Xd, 5.0, C, (True, True, True))
+    h = pl.cpu()
+    assert nl.maxneigs(pl) == O.maxneigs(h["first"]) >= 39
+    rows = np.array([1, 2, 40, 41, 5000, 7, 7, 2500], dtype=np.int64)
+    for width in (O.maxneigs(h["first"]), 16, 0):
+        n, j, R, S = nl.sites_padded(pl, rows, width)
+        wn, wj, wS, wR = O.rows_padded(X, h["first"], h["j"], h["S"], C, rows, width)
+        assert np.array_equal(n.cpu().numpy(), wn)
+        assert np.array_equal(j.cpu().numpy(), wj) and np.array_equal(S.cpu().numpy(), wS) and np.array_equal(R.cpu().numpy(), wR)
+    # all atoms, default width; without R / S
+    n, j, R, S = nl.sites_padded(pl, with_R=False, with_S=False)
+    assert R is None and S is None and j.shape == (5000, nl.maxneigs(pl))
+    assert np.array_equal(n.cpu().numpy(), np.diff(h["first"]))
+    assert int((j != 0).sum().item()) == nl.npairs(pl)
+    with pytest.raises(IndexError):
+        nl.sites_padded(pl, [0])
+    with pytest.raises(IndexError):
+        nl.sites_padded(pl, [5001])
+
+
+def test_iterators(nl):
+    # src/iterators.jl: pairs -> (i, j, R) over all pairs; sites -> (i, j, R) per atom
+    import torch
+    X, C, L = U.rand_config(120, seed=73)
+    pl = nl.neighbour_list(torch.from_numpy(X).cuda(), 4.5, C, (True, True, False))
+    h = pl.cpu()
+    wantR = O.pairs_R(X, h["i"], h["j"], h["S"], C)
+    got = list(nl.pairs(pl, chunk=1000))
+    assert len(got) == nl.npairs(pl)
+    assert [g[0] for g in got] == h["i"].tolist() and [g[1] for g in got] == h["j"].tolist()
+    assert np.array_equal(np.array([g[2] for g in got]), wantR)
+    seen = 0
+    for i, j, R in nl.sites(pl, chunk=50):
+        seen += 1
+        lo, hi = h["first"][i - 1] - 1, h["first"][i] - 1
+        assert i == seen and np.array_equal(j, h["j"][lo:hi]) and np.array_equal(R, wantR[lo:hi])
+    assert seen == 120
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_bounding_box_and_isolated_system(nl, dtype):
+    import torch
+    rng = np.random.default_rng(9)
+    X = (rng.normal(size=(100_003, 3)) * np.array([30.0, 2.0, 11.0]) + np.array([5.0, -40.0, 0.25])).astype(dtype)
+    Xd = torch.from_numpy(X).cuda()
+    mm = nl.bounding_box(Xd).cpu().numpy()
+    assert mm.dtype == np.dtype(dtype)
+    assert np.array_equal(mm[:3], X.min(axis=0)) and np.array_equal(mm[3:], X.max(axis=0))
+    assert np.array_equal(nl.bounding_cell(Xd), O.bounding_cell(X, dtype))
+    one = torch.tensor([[1.5, -2.0, 3.0]], dtype=Xd.dtype).cuda()
+    assert np.array_equal(nl.bounding_cell(one), np.eye(3, dtype=dtype))
+    with pytest.raises(ValueError):
+        nl.bounding_box(Xd[:0])
+    # an isolated system end to end == the explicit call with the bounding cell and open boundaries
+    Xs = X[:4000] * np.asarray(0.2, dtype=dtype)
+    sysm = nl.isolated_system(torch.from_numpy(Xs).cuda())
+    pl = nl.neighbour_list(sysm, 1.5)
+    orc = O.sortbased(Xs, 1.5, O.bounding_cell(Xs, dtype), (False, False, False), dtype=dtype)
+    U.assert_engine_matches_oracle(pl.cpu(), orc, rtol=0, check_R=False, msg="isolated system")
+
+
+def test_atoms_adapter_known_answers(nl):
+    # test/test_atoms_base.jl:13-69 (fcc Cu: 12 neighbours), :71-104 (H3), :106-120 (cutoffs), :122-133 (units), :135-144 (2-D)
+    import torch
+    for reps in ((4, 2, 3), (3, 3, 3), (2, 2, 2)):
+        X, C = U.fcc(3.61, reps)
+        cu = nl.periodic_system(X, C)  # host positions are uploaded
+        pl = nl.neighbour_list(cu, 3.5)
+        assert isinstance(pl, nl.PairList) and nl.nsites(pl) == len(cu) == X.shape[0] and nl.npairs(pl) == 12 * X.shape[0]
+        assert all(nl.num_neighbours(pl, i) == 12 for i in range(1, X.shape[0] + 1))
+        cl = nl.neighbour_list(cu, 3.5, lazy=True)
+        assert isinstance(cl, nl.SortedCellList) and nl.count_neighbours(cl, 1) == 12
+        assert int(nl.count_neighbours(cl).sum().item()) == nl.npairs(pl)
+        assert len(nl.neighbours(nl.build_cell_list(cu, 3.5), 1)[0]) == 12
+    X, C = U.fcc(3.61, (3, 3, 3))
+    cu = nl.periodic_system(X, C)
+    assert nl.num_neighbours(nl.neighbour_list(cu, 2.6), 1) == 12
+    assert nl.num_neighbours(nl.neighbour_list(cu, 3.7), 1) > 12
+    assert nl.npairs(nl.neighbour_list(cu, 1.0)) == 0
+    nA, nnm, npm = (nl.npairs(nl.neighbour_list(cu, c)) for c in (3.5, (0.35, "nm"), (350.0, "pm")))
+    assert nA == nnm == npm == 12 * X.shape[0]
+    # isolated H3
+    h3 = nl.isolated_system(np.array([[0., 0., 0.], [0., 0., 2.], [0., 10., 0.]]))
+    pl = nl.neighbour_list(h3, 5.0)
+    assert np.array_equal(pl.C, np.diag([1.0, 11.0, 3.0]))
+    j, R, S = nl.neighbours(pl, 1)
+    assert j.tolist() == [2] and R.tolist() == [[0.0, 0.0, 2.0]]
+    j, R, S = nl.neighbours(pl, 2)
+    assert j.tolist() == [1] and R.tolist() == [[0.0, 0.0, -2.0]]
+    assert [nl.num_neighbours(pl, i) for i in (1, 2, 3)] == [1, 1, 0]
+    assert len(nl.neighbours(nl.neighbour_list(h3, 5.0, lazy=True), 1)[0]) == 1
+    # 2-D systems are an error in both entry points
+    h2d = nl.isolated_system(np.array([[0., 0.], [0., 2.], [10., 0.]]))
+    with pytest.raises(nl.NlError):
+        nl.neighbour_list(h2d, 5.0)
+    with pytest.raises(nl.NlError):
+        nl.build_cell_list(h2d, 5.0)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_skin_list(nl, dtype):
+    import torch
+    rc, skin = 4.0, 1.0
+    X, C, L = U.rand_config(4000, seed=74, dtype=dtype)
+    pbc = (True, True, False)
+    Xd = torch.from_numpy(X).cuda()
+    sl = nl.SkinList(Xd, rc, skin, C, pbc)
+    assert sl.builds == 1
+    rng = np.random.default_rng(3)
+    X1 = (X + rng.uniform(-0.28, 0.28, size=X.shape)).astype(dtype)  # |d| <= 0.485 < skin / 2
+    d2 = nl.max_displacement2(torch.from_numpy(X1).cuda(), Xd).cpu().numpy()[0]
+    assert d2 == O.max_displacement2(X1, X, dtype)
+    assert sl.update(torch.from_numpy(X1).cuda()) is False and sl.builds == 1
+    h = sl.nlist.cpu()
+    assert np.array_equal(h["R"], O.pairs_R(X1, h["i"], h["j"], h["S"], C, dtype)), "R refreshed for the moved atoms"
+    # completeness: the pairs within rc at the NEW positions are exactly the list's pairs with r^2 < rc^2 (contract arithmetic)
+    T = np.dtype(dtype).type
+    R = h["R"]
+    r2 = (R[:, 0] * R[:, 0] + R[:, 1] * R[:, 1]) + R[:, 2] * R[:, 2]
+    keep = r2 < T(rc) * T(rc)
+    orc = O.sortbased(X1, rc, C, pbc, dtype=dtype)
+    sub = dict(i=h["i"][keep], j=h["j"][keep], S=h["S"][keep])
+    U.assert_same_pairs(sub, orc, "skin list filtered to rc at the new positions")
+    # a large move forces a rebuild, after which the list equals a fresh one
+    X2 = X1.copy()
+    X2[17] += np.asarray([0.9, 0.0, 0.0], dtype=dtype)
+    assert sl.update(torch.from_numpy(X2).cuda()) is True and sl.builds == 2
+    fresh = O.sortbased(X2, rc + skin, C, pbc, dtype=dtype)
+    U.assert_engine_matches_oracle(sl.nlist.cpu(), fresh, rtol=1e-12 if dtype == np.float64 else 1e-5, msg="rebuilt skin list")

@@ -16,7 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def declared_symbols():
     src = open(os.path.join(ROOT, "include", "nlcuda.h")).read()
-    return sorted(set(re.findall(r"NL_API[^;(]*?\b(nl_[a-z_0-9]+)\s*\(", src)))
+    return sorted(set(re.findall(r"NL_API[^;(]*?\b(nl_[A-Za-z_0-9]+)\s*\(", src)))
 
 
 def test_library_exports_every_declared_symbol():
@@ -118,3 +118,64 @@ def test_shard_plan_matches_host_logic():
         ref = sh.plan_slabs(hist, world, halo, True, 0).bounds
         assert np.array_equal(out, ref), (hist, world, halo, out, ref)
         assert out[0] == 0 and out[-1] == nplanes and np.all(np.diff(out) >= minw)
+
+
+def test_accessor_entry_points_validate_arguments():
+    # SURVEY 8f entry points: argument errors come back before any CUDA call
+    geo = nl.cellmath.geometry(np.eye(3) * 20.0, 5.0, (True, True, False), np.float64)
+    p = nl._lib.make_params(geo, np.float64, np.int32)
+    L = nl._lib.lib()
+    E = nl._lib
+    dummy = (C.c_char * 64)()
+    ptr = C.cast(dummy, C.c_void_p)
+    assert L.nl_pairs_R(None, ptr, 1, ptr, ptr, ptr, 0, 1, ptr, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_pairs_R(p, ptr, 1, ptr, ptr, ptr, 3, 2, ptr, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_pairs_R(p, None, 1, ptr, ptr, ptr, 0, 1, ptr, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_pairs_R(p, None, 1, None, None, None, 4, 4, None, None) == E.NL_OK  # empty range: nothing to do
+    assert L.nl_max_neighbours(p, ptr, 0, ptr, None) == E.NL_ERR_BAD_ARG  # maximum over an empty collection throws
+    assert L.nl_max_neighbours(p, None, 5, ptr, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_rows_padded(p, ptr, 5, ptr, ptr, ptr, ptr, -1, 4, ptr, ptr, ptr, ptr, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_rows_padded(p, ptr, 5, ptr, ptr, ptr, None, 2, 4, ptr, ptr, ptr, ptr, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_rows_padded(p, ptr, 5, ptr, ptr, ptr, ptr, 0, 4, ptr, ptr, ptr, ptr, None) == E.NL_OK
+    assert L.nl_bounding_box(7, ptr, 5, ptr, ptr, 1 << 20, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_bounding_box(E.NL_F64, ptr, 0, ptr, ptr, 1 << 20, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_bounding_box(E.NL_F64, ptr, 5, ptr, None, 0, None) == E.NL_ERR_WORKSPACE
+    assert L.nl_max_displacement2(E.NL_F32, None, ptr, 5, ptr, ptr, 1 << 20, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_max_displacement2(E.NL_F32, ptr, ptr, 5, ptr, ptr, 16, None) == E.NL_ERR_WORKSPACE
+    assert E.NL_REDUCE_WS_BYTES == int(re.search(r"#define NL_REDUCE_WS_BYTES (\d+)", open(os.path.join(ROOT, "include", "nlcuda.h")).read()).group(1))
+
+
+def test_accessor_restatements_known_answers():
+    # the numpy restatements used as the checker for the 8f rows, pinned on the reference's own known answers
+    h3 = np.array([[0., 0., 0.], [0., 0., 2.], [0., 10., 0.]])
+    Cb = O.bounding_cell(h3)
+    assert np.array_equal(Cb, np.diag([1.0, 11.0, 3.0]))  # ext/NeighbourListsAtomsBaseExt.jl:27-31 (bbox + 1)
+    d = O.sortbased(h3, 5.0, Cb, (False, False, False))
+    assert d["i"].tolist() == [1, 2] and d["j"].tolist() == [2, 1]  # test_atoms_base.jl:71-104
+    R = O.pairs_R(h3, d["i"], d["j"], d["S"], Cb)
+    assert R.tolist() == [[0.0, 0.0, 2.0], [0.0, 0.0, -2.0]] and np.array_equal(R, d["R"])
+    assert O.maxneigs(d["first"]) == 1
+    with pytest.raises(ValueError):
+        O.maxneigs(np.array([1]))
+    # _getR == the traversal's R for a periodic triclinic case with shifts (same expression)
+    from tests import util as U
+    Ct = U.TRICLINIC.copy()
+    X = U.displace_by_lattice(U.rand_in_cell(200, Ct, seed=5), Ct, (True, True, True))
+    d = O.sortbased(X, 3.0, Ct, (True, True, True))
+    assert (d["S"] != 0).any() and np.array_equal(O.pairs_R(X, d["i"], d["j"], d["S"], Ct), d["R"])
+    n, j, S, Rp = O.rows_padded(X, d["first"], d["j"], d["S"], Ct, [1, 200], 4)
+    assert n.tolist() == [int(d["first"][1] - d["first"][0]), int(d["first"][200] - d["first"][199])] and j.shape == (2, 4)
+    Z = np.round(X)
+    assert O.max_displacement2(Z + 0.5, Z) == 0.75
+
+
+def test_units_and_system_dispatch_host_logic():
+    from neighbourlists_jl_b200 import atoms
+    assert atoms._unit_scale("Å", 3.5) == (3.5, 1.0)
+    v, s = atoms._unit_scale("Å", (0.35, "nm"))
+    assert v == 0.35 and abs(s - 0.1) < 1e-15
+    v, s = atoms._unit_scale("Å", (350.0, "pm"))
+    assert abs(s - 100.0) < 1e-9
+    with pytest.raises(ValueError):
+        atoms._unit_scale("Å", (1.0, "furlong"))
+    assert atoms.is_system(atoms.isolated_system(np.zeros((2, 3)))) and not atoms.is_system(np.zeros((2, 3)))
