@@ -139,6 +139,16 @@ NL_API int nl_lazy_lj_energy(const nl_params* params, const void* X_sorted, int6
                       const void* cell_offsets, double eps, double sigma, double* energy_out, void* ws,
                       size_t ws_bytes, void* stream);
 
+/* nl_lazy_lj_forces: the fused traversal with a force sink.  fe_out (DEVICE, N x 4 T, 16-byte aligned, ORIGINAL atom order,
+ * overwritten) = (F_x, F_y, F_z, e) per atom with
+ *   e_n = sum over n's neighbours of phi(r),  phi = 4 eps ((sigma/r)^12 - (sigma/r)^6)   (sum_n e_n = nl_lazy_lj_energy)
+ *   F_n = -dE/dx_n for E = 1/2 sum_n e_n     = sum over ordered pairs (m, n) of 24 eps (2 (sigma/r)^12 - (sigma/r)^6) / r^2 * R_mn
+ * Sums are accumulated in T with atomics (order not deterministic: compare to a tolerance).  Float32 runs on the packed
+ * counting kernel with per-tile shared-memory accumulators; Float64 on the exact tiled traversal.                     */
+NL_API int nl_lazy_lj_forces(const nl_params* params, const void* X_sorted, int64_t N, const void* perm,
+                             const void* cell_offsets, double eps, double sigma, void* fe_out, void* ws,
+                             size_t ws_bytes, void* stream);
+
 /* ---- The callers either side of the hot path: device-side PairList accessors, the IsolatedCell
  * bounding box of the AtomsBase adapter, and the displacement check of a skin (Verlet) list. ------------------- */
 

@@ -102,6 +102,16 @@ function lj_energy(clist::SortedCellList{T,TI,<:CuVector}, eps, sigma) where {T,
     return e
 end
 
+"(F, e): per-atom LJ forces and energies from one fused traversal; fe is N x 4 (F_x, F_y, F_z, e)"
+function lj_forces(clist::SortedCellList{T,TI,<:CuVector}, eps, sigma) where {T,TI}
+    nat = length(clist.X); p = _params(clist.cell, clist.inv_cell, clist.pbc, clist.cutoff, clist.ncells)
+    fe = CUDA.zeros(T, 4, nat); ws = _ws(p, nat, 1)
+    _check(ccall((:nl_lazy_lj_forces, libnlcuda), Cint,
+                 (Ref{NlParams}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, Float64, Float64, CuPtr{Cvoid}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                 p, clist.X, nat, clist.perm, clist.cell_offsets, Float64(eps), Float64(sigma), fe, ws, length(ws), _stream()))
+    return (@view fe[1:3, :]), (@view fe[4, :])
+end
+
 # ---- PairList accessors without scalar indexing (src/cell_list.jl:513-606, src/iterators.jl) ------------------
 const DevPairList{T,TI} = PairList{T,TI,<:CuVector}
 

@@ -45,7 +45,7 @@ class NlError(RuntimeError):
 _lib = None
 
 EXPORTS = ("nl_version", "nl_strerror", "nl_last_cuda_error", "nl_launch_count", "nl_workspace_bytes", "nl_build_cells", "nl_count_pairs",
-           "nl_fill_pairs", "nl_fill_pairs_rows", "nl_cell_ids", "nl_shard_plan", "nl_lazy_count", "nl_lazy_lj_energy",
+           "nl_fill_pairs", "nl_fill_pairs_rows", "nl_cell_ids", "nl_shard_plan", "nl_lazy_count", "nl_lazy_lj_energy", "nl_lazy_lj_forces",
            "nl_pairs_R", "nl_max_neighbours", "nl_rows_padded", "nl_bounding_box", "nl_max_displacement2")
 NL_REDUCE_WS_BYTES = 32768
 
@@ -75,6 +75,8 @@ def lib():
         L.nl_shard_plan.restype = C.c_int
         L.nl_lazy_count.argtypes = [pp, vp, i64, vp, vp, vp, vp, sz, vp]
         L.nl_lazy_lj_energy.argtypes = [pp, vp, i64, vp, vp, C.c_double, C.c_double, vp, vp, sz, vp]
+        L.nl_lazy_lj_forces.argtypes = [pp, vp, i64, vp, vp, C.c_double, C.c_double, vp, vp, sz, vp]
+        L.nl_lazy_lj_forces.restype = C.c_int
         L.nl_pairs_R.argtypes = [pp, vp, i64, vp, vp, vp, i64, i64, vp, vp]
         L.nl_max_neighbours.argtypes = [pp, vp, i64, vp, vp]
         L.nl_rows_padded.argtypes = [pp, vp, i64, vp, vp, vp, vp, i64, C.c_int32, vp, vp, vp, vp, vp]

@@ -397,6 +397,20 @@ def lj_energy(clist: SortedCellList, eps: float, sigma: float) -> torch.Tensor:
     return e
 
 
+def lj_forces(clist: SortedCellList, eps: float, sigma: float):
+    """Fused traversal with a Lennard-Jones FORCE sink (nl_lazy_lj_forces): returns (F, e), views of one (N,4) device
+    tensor in original atom order: F[n] = -dE/dx_n for E = 1/2 sum(e), e[n] = sum over n's neighbours of
+    4 eps ((sigma/r)^12 - (sigma/r)^6); e.sum() equals lj_energy(clist) (ordered-pair convention)."""
+    N = clist.X.shape[0]
+    dev = clist.X.device
+    with torch.cuda.device(dev):
+        fe = torch.zeros((N, 4), dtype=clist.X.dtype, device=dev)
+        ws = _pairs_workspace(clist)
+        _lib.check(_lib.lib().nl_lazy_lj_forces(clist.params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets),
+                                                float(eps), float(sigma), _ptr(fe), _ptr(ws), ws.numel(), _stream(dev)))
+    return fe[:, :3], fe[:, 3]
+
+
 def neighbours(nl, i: int):
     """neighbours(nlist_or_clist, i) -> (j, R, S)  (src/cell_list.jl:606, :821-833)."""
     if isinstance(nl, PairList):

@@ -96,6 +96,36 @@ __device__ __noinline__ bool exact_pair_hit(const MaskArgs<T, TI>* ad, long long
   return r2 < g.cutoff_sq;
 }
 
+// The same, also returning R (fused force sink, rare path).
+template <class T, class TI>
+__device__ __noinline__ bool exact_pair_R(const MaskArgs<T, TI>* ad, long long gi, long long gj, int shp, T* r2_out, T* R_out) {
+  const Geo<T>& g = ad->g;
+  const Records<T>& rec = ad->rec;
+  const T xi = rec.px[gi], yi = rec.py[gi], zi = rec.pz[gi];
+  const T xj = rec.px[gj], yj = rec.py[gj], zj = rec.pz[gj];
+  long long wi[3], wj[3], sl[3];
+  int cc[3];
+  const uint32_t pwi = rec.pw[gi], pwj = rec.pw[gj];
+  if (pwi & WIND_OVERFLOW) cell_of(g, xi, yi, zi, cc, wi); else unpack_wind(pwi, wi);
+  if (pwj & WIND_OVERFLOW) cell_of(g, xj, yj, zj, cc, wj); else unpack_wind(pwj, wj);
+  unpack_shift(shp, sl);
+  const long long S[3] = {sl[0] + wi[0] - wj[0], sl[1] + wi[1] - wj[1], sl[2] + wi[2] - wj[2]};
+  T R[3];
+  const T r2 = pair_r2(g, xi, yi, zi, xj, yj, zj, S, R);
+  *r2_out = r2;
+  R_out[0] = R[0]; R_out[1] = R[1]; R_out[2] = R[2];
+  return r2 < g.cutoff_sq;
+}
+
+// Float32 Lennard-Jones pair terms (fused force sink): phi = 4 eps (s^12 - s^6), gg = 24 eps (2 s^12 - s^6) / r2.
+__device__ __forceinline__ void lj_pair_terms_f32(float eps4, float eps24, float sigma2, float r2, float& phi, float& gg) {
+  float rc = __frcp_rn(r2);
+  rc = rc * (2.0f - r2 * rc);  // one Newton step: ~1 ulp
+  const float s2 = sigma2 * rc, s6 = s2 * s2 * s2, s12 = s6 * s6;
+  phi = eps4 * (s12 - s6);
+  gg = eps24 * (2.0f * s12 - s6) * rc;
+}
+
 // Shared tile prologue: virtual cell table (slot starts, global starts, packed shifts).
 // Returns the total number of staged slots.
 template <class T, class TI>
@@ -208,12 +238,21 @@ __device__ __forceinline__ long long cell_linear(const int nc[3], int cx, int cy
 //   CM_MASK  counts + hit masks + per-cell flags for the fill pass (candidate lists up to 256)
 //   CM_COUNT counts only: the lazy count_neighbours sink (candidate lists up to 512, so denser systems stay on this path)
 //   CM_LJ    fused Lennard-Jones energy over the hits, Float32 positions (BASELINE config 5); no counts, no masks
-enum { CM_MASK = 0, CM_COUNT = 1, CM_LJ = 2 };
+//   CM_LJF   fused Lennard-Jones forces + per-atom energies, Float32: every lane sums what the home atoms do to ITS candidate,
+//            adds that to a per-slot accumulator in shared memory, and the tile flushes each slot with one vector atomic
+enum { CM_MASK = 0, CM_COUNT = 1, CM_LJ = 2, CM_LJF = 3 };
+#ifndef NL_LJF_SMEM_KB
+#define NL_LJF_SMEM_KB 72
+#endif
+#ifndef NL_LJF_MINB
+#define NL_LJF_MINB 3
+#endif
 __host__ __device__ constexpr int cm_tabcap(int cm) { return cm == CM_MASK ? MASK_MAXCAND : 2 * MASK_MAXCAND; }
-__host__ __device__ constexpr int cm_smem_bytes(int cm) { return cm == CM_MASK ? 48 * 1024 : 64 * 1024; }
+__host__ __device__ constexpr int cm_smem_bytes(int cm) { return cm == CM_MASK ? 48 * 1024 : (cm == CM_LJF ? NL_LJF_SMEM_KB * 1024 : 64 * 1024); }
+__host__ __device__ constexpr int cm_slot_bytes(int cm) { return cm == CM_LJF ? 32 : 16; }  // float4 position (+ float4 force/energy accumulator)
 __host__ __device__ constexpr int cm_warp_bytes(int cm) { return cm_tabcap(cm) * 3 + MASK_WORDS * 34 * 4 + 16 * 32; }
 __host__ __device__ constexpr int cm_fixed_bytes(int cm) { return 3 * TILE_VPAD * 4 + 64 * 4 + (TILE_NT / 32) * cm_warp_bytes(cm); }
-__host__ __device__ constexpr int cm_cap(int cm) { return (cm_smem_bytes(cm) - cm_fixed_bytes(cm)) / 16 / 8 * 8; }
+__host__ __device__ constexpr int cm_cap(int cm) { return (cm_smem_bytes(cm) - cm_fixed_bytes(cm)) / cm_slot_bytes(cm) / 8 * 8; }
 static_assert(cm_warp_bytes(CM_MASK) % 16 == 0 && cm_fixed_bytes(CM_MASK) % 16 == 0 && cm_warp_bytes(CM_COUNT) % 16 == 0, "alignment");
 //
 // Shared memory: tile tables | per-warp {cell tables, chunk-major mask words, home-atom pair buffer} |
@@ -228,12 +267,13 @@ constexpr float SLOT_FAR = -1.0e18f;  // staged slots that need the exact path: 
 #define NL_CNT_MINB 4
 #endif
 template <class T, class TI, int CM>
-__global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : 3) k_count_mask(const MaskArgs<T, TI> a) {
+__global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : (CM == CM_LJF ? NL_LJF_MINB : 3)) k_count_mask(const MaskArgs<T, TI> a) {
   constexpr bool WANT_MASK = CM == CM_MASK;
   constexpr int TABCAP = cm_tabcap(CM);
   constexpr int CNT_WARP_BYTES = cm_warp_bytes(CM);
   constexpr int CAPSLOTS = cm_cap(CM);
-  static_assert(CM != CM_LJ || sizeof(T) == 4, "the fused LJ sink of this kernel is Float32 only");
+  static_assert((CM != CM_LJ && CM != CM_LJF) || sizeof(T) == 4, "the fused LJ sinks of this kernel are Float32 only");
+  constexpr bool LJ_ANY = CM == CM_LJ || CM == CM_LJF;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* vstart = (int*)smem_raw;
   int* vgs = vstart + TILE_VPAD;
@@ -241,6 +281,7 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : 3) k_co
   int* hcell = vsh + TILE_VPAD;  // [64] packed (lx, ly, lz) of each home cell
   unsigned char* wbase = (unsigned char*)(hcell + 64);
   float4* sq = (float4*)(wbase + (TILE_NT / 32) * CNT_WARP_BYTES);
+  float4* sF = sq + CAPSLOTS;  // CM_LJF: (force x, y, z, energy) accumulated per staged slot
   __shared__ int scan_sm[33];
   __shared__ int s_next;
 
@@ -272,7 +313,7 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : 3) k_co
   if (tid == 0) s_next = 0;
   __syncthreads();
 
-  constexpr int GMODE = CM == CM_LJ ? MODE_LJ : MODE_COUNT;
+  constexpr int GMODE = CM == CM_LJ ? MODE_LJ : (CM == CM_LJF ? MODE_LJF : MODE_COUNT);
   const bool tile_generic = total > CAPSLOTS;   // denser than the staging capacity: the whole tile takes the generic route
   if (tile_generic) {
     for (int hc = wid; hc < nhome; hc += TILE_NT / 32) {
@@ -316,6 +357,7 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : 3) k_co
       const int v = find_vcell(vstart, NV, sl);
       const long long src = (long long)vgs[v] + (sl - vstart[v]);
       sq[sl] = make_float4((float)a.rec.px[src], (float)a.rec.py[src], (float)a.rec.pz[src], __uint_as_float(a.rec.pw[src]));
+      if (CM == CM_LJF) sF[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   __syncthreads();
@@ -324,6 +366,7 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : 3) k_co
   const float mid = a.mid, hw = a.hw;
   const float2 nmid2 = make_float2(-mid, -mid);
   const float csqf = (float)g.cutoff_sq;
+  const float lj_s2 = (float)a.out.lj_sigma2, lj_e4 = (float)(4.0 * a.out.lj_eps), lj_e24 = (float)(24.0 * a.out.lj_eps);
 
   while (true) {
     int hc = 0;
@@ -403,6 +446,7 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : 3) k_co
             mtv(g.cell, (T)(s[0] + w0[0] - w1[0]), (T)(s[1] + w0[1] - w1[1]), (T)(s[2] + w0[2] - w1[2]), cs0, cs1, cs2);
           }
         }
+        float lf0 = 0.f, lf1 = 0.f, lf2 = 0.f, lfe = 0.f;  // CM_LJF: what this group's home atoms do to the lane's candidate
         float bmin = 3.0e38f;  // min |t| over this lane's pairs: <= hw means some pair fell in the uncertainty band
         uint32_t* mrow = mkT + (kc & (MASK_WORDS - 1)) * 34;
         const int self_aa = valid ? (int)tab.cslot[f] - (hstart + g0) : -1;  // the home atom this candidate IS under zero shift (CM_LJ)
@@ -444,6 +488,19 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : 3) k_co
                 if (valid && r2x < csqf && 2 * pr != self_aa) e_acc += lj_term(a.out.lj_eps, a.out.lj_sigma2, r2x);
                 if (valid && r2y < csqf && 2 * pr + 1 != self_aa && 2 * pr + 1 < ng) e_acc += lj_term(a.out.lj_eps, a.out.lj_sigma2, r2y);
               }
+            } else if (CM == CM_LJF) {
+              if (!slow_group && !cand_bad) {
+                if (valid && r2x < csqf && 2 * pr != self_aa) {
+                  float phi, gg;
+                  lj_pair_terms_f32(lj_e4, lj_e24, lj_s2, r2x, phi, gg);
+                  lf0 += gg * R0.x; lf1 += gg * R1.x; lf2 += gg * R2.x; lfe += phi;
+                }
+                if (valid && r2y < csqf && 2 * pr + 1 != self_aa && 2 * pr + 1 < ng) {
+                  float phi, gg;
+                  lj_pair_terms_f32(lj_e4, lj_e24, lj_s2, r2y, phi, gg);
+                  lf0 += gg * R0.y; lf1 += gg * R1.y; lf2 += gg * R2.y; lfe += phi;
+                }
+              }
             } else {
               const unsigned b0 = __ballot_sync(FULL, valid && r2x < csqf);
               const unsigned b1 = __ballot_sync(FULL, valid && r2y < csqf);
@@ -462,6 +519,16 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : 3) k_co
               const float t = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmaf_rn(dx, dx, -mid)));
               hit = valid && t < -hw;
               if (valid && (cand_bad || ((hbad >> aa) & 1u) || fabsf(t) <= hw)) hit = exact_pair_hit<T, TI>(a.self, hg0 + g0 + aa, gj, shp);
+            } else if (CM == CM_LJF) {
+              hit = false;
+              if (valid && (slow_group || cand_bad) && aa != self_aa) {
+                T r2e, Re[3];
+                if (exact_pair_R<T, TI>(a.self, hg0 + g0 + aa, gj, shp, &r2e, Re)) {
+                  float phi, gg;
+                  lj_pair_terms_f32(lj_e4, lj_e24, lj_s2, (float)r2e, phi, gg);
+                  lf0 += gg * (float)Re[0]; lf1 += gg * (float)Re[1]; lf2 += gg * (float)Re[2]; lfe += phi;
+                }
+              }
             } else if (CM == CM_LJ) {
               hit = false;
               if (valid && (slow_group || cand_bad) && aa != self_aa) {  // exactly the pairs the fast loop skipped
@@ -474,7 +541,7 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : 3) k_co
             } else {
               hit = valid && exact_pair_hit<T, TI>(a.self, hg0 + g0 + aa, gj, shp);
             }
-            if (CM != CM_LJ) {
+            if (!LJ_ANY) {
               const unsigned bal = __ballot_sync(FULL, hit);
               if (lane == 0) mrow[aa] = bal;
             }
@@ -482,7 +549,11 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : 3) k_co
           __syncwarp();
         }
         // drop the self pair (same atom, zero shift): flat index fh + g0 + aa of home atom aa; accumulate the counts
-        if (CM != CM_LJ && lane < ng) {
+        if (CM == CM_LJF && valid && (lf0 != 0.f || lf1 != 0.f || lf2 != 0.f || lfe != 0.f)) {
+          float* d = (float*)(sF + tab.cslot[f]);  // lanes hold distinct slots; other warps may hit the same slot
+          atomicAdd(d, lf0); atomicAdd(d + 1, lf1); atomicAdd(d + 2, lf2); atomicAdd(d + 3, lfe);
+        }
+        if (!LJ_ANY && lane < ng) {
           const int fs = fh + g0 + lane;
           if ((fs >> 5) == kc) mrow[lane] &= ~(1u << (fs & 31));
           cnt_acc += __popc(mrow[lane]);
@@ -491,11 +562,23 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : 3) k_co
       }
       __syncwarp();
       // per-atom counts; masks to global (atom-major, MASK_WORDS per atom)
-      if (CM != CM_LJ && lane < ng) a.out.counts[a.rec.pidx[hg0 + g0 + lane]] = cnt_acc;
+      if (!LJ_ANY && lane < ng) a.out.counts[a.rec.pidx[hg0 + g0 + lane]] = cnt_acc;
       if (WANT_MASK) {
         uint32_t* dst = a.masks + (hg0 + g0) * MASK_WORDS;
         for (int w = lane; w < ng * MASK_WORDS; w += 32) dst[w] = (w & 7) < nchunk ? mkT[(w & 7) * 34 + (w >> 3)] : 0u;
       }
+    }
+  }
+  if (CM == CM_LJF) {
+    // flush: one vector atomic per staged slot (home AND halo slots: a halo atom's other contributions come from its own tiles)
+    __syncthreads();
+    for (int sl = tid; sl < total; sl += TILE_NT) {
+      const float4 f = sF[sl];
+      if (f.x == 0.f && f.y == 0.f && f.z == 0.f && f.w == 0.f) continue;
+      const int v = find_vcell(vstart, NV, sl);
+      const uint32_t jo = a.rec.pidx[(long long)vgs[v] + (sl - vstart[v])];
+      float* dst = (float*)a.out.fe + 4ll * jo;
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(f.x), "f"(f.y), "f"(f.z), "f"(f.w) : "memory");
     }
   }
   }  // !tile_generic

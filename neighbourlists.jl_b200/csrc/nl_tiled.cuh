@@ -226,6 +226,7 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_tiled(const TiledArgs<T, TI> a) 
             mtv(g.cell, (T)sl0, (T)sl1, (T)sl2, cs0, cs1, cs2);  // cell' * s_loop, shared by every home atom with w_i == w_j
           }
 
+          T lf0 = 0, lf1 = 0, lf2 = 0, lfe = 0;  // MODE_LJF: force / energy this chunk's home atoms put on the lane's candidate
           for (int aa = 0; aa < ng; aa++) {
             const int hs = hstart + g0 + aa;
             const T xi = sx[hs], yi = sy[hs], zi = sz[hs];
@@ -256,8 +257,13 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_tiled(const TiledArgs<T, TI> a) 
                 const double s2 = a.out.lj_sigma2 / (double)r2, s6 = s2 * s2 * s2;
                 e_acc += 4.0 * a.out.lj_eps * (s6 * s6 - s6);
               }
+              if (MODE == MODE_LJF && hit) {
+                double phi, gg;
+                lj_pair_terms(a.out.lj_eps, a.out.lj_sigma2, (double)r2, phi, gg);
+                lf0 += (T)(gg * (double)R0); lf1 += (T)(gg * (double)R1); lf2 += (T)(gg * (double)R2); lfe += (T)phi;
+              }
             }
-            if (MODE != MODE_LJ) {
+            if (MODE == MODE_COUNT || MODE == MODE_FILL) {
               const unsigned bal = __ballot_sync(FULL, hit);
               if (MODE == MODE_FILL) {
                 const long long base = __shfl_sync(FULL, my_base, aa) + __shfl_sync(FULL, my_cnt, aa);
@@ -275,6 +281,7 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_tiled(const TiledArgs<T, TI> a) 
               if (lane == aa) my_cnt += __popc(bal);
             }
           }
+          if (MODE == MODE_LJF && valid && (lf0 != 0 || lf1 != 0 || lf2 != 0 || lfe != 0)) ljf_add_global<T, TI>(a.out, jo, lf0, lf1, lf2, lfe);
         }
         if (MODE == MODE_COUNT && lane < ng) a.out.counts[my_io] = my_cnt;
       }

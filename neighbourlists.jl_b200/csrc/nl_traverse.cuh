@@ -11,7 +11,7 @@
 
 namespace nl {
 
-enum { MODE_COUNT = 0, MODE_FILL = 1, MODE_LJ = 2 };
+enum { MODE_COUNT = 0, MODE_FILL = 1, MODE_LJ = 2, MODE_LJF = 3 };
 
 
 template <class T> struct Records {
@@ -34,7 +34,23 @@ template <class T, class TI> struct Sinks {
   const uint32_t* pgid0; //            with gmap: gmap[pidx[s]] - 1 per SORTED atom (one gather per atom instead of one per pair)
   double* energy;        // MODE_LJ: device scalar
   double lj_eps, lj_sigma2;
+  T* fe;                 // MODE_LJF: N x 4 (force x, y, z, energy) per ORIGINAL atom, accumulated with atomics
 };
+
+// Lennard-Jones pair terms for squared distance r2: phi = 4 eps (s^12 - s^6), gg = 24 eps (2 s^12 - s^6) / r2 with
+// s^2 = sigma^2 / r2.  A visit of the ordered pair (i, j) with R = x_j - x_i + shift adds gg * R to the force on j and
+// phi to j's energy; every ordered pair is visited exactly once, so each atom ends up with its full force
+// F_j = -dE/dx_j (E = half the ordered-pair sum) and with e_j = sum of phi over its neighbours.
+__device__ __forceinline__ void lj_pair_terms(double eps, double sigma2, double r2, double& phi, double& gg) {
+  const double inv = 1.0 / r2, s2 = sigma2 * inv, s6 = s2 * s2 * s2;
+  phi = 4.0 * eps * (s6 * s6 - s6);
+  gg = 24.0 * eps * (2.0 * s6 * s6 - s6) * inv;
+}
+template <class T, class TI>
+__device__ __forceinline__ void ljf_add_global(const Sinks<T, TI>& out, uint32_t jo, T f0, T f1, T f2, T e) {
+  T* d = out.fe + 4ll * jo;
+  atomicAdd(d, f0); atomicAdd(d + 1, f1); atomicAdd(d + 2, f2); atomicAdd(d + 3, e);
+}
 
 template <class T, class TI> __device__ __forceinline__ TI out_index(const Sinks<T, TI>& out, uint32_t orig) {
   return out.gmap ? out.gmap[orig] : (TI)orig + 1;
@@ -135,6 +151,11 @@ __device__ __forceinline__ double generic_atom(long long s, const Records<T>& re
             if (MODE == MODE_LJ) {
               const double s2 = out.lj_sigma2 / (double)r2, s6 = s2 * s2 * s2;
               e_acc += 4.0 * out.lj_eps * (s6 * s6 - s6);
+            }
+            if (MODE == MODE_LJF) {
+              double phi, gg;
+              lj_pair_terms(out.lj_eps, out.lj_sigma2, (double)r2, phi, gg);
+              ljf_add_global<T, TI>(out, jo, (T)(gg * (double)R[0]), (T)(gg * (double)R[1]), (T)(gg * (double)R[2]), (T)phi);
             }
           }
         }

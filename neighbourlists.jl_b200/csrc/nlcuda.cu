@@ -189,6 +189,8 @@ template <class T> struct Plan {
   int lazy_ok;          // the packed counting kernel can serve the lazy sinks (count; LJ for Float32)
   TileShape ts_lazy;
   MaskThresholds th_lazy;
+  int ljf_ok;           // ... and the fused force sink (Float32; its own tile: the slots also carry accumulators)
+  TileShape ts_ljf;
 };
 template <class T, class TI> Plan<T> make_plan(const nl_params* p, const Geo<T>& g, int64_t N) {
   Plan<T> pl;
@@ -196,6 +198,7 @@ template <class T, class TI> Plan<T> make_plan(const nl_params* p, const Geo<T>&
   pl.th = MaskThresholds{0.f, 0.f, 0.f, 0};
   pl.th_lazy = pl.th;
   pl.lazy_ok = 0;
+  pl.ljf_ok = 0;
   if (N <= 0) return pl;
   if (!tiled_applicable<T>(p, g, N, tile_cap<T>(), pl.ts_exact)) return pl;
   pl.path = PATH_TILED;
@@ -207,6 +210,7 @@ template <class T, class TI> Plan<T> make_plan(const nl_params* p, const Geo<T>&
       pl.lazy_ok = pl.th_lazy.ok;
     }
   }
+  if (sizeof(T) == 4 && 27.0 * dens <= 400.0 && pick_tile<T>(g, N, cm_cap(CM_LJF), pl.ts_ljf)) pl.ljf_ok = 1;
   if (27.0 * dens > 200.0) return pl;  // candidate lists would overflow the 256-bit masks too often
   if (!pick_tile<T>(g, N, CNT_CAP2, pl.ts_count) || !pick_tile<T>(g, N, fill_cap<T, TI>(), pl.ts_fill)) return pl;
   if (sizeof(T) == 8) {
@@ -251,23 +255,24 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
   Records<T> rec = records_of<T>(w);
   const Plan<T> pl = make_plan<T, TI>(p, g, N);
   constexpr bool LJ_FAST = MODE == MODE_LJ && sizeof(T) == 4;
-  if (pl.lazy_ok && ((MODE == MODE_COUNT && !want_mask) || LJ_FAST)) {
+  constexpr bool LJF_FAST = MODE == MODE_LJF && sizeof(T) == 4;
+  if ((pl.lazy_ok && ((MODE == MODE_COUNT && !want_mask) || LJ_FAST)) || (pl.ljf_ok && LJF_FAST)) {
     // lazy sinks on the packed counting kernel: no masks, candidate lists up to 512
-    constexpr int CM = MODE == MODE_LJ ? CM_LJ : CM_COUNT;
+    constexpr int CM = MODE == MODE_LJ ? CM_LJ : (MODE == MODE_LJF ? CM_LJF : CM_COUNT);
     MaskArgs<T, TI> a;
-    mask_args<T, TI>(a, N, (const TI*)co, rec, g, sk, pl.ts_lazy, nullptr);
+    mask_args<T, TI>(a, N, (const TI*)co, rec, g, sk, LJF_FAST ? pl.ts_ljf : pl.ts_lazy, nullptr);
     a.mid = pl.th_lazy.mid; a.hw = pl.th_lazy.hw; a.dguard = pl.th_lazy.dguard;
     a.self = (const MaskArgs<T, TI>*)((char*)w.hdr + 3072);
     NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
     const unsigned nblk = (unsigned)((long long)a.ntx * a.nty * a.ntz);
-    if constexpr (CM == CM_COUNT || LJ_FAST) {
+    if constexpr (CM == CM_COUNT || LJ_FAST || LJF_FAST) {
       static bool done = false;
       int rc = set_smem_once(k_count_mask<T, TI, CM>, cm_smem_bytes(CM), done);
       if (rc) return rc;
       k_count_mask<T, TI, CM><<<nblk, TILE_NT, cm_smem_bytes(CM), st>>>(a);
     }
     NL_LAUNCHED(1);
-  } else if (pl.path == PATH_MASK && MODE != MODE_LJ) {
+  } else if (pl.path == PATH_MASK && (MODE == MODE_COUNT || MODE == MODE_FILL)) {
     TiledScratch tsx = tiled_scratch(w.tiled, N);
     MaskArgs<T, TI> a;
     mask_args<T, TI>(a, N, (const TI*)co, rec, g, sk, MODE == MODE_FILL ? pl.ts_fill : pl.ts_count, tsx.masks);
@@ -443,6 +448,22 @@ template <class T> int maxdisp_impl(const void* X, const void* Y, int64_t N, voi
   return NL_OK;
 }
 
+template <class T, class TI>
+int lazy_ljf_impl(const nl_params* p, const void* Xs, int64_t N, const void* perm, const void* co, double eps, double sigma, void* fe_out,
+                  void* ws, cudaStream_t st) {
+  if (N <= 0) return NL_OK;
+  NL_CUDA(cudaMemsetAsync(fe_out, 0, (size_t)N * 4 * sizeof(T), st));
+  Geo<T> g = make_geo<T>(p);
+  PairWs w = pair_ws(ws, p, N);
+  int rc = prep_impl<T, TI>(p, Xs, N, perm, w, g, st);
+  if (rc) return rc;
+  Sinks<T, TI> sk = {};
+  sk.fe = (T*)fe_out;
+  sk.lj_eps = eps;
+  sk.lj_sigma2 = sigma * sigma;
+  return traverse<T, TI, MODE_LJF>(p, N, co, w, g, sk, false, st);
+}
+
 #define NL_DISPATCH(p, FN, ...)                                                              \
   ((p)->float_type == NL_F64                                                                 \
        ? ((p)->int_type == NL_I64 ? FN<double, int64_t>(__VA_ARGS__) : FN<double, int32_t>(__VA_ARGS__)) \
@@ -579,6 +600,17 @@ int nl_lazy_lj_energy(const nl_params* params, const void* X_sorted, int64_t N, 
   rc = check_ws(ws, ws_bytes, pair_ws(nullptr, params, N).total_bytes);
   if (rc) return rc;
   return NL_DISPATCH(params, lazy_lj_impl, params, X_sorted, N, perm, cell_offsets, eps, sigma, energy_out, ws, (cudaStream_t)stream);
+}
+
+int nl_lazy_lj_forces(const nl_params* params, const void* X_sorted, int64_t N, const void* perm, const void* cell_offsets, double eps,
+                      double sigma, void* fe_out, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_params(params, N);
+  if (rc) return rc;
+  if (N == 0) return NL_OK;
+  if (!fe_out || !cell_offsets || !X_sorted || !perm || ((uintptr_t)fe_out & 15) != 0) return NL_ERR_BAD_ARG;
+  rc = check_ws(ws, ws_bytes, pair_ws(nullptr, params, N).total_bytes);
+  if (rc) return rc;
+  return NL_DISPATCH(params, lazy_ljf_impl, params, X_sorted, N, perm, cell_offsets, eps, sigma, fe_out, ws, (cudaStream_t)stream);
 }
 
 int nl_pairs_R(const nl_params* params, const void* X, int64_t N, const void* i, const void* j, const void* S, int64_t p_lo, int64_t p_hi,

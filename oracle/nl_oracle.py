@@ -238,3 +238,21 @@ def max_displacement2(X, X_ref, dtype=np.float64):
     d = np.asarray(X, dtype=T) - np.asarray(X_ref, dtype=T)
     d2 = (d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1]) + d[:, 2] * d[:, 2]
     return T(d2.max()) if d2.size else T(0)
+
+
+def lj_forces(d, eps, sigma, N):
+    """Per-atom Lennard-Jones forces and energies from an oracle pair list d (with R), in float64: a visit of the
+    ordered pair (i, j), R = x_j - x_i + C'S, adds 24 eps (2 s^12 - s^6) / r^2 * R to the force on j and
+    phi = 4 eps (s^12 - s^6) to j's energy (s = sigma / r).  Returns (F (N,3), e (N,)); F = -dE/dX for E = e.sum() / 2."""
+    R = np.asarray(d["R"], dtype=np.float64)
+    j0 = np.asarray(d["j"], dtype=np.int64) - 1
+    r2 = (R * R).sum(axis=1)
+    s2 = sigma * sigma / r2
+    s6 = s2 * s2 * s2
+    phi = 4.0 * eps * (s6 * s6 - s6)
+    gg = 24.0 * eps * (2.0 * s6 * s6 - s6) / r2
+    F = np.zeros((N, 3))
+    e = np.zeros(N)
+    np.add.at(F, j0, gg[:, None] * R)
+    np.add.at(e, j0, phi)
+    return F, e

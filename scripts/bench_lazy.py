@@ -16,7 +16,7 @@ for name, fn in (("build_cell_list", lambda: nl.neighbour_list(Xd, 6.0, C, (True
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(); clist = fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
     res[name + "_ms"] = min(ts[2:])
-for name, fn in (("lj_energy", lambda: nl.lj_energy(clist, 1.0, 3.4)), ("count_neighbours", lambda: (setattr(clist, "_counts", None), nl.count_neighbours(clist))[1])):
+for name, fn in (("lj_energy", lambda: nl.lj_energy(clist, 1.0, 3.4)), ("lj_forces", lambda: nl.lj_forces(clist, 1.0, 3.4)), ("count_neighbours", lambda: (setattr(clist, "_counts", None), nl.count_neighbours(clist))[1])):
     ts = []
     for _ in range(6):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -24,5 +24,6 @@ for name, fn in (("lj_energy", lambda: nl.lj_energy(clist, 1.0, 3.4)), ("count_n
     res[name + "_ms"] = min(ts[2:])
 pairs = int(nl.count_neighbours(clist).sum().item())
 res.update(atoms=N, virtual_pairs=pairs, energy=float(nl.lj_energy(clist, 1.0, 3.4).item()),
+           ljf_pairs_per_s=pairs / (res["lj_forces_ms"] * 1e-3), energy_from_forces=float(nl.lj_forces(clist, 1.0, 3.4)[1].double().sum().item()),
            lj_pairs_per_s=pairs / (res["lj_energy_ms"] * 1e-3), count_pairs_per_s=pairs / (res["count_neighbours_ms"] * 1e-3))
 print(json.dumps(res))

@@ -175,3 +175,49 @@ def test_skin_list(nl, dtype):
     assert sl.update(torch.from_numpy(X2).cuda()) is True and sl.builds == 2
     fresh = O.sortbased(X2, rc + skin, C, pbc, dtype=dtype)
     U.assert_engine_matches_oracle(sl.nlist.cpu(), fresh, rtol=1e-12 if dtype == np.float64 else 1e-5, msg="rebuilt skin list")
+
+
+def _check_lj_forces(nl, X, C, pbc, rc, dtype, eps=0.8, sig=2.5, tol=None):
+    import torch
+    N = X.shape[0]
+    cl = nl.neighbour_list(torch.from_numpy(X).cuda(), rc, C, pbc, lazy=True)
+    F, e = nl.lj_forces(cl, eps, sig)
+    assert F.shape == (N, 3) and e.shape == (N,) and F.dtype == cl.X.dtype
+    d = O.sortbased(X, rc, C, pbc, dtype=dtype)
+    wF, we = O.lj_forces(d, eps, sig, N)
+    tol = tol or (1e-10 if dtype == np.float64 else 2e-5)
+    F, e = F.cpu().numpy().astype(np.float64), e.cpu().numpy().astype(np.float64)
+    # per-atom scale: the sum of the magnitudes of the terms (forces cancel)
+    R = d["R"].astype(np.float64)
+    r2 = (R * R).sum(axis=1)
+    s6 = (sig * sig / r2) ** 3
+    mag = np.zeros(N)
+    np.add.at(mag, d["j"].astype(np.int64) - 1, np.abs(24 * eps * (2 * s6 * s6 - s6) / r2) * np.sqrt(r2))
+    emag = np.zeros(N)
+    np.add.at(emag, d["j"].astype(np.int64) - 1, np.abs(4 * eps * (s6 * s6 - s6)))
+    assert (np.abs(F - wF).max(axis=1) <= tol * np.maximum(mag, 1e-30) + 1e-300).all(), np.abs(F - wF).max()
+    assert (np.abs(e - we) <= tol * np.maximum(emag, 1e-30) + 1e-300).all()
+    etot = float(nl.lj_energy(cl, eps, sig).item())
+    assert abs(e.sum() - etot) <= 10 * tol * emag.sum()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_lj_forces_match_oracle(nl, dtype):
+    # fast packed path (Float32) / exact tiled path (Float64): cubic periodic, triclinic mixed pbc with displaced atoms
+    X, C, L = U.rand_config(20000, seed=81, dtype=dtype)
+    _check_lj_forces(nl, X, C, (True, True, True), 5.0, dtype)
+    Ct = (U.TRICLINIC * 3.0).astype(dtype)
+    pbc = (True, False, True)
+    Xt = U.displace_by_lattice(U.rand_in_cell(8000, Ct, seed=82, dtype=dtype), Ct, pbc)
+    _check_lj_forces(nl, Xt, Ct, pbc, 3.0, dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_lj_forces_fallback_routes(nl, dtype):
+    # generic route: box narrower than two cutoffs (self images, nxyz-wide stencils); dense cluster: cells beyond the tables
+    X, C = U.fcc(3.61, (2, 2, 2), dtype=dtype)
+    _check_lj_forces(nl, X, C, (True, True, True), 5.0, dtype)
+    X, C, L = U.rand_config(6000, seed=83, dtype=dtype)
+    rng = np.random.default_rng(4)
+    X[:700] = (X[0] + rng.uniform(0, 4.0, size=(700, 3))).astype(dtype)
+    _check_lj_forces(nl, X, C, (True, True, False), 4.0, dtype, sig=0.6)

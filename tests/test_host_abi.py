@@ -179,3 +179,29 @@ def test_units_and_system_dispatch_host_logic():
     with pytest.raises(ValueError):
         atoms._unit_scale("Å", (1.0, "furlong"))
     assert atoms.is_system(atoms.isolated_system(np.zeros((2, 3)))) and not atoms.is_system(np.zeros((2, 3)))
+
+
+def test_lj_force_restatement_is_minus_gradient():
+    # pins the checker of nl_lazy_lj_forces: F = -dE/dX (central differences) and sum(e) = the oracle's LJ energy
+    from tests import util as U
+    X, C = U.fcc(3.61, (3, 3, 3))
+    rng = np.random.default_rng(11)
+    X = X + rng.uniform(-0.05, 0.05, size=X.shape)
+    pbc, rc, eps, sig = (True, True, False), 4.6, 0.7, 2.3  # cutoff between the 3rd (4.42) and 4th (5.11) fcc shells
+    N = X.shape[0]
+
+    def energy(Y):
+        d = O.sortbased(Y, rc, C, pbc)
+        return O.lj_forces(d, eps, sig, N)[1].sum() / 2.0, d
+
+    E0, d0 = energy(X)
+    F, e = O.lj_forces(d0, eps, sig, N)
+    assert abs(e.sum() - O.lj_energy(O.sortbased(X, rc, C, pbc, lazy=True), eps, sig)) <= 1e-9 * abs(e.sum())
+    h = 1e-5
+    for n, k in ((0, 0), (17, 1), (55, 2), (107, 0)):
+        Xp, Xm = X.copy(), X.copy()
+        Xp[n, k] += h
+        Xm[n, k] -= h
+        fd = -(energy(Xp)[0] - energy(Xm)[0]) / (2 * h)
+        assert abs(fd - F[n, k]) <= 1e-6 * max(1.0, abs(F[n, k])), (n, k, fd, F[n, k])
+    assert np.abs(F.sum(axis=0)).max() <= 1e-9 * np.abs(F).max() * N  # Newton's third law
