@@ -64,8 +64,16 @@ typedef struct nl_params {
   int32_t ncells[3];   /* clist.ncells = max(floor(lens / cutoff), 1)                               */
   int32_t nxyz[3];     /* ceil(cutoff * ncells / |lens|): stencil half-widths, >= 1                 */
   uint8_t pbc[3];      /* clist.pbc                                                                 */
-  uint8_t reserved[5]; /* must be zero                                                              */
+  uint8_t reserved[5]; /* reserved[0]: NL_FLAG_* bits; the rest must be zero                        */
 } nl_params;
+
+/* params->reserved[0] flags.
+ * NL_FLAG_HALF (nl_count_pairs / nl_fill_pairs only): HALF list -- of every mirror couple (i, j, S) / (j, i, -S) exactly
+ * one pair is stored (which one is unspecified: the engine keeps the pair whose second atom comes later in cell-sorted
+ * order; self images keep the lexicographically positive shift).  `first` then holds the half-list row sizes; P is exactly
+ * half the full count.  Absent in the reference: halves the output traffic for consumers that use Newton's
+ * third law.  The lazy sinks ignore the flag.                                                                          */
+#define NL_FLAG_HALF 1
 
 /* Workspace stages for nl_workspace_bytes. */
 enum { NL_STAGE_BUILD = 0, NL_STAGE_PAIRS = 1 };

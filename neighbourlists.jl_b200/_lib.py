@@ -13,6 +13,7 @@ import numpy as np
 NL_F32, NL_F64 = 0, 1
 NL_I32, NL_I64 = 0, 1
 NL_STAGE_BUILD, NL_STAGE_PAIRS = 0, 1
+NL_FLAG_HALF = 1
 NL_OK, NL_ERR_BAD_ARG, NL_ERR_WORKSPACE, NL_ERR_CUDA, NL_ERR_OVERFLOW, NL_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 
 _HERE = os.path.dirname(os.path.abspath(__file__))

@@ -99,6 +99,7 @@ class PairList:
     first: torch.Tensor   # (N+1,) TI, 1-based
     R: Optional[torch.Tensor] = None
     params: object = field(repr=False, default=None)  # host-side extra: nl_params of the list (types, cell)
+    half: bool = False    # half list: one pair per mirror couple (i, j, S) / (j, i, -S)  (NL_FLAG_HALF)
 
     def cpu(self):
         """Device -> host copies of every array (numpy), for inspection and tests."""
@@ -152,13 +153,20 @@ def build_cell_list(X, cutoff, cell=None, pbc=None, *, int_type=np.int32, device
 
 
 def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers: Optional[dict] = None,
-                         n_rows: Optional[int] = None, index_map: Optional[torch.Tensor] = None) -> PairList:
+                         n_rows: Optional[int] = None, index_map: Optional[torch.Tensor] = None, half: bool = False) -> PairList:
     """materialize_pairlist(clist) -> PairList  (src/gpu_kernels.jl:299-364).  with_R additionally
     stores R = X[j] - X[i] + C' S per pair (what the reference recomputes in _getR).
 
     Shard mode (sharded.py): with n_rows, only the first n_rows atoms get rows (`first` has n_rows+1
-    entries) and i/j are written through index_map (global 1-based indices, one per local atom)."""
+    entries) and i/j are written through index_map (global 1-based indices, one per local atom).
+
+    half=True stores one pair of every mirror couple (i, j, S) / (j, i, -S) (NL_FLAG_HALF, include/nlcuda.h): half the
+    pairs, half the output traffic; which of the two is kept is unspecified."""
     import ctypes as C
+    params = clist.params
+    if half:
+        params = type(clist.params).from_buffer_copy(clist.params)
+        params.reserved[0] = _lib.NL_FLAG_HALF
     N = clist.X.shape[0]
     dev = clist.X.device
     it = clist.perm.dtype
@@ -170,7 +178,7 @@ def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers:
         if timers is not None:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
-        _lib.check(L.nl_count_pairs(clist.params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
+        _lib.check(L.nl_count_pairs(params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
                                     C.byref(total), _ptr(ws), ws.numel(), _stream(dev)))
         P = int(total.value)
         if n_rows is not None:
@@ -186,13 +194,13 @@ def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers:
         if timers is not None:
             ev[2].record()
         if P > 0 and n_rows is None and index_map is None:
-            _lib.check(L.nl_fill_pairs(clist.params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
+            _lib.check(L.nl_fill_pairs(params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
                                        _ptr(i), _ptr(j), _ptr(S), _ptr(R), _ptr(ws), ws.numel(), _stream(dev)))
         elif P > 0:
             if index_map is not None:
                 index_map = index_map.to(device=dev, dtype=it).contiguous()
                 assert index_map.shape[0] == N
-            _lib.check(L.nl_fill_pairs_rows(clist.params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
+            _lib.check(L.nl_fill_pairs_rows(params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
                                             N if n_rows is None else n_rows, _ptr(index_map), _ptr(i), _ptr(j), _ptr(S), _ptr(R),
                                             _ptr(ws), ws.numel(), _stream(dev)))
         if n_rows is not None:
@@ -200,7 +208,7 @@ def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers:
         if timers is not None:
             ev[3].record()
             timers.setdefault("events", []).append(ev)
-    return PairList(X=clist.X_orig, C=clist.cell, cutoff=clist.cutoff, i=i, j=j, S=S, first=first, R=R, params=clist.params)
+    return PairList(X=clist.X_orig, C=clist.cell, cutoff=clist.cutoff, i=i, j=j, S=S, first=first, R=R, params=clist.params, half=half)
 
 
 def cell_ids(X, cutoff, cell, pbc, *, int_type=np.int32, device=None) -> torch.Tensor:
@@ -216,16 +224,17 @@ def cell_ids(X, cutoff, cell, pbc, *, int_type=np.int32, device=None) -> torch.T
     return out
 
 
-def neighbour_list(X, cutoff, cell=None, pbc=None, *, lazy: bool = False, int_type=np.int32, with_R: bool = False, device=None):
+def neighbour_list(X, cutoff, cell=None, pbc=None, *, lazy: bool = False, int_type=np.int32, with_R: bool = False, device=None,
+                   half: bool = False):
     """neighbour_list(X, cutoff, cell, pbc; lazy, int_type)  (src/cell_list.jl:897-916);
     neighbour_list(system, cutoff; lazy, int_type) for AtomsBase-style systems (atoms.py)."""
     if cell is None and pbc is None and hasattr(X, "positions"):
         from . import atoms
-        return atoms.neighbour_list(X, cutoff, lazy=lazy, int_type=int_type, with_R=with_R, device=device)
+        return atoms.neighbour_list(X, cutoff, lazy=lazy, int_type=int_type, with_R=with_R, device=device, half=half)
     clist = build_cell_list(X, cutoff, cell, pbc, int_type=int_type, device=device)
     if lazy:
         return clist
-    return materialize_pairlist(clist, with_R=with_R)
+    return materialize_pairlist(clist, with_R=with_R, half=half)
 
 
 # ------------------------------------------------------------------ accessors (src/cell_list.jl:25-27, 507-611, 753-833, 919-927)

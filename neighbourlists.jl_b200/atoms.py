@@ -108,10 +108,10 @@ def build_cell_list(system, cutoff, *, int_type=np.int32, device=None):
     return api.build_cell_list(X, rc, cell, pbc, int_type=int_type)
 
 
-def neighbour_list(system, cutoff, *, lazy: bool = False, int_type=np.int32, with_R: bool = False, device=None):
+def neighbour_list(system, cutoff, *, lazy: bool = False, int_type=np.int32, with_R: bool = False, device=None, half: bool = False):
     """neighbour_list(system, cutoff; lazy, int_type) (ext/NeighbourListsAtomsBaseExt.jl:116-138)."""
     clist = build_cell_list(system, cutoff, int_type=int_type, device=device)
-    return clist if lazy else api.materialize_pairlist(clist, with_R=with_R)
+    return clist if lazy else api.materialize_pairlist(clist, with_R=with_R, half=half)
 
 
 def pair_list(system, cutoff, *, int_type=np.int32, device=None):

@@ -548,6 +548,21 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : (CM == 
           }
           __syncwarp();
         }
+        if (WANT_MASK && a.out.half) {
+          // half list (half_keep): a candidate later than the whole home group in sorted order is kept for every home atom,
+          // an earlier one for none; candidates INSIDE the group (d = sorted distance to its first atom) are settled one by one
+          const int d = valid ? gj - (int)(hg0 + g0) : -1;
+          const int pos = ((shp & 3) > 1 || ((shp & 3) == 1 && (((shp >> 2) & 3) > 1 || (((shp >> 2) & 3) == 1 && ((shp >> 4) & 3) > 1)))) ? 1 : 0;
+          unsigned word = __ballot_sync(FULL, valid && d >= ng);
+          unsigned ingrp = __ballot_sync(FULL, valid && d >= 0 && d < ng);
+          while (ingrp) {
+            const int l = __ffs(ingrp) - 1;
+            ingrp &= ingrp - 1;
+            const int dl = __shfl_sync(FULL, d, l), pl = __shfl_sync(FULL, pos, l);
+            if (dl > lane || (dl == lane && pl)) word |= 1u << l;
+          }
+          if (lane < ng) mrow[lane] &= word;
+        }
         // drop the self pair (same atom, zero shift): flat index fh + g0 + aa of home atom aa; accumulate the counts
         if (CM == CM_LJF && valid && (lf0 != 0.f || lf1 != 0.f || lf2 != 0.f || lfe != 0.f)) {
           float* d = (float*)(sF + tab.cslot[f]);  // lanes hold distinct slots; other warps may hit the same slot

@@ -211,11 +211,13 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_tiled(const TiledArgs<T, TI> a) 
           T xj = 0, yj = 0, zj = 0, cs0 = 0, cs1 = 0, cs2 = 0;
           uint32_t wj = 0, jo = 0;
           long long sl0 = 0, sl1 = 0, sl2 = 0;
+          long long gsj = 0;  // global sorted index of the candidate (half lists)
           if (valid) {
             slot = r_start + (f - (r_incl - r_len));
             // x offset of the candidate's cell inside its row
             const int vrow = ((lz + rr / 3) * VY + (ly + rr % 3)) * VX + lx;
             const int dxi = (slot >= vstart[vrow + 1] ? 1 : 0) + (slot >= vstart[vrow + 2] ? 1 : 0);
+            gsj = (long long)vgs[vrow + dxi] + (slot - vstart[vrow + dxi]);
             int c, s;
             map_virtual(hx0 + lx + dxi - 1, g.nc[0], g.pbc[0], c, s); sl0 = s;
             map_virtual(hy0 + ly + rr % 3 - 1, g.nc[1], g.pbc[1], c, s); sl1 = s;
@@ -234,7 +236,9 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_tiled(const TiledArgs<T, TI> a) 
             bool hit = false;
             T R0 = 0, R1 = 0, R2 = 0;
             long long S0 = sl0, S1 = sl1, S2 = sl2;
-            if (valid && slot != hs) {  // slot == hs <=> same atom under zero shift (_is_self_interaction)
+            const bool dropped = (MODE == MODE_COUNT || MODE == MODE_FILL) && a.out.half &&
+                                 !half_keep((long long)vgs[vh] + g0 + aa, gsj, sl0, sl1, sl2);
+            if (valid && slot != hs && !dropped) {  // slot == hs <=> same atom under zero shift (_is_self_interaction)
               T r2;
               if (wi == wj && !(wi & WIND_OVERFLOW)) {
                 R0 = add_rn(sub_rn(xj, xi), cs0);

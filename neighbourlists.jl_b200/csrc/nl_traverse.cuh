@@ -34,6 +34,7 @@ template <class T, class TI> struct Sinks {
   const uint32_t* pgid0; //            with gmap: gmap[pidx[s]] - 1 per SORTED atom (one gather per atom instead of one per pair)
   double* energy;        // MODE_LJ: device scalar
   double lj_eps, lj_sigma2;
+  int half;              // MODE_COUNT / MODE_FILL of a materialisation: keep one pair of each mirror couple (see half_keep)
   T* fe;                 // MODE_LJF: N x 4 (force x, y, z, energy) per ORIGINAL atom, accumulated with atomics
 };
 
@@ -50,6 +51,16 @@ template <class T, class TI>
 __device__ __forceinline__ void ljf_add_global(const Sinks<T, TI>& out, uint32_t jo, T f0, T f1, T f2, T e) {
   T* d = out.fe + 4ll * jo;
   atomicAdd(d, f0); atomicAdd(d + 1, f1); atomicAdd(d + 2, f2); atomicAdd(d + 3, e);
+}
+
+// Half lists: of the mirror couple (i, j, S) / (j, i, -S) exactly one pair is kept -- the one whose SECOND atom comes
+// later in cell-sorted order, or, for self images (same atom), the one with a lexicographically positive shift.  The rule
+// only uses sorted indices and the shift, so every traversal route reaches the same verdict.
+__device__ __forceinline__ bool shift_lex_positive(long long s0, long long s1, long long s2) {
+  return s0 > 0 || (s0 == 0 && (s1 > 0 || (s1 == 0 && s2 > 0)));
+}
+__device__ __forceinline__ bool half_keep(long long sorted_i, long long sorted_j, long long s0, long long s1, long long s2) {
+  return sorted_j > sorted_i || (sorted_j == sorted_i && shift_lex_positive(s0, s1, s2));
 }
 
 template <class T, class TI> __device__ __forceinline__ TI out_index(const Sinks<T, TI>& out, uint32_t orig) {
@@ -130,6 +141,7 @@ __device__ __forceinline__ double generic_atom(long long s, const Records<T>& re
         for (long long t = b0; t < b1; t++) {
           const uint32_t jo = rec.pidx[t];
           if (jo == io && zero_shift) continue;  // _is_self_interaction, src/gpu_kernels.jl:30-33
+          if ((MODE == MODE_COUNT || MODE == MODE_FILL) && out.half && !half_keep(s, t, sx, sy, sz)) continue;
           const T xj = rec.px[t], yj = rec.py[t], zj = rec.pz[t];
           long long wj[3];
           const uint32_t pwj = rec.pw[t];

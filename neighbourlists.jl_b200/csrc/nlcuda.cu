@@ -50,6 +50,7 @@ int check_params(const nl_params* p, int64_t N) {
   }
   if (N >= 2147483647ll) return NL_ERR_UNSUPPORTED;
   if (!(p->cutoff > 0.0)) return NL_ERR_BAD_ARG;
+  if ((p->reserved[0] & ~NL_FLAG_HALF) || p->reserved[1] || p->reserved[2] || p->reserved[3] || p->reserved[4]) return NL_ERR_BAD_ARG;
   return NL_OK;
 }
 
@@ -334,6 +335,7 @@ int count_pairs_impl(const nl_params* p, const void* Xs, int64_t N, const void* 
     if (rc) return rc;
     Sinks<T, TI> sk = {};
     sk.counts = w.counts;
+    sk.half = p->reserved[0] & NL_FLAG_HALF;
     rc = traverse<T, TI, MODE_COUNT>(p, N, co, w, g, sk, true, st);
     if (rc) return rc;
     exclusive_scan<uint32_t, unsigned long long, TI>(w.counts, N, (TI*)first, 1ull, true, w.tsum, w.total, st);
@@ -358,6 +360,7 @@ int fill_pairs_impl(const nl_params* p, int64_t N, const void* co, const void* f
   sk.first = (const TI*)first;
   sk.io = (TI*)io; sk.jo = (TI*)jo; sk.So = (TI*)So; sk.Ro = (T*)Ro;
   sk.n_rows = n_rows; sk.gmap = (const TI*)gmap;
+  sk.half = p->reserved[0] & NL_FLAG_HALF;
   if (gmap && N > 0) {
     k_make_pgid<TI><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(w.pidx, (const TI*)gmap, N, w.pgid0);
     NL_LAUNCHED(1);

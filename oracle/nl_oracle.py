@@ -256,3 +256,25 @@ def lj_forces(d, eps, sigma, N):
     np.add.at(F, j0, gg[:, None] * R)
     np.add.at(e, j0, phi)
     return F, e
+
+
+def mirror_canonical(i, j, S):
+    """Canonical representative of each pair's mirror couple {(i, j, S), (j, i, -S)}: the lexicographically smaller
+    (i, j, S1, S2, S3) tuple.  Returns the sorted (P, 5) int64 array (duplicates kept)."""
+    a = np.concatenate([np.asarray(i, np.int64)[:, None], np.asarray(j, np.int64)[:, None], np.asarray(S, np.int64).reshape(-1, 3)], axis=1)
+    b = np.concatenate([a[:, 1:2], a[:, 0:1], -a[:, 2:]], axis=1)
+    swap = np.zeros(len(a), dtype=bool)
+    undecided = np.ones(len(a), dtype=bool)
+    for k in range(5):
+        lt, gt = undecided & (b[:, k] < a[:, k]), undecided & (b[:, k] > a[:, k])
+        swap |= lt
+        undecided &= ~(lt | gt)
+    c = np.where(swap[:, None], b, a)
+    return c[np.lexsort(c.T[::-1])]
+
+
+def half_list(d):
+    """The half list as a SET: one canonical representative per mirror couple of the full oracle list d."""
+    c = mirror_canonical(d["i"], d["j"], d["S"])
+    assert len(c) % 2 == 0 and np.array_equal(c[0::2], c[1::2]), "the full list consists of mirror couples"
+    return c[0::2]

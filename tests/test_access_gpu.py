@@ -221,3 +221,51 @@ def test_lj_forces_fallback_routes(nl, dtype):
     rng = np.random.default_rng(4)
     X[:700] = (X[0] + rng.uniform(0, 4.0, size=(700, 3))).astype(dtype)
     _check_lj_forces(nl, X, C, (True, True, False), 4.0, dtype, sig=0.6)
+
+
+def _check_half(nl, X, C, pbc, rc, dtype, int_type=np.int32):
+    import torch
+    Xd = torch.from_numpy(X).cuda()
+    full = O.sortbased(X, rc, C, pbc, dtype=dtype)
+    want = O.half_list(full)
+    pl = nl.neighbour_list(Xd, rc, C, pbc, half=True, with_R=True, int_type=int_type)
+    h = pl.cpu()
+    assert pl.half and nl.npairs(pl) * 2 == len(full["i"])
+    got = O.mirror_canonical(h["i"], h["j"], h["S"])
+    assert np.array_equal(got, want), "half list == one representative of every mirror couple of the reference's list"
+    # rows are still CSR rows of i in original order, and R follows the contract for the stored orientation
+    f = h["first"].astype(np.int64)
+    assert f[0] == 1 and f[-1] - 1 == len(h["i"]) and np.array_equal(h["i"].astype(np.int64), np.repeat(np.arange(1, len(f)), np.diff(f)))
+    assert np.array_equal(h["R"], O.pairs_R(X, h["i"], h["j"], h["S"], C, dtype))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_half_list_fast_route(nl, dtype):
+    X, C, L = U.rand_config(30000, seed=91, dtype=dtype)
+    _check_half(nl, X, C, (True, True, True), 5.0, dtype)
+    Ct = (U.TRICLINIC * 3.0).astype(dtype)
+    pbc = (True, True, False)
+    Xt = U.displace_by_lattice(U.rand_in_cell(9000, Ct, seed=92, dtype=dtype), Ct, pbc)
+    _check_half(nl, Xt, Ct, pbc, 3.0, dtype, int_type=np.int64)
+    # cells with more than 32 atoms: several home groups per cell
+    X, C, L = U.rand_config(20000, seed=93, dtype=dtype, density=0.25)
+    _check_half(nl, X, C, (True, False, True), 5.0, dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_half_list_other_routes(nl, dtype):
+    # self images and repeated cells (2 cells per axis: the same real cell under several shifts), 1-cell box (generic route),
+    # dense cluster (cells beyond the mask capacity -> generic per-cell route mixed with the fast one)
+    X, C = U.fcc(3.61, (4, 4, 4), dtype=dtype)
+    _check_half(nl, X, C, (True, True, True), 5.0, dtype)
+    X, C = U.fcc(3.61, (2, 2, 2), dtype=dtype)
+    _check_half(nl, X, C, (True, True, True), 5.0, dtype)
+    X, C = U.fcc(3.61, (1, 1, 1), dtype=dtype)
+    _check_half(nl, X, C, (True, True, True), 4.0, dtype)
+    X, C, L = U.rand_config(6000, seed=94, dtype=dtype)
+    rng = np.random.default_rng(4)
+    X[:700] = (X[0] + rng.uniform(0, 4.0, size=(700, 3))).astype(dtype)
+    _check_half(nl, X, C, (True, True, False), 4.0, dtype)
+    # density beyond the mask path altogether (27 * dens > 200): exact tiled route
+    X, C, L = U.rand_config(40000, seed=95, dtype=dtype, density=0.08)
+    _check_half(nl, X, C, (True, True, True), 5.0, dtype)
