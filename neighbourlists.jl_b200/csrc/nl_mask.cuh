@@ -68,6 +68,7 @@ template <class T, class TI> struct MaskArgs {
   uint8_t* cellflag;  // per cell: 1 if the count pass stored masks for its atoms
   int tx, ty, tz, ntx, nty, ntz;
   float mid, hw, dguard;
+  const void* srow;   // fill pass: row start per sorted atom (k_row_starts)
   const MaskArgs<T, TI>* self;  // this struct in GLOBAL memory: the rare out-of-line paths read their inputs from there, so the
                                 // kernels never copy their parameters onto the local-memory stack (measured: that copy cost
                                 // 77 KB of local stores per CTA, 9 GB per launch on a slab of an 8x larger global grid)
@@ -629,6 +630,18 @@ static_assert(FILL_WARP_BYTES % 16 == 0 && FILL_FIXED_BYTES % 16 == 0, "alignmen
 #ifndef NL_FILL_MINB
 #define NL_FILL_MINB 2
 #endif
+template <class TI> struct FillBase { typedef typename std::conditional<sizeof(TI) == 4, uint32_t, unsigned long long>::type type; };
+
+// 0-based start of the row of every SORTED atom (all ones: the atom gets no row -- halo atoms of a shard).
+template <class T, class TI>
+__global__ void __launch_bounds__(256) k_row_starts(const uint32_t* __restrict__ pidx, const TI* __restrict__ first, long long n, long long n_rows,
+                                                    typename FillBase<TI>::type* __restrict__ srow) {
+  typedef typename FillBase<TI>::type BaseT;
+  const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const uint32_t io = pidx[s];
+  srow[s] = (long long)io < n_rows ? (BaseT)(first[io] - 1) : ~(BaseT)0;
+}
 template <class T, class TI>
 __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskArgs<T, TI> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -644,7 +657,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
   uint32_t* sidx = (uint32_t*)(sz + CAP);
   uint32_t* sw = sidx + CAP;
   uint32_t* sgid = sw + CAP;  // shard mode: global index - 1 of each staged atom
-  typedef typename std::conditional<sizeof(TI) == 4, uint32_t, unsigned long long>::type BaseT;
+  typedef typename FillBase<TI>::type BaseT;
   BaseT* sbase = (BaseT*)(sgid + CAP);  // home slots: 0-based start of the atom's row (all ones: no row); gathered once per tile
   __shared__ int scan_sm[33];
   __shared__ int s_next;
@@ -698,13 +711,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
     sidx[sl] = a.rec.pidx[src];
     sw[sl] = a.rec.pw[src];
     if (a.out.pgid0) sgid[sl] = a.out.pgid0[src];
-    {  // row starts of the HOME atoms (interior virtual cells): one random gather per atom, all in flight together here
-      const int vx = v % VX, vy = (v / VX) % VY, vz = v / (VX * VY);
-      if (vx >= 1 && vx <= VX - 2 && vy >= 1 && vy <= VY - 2 && vz >= 1 && vz <= VZ - 2) {
-        const uint32_t io = sidx[sl];
-        sbase[sl] = (long long)io < a.out.n_rows ? (BaseT)(a.out.first[io] - 1) : ~(BaseT)0;
-      }
-    }
+    sbase[sl] = ((const BaseT*)a.srow)[src];  // row start (k_row_starts): coalesced, like the rest of the record
   }
   if (tid < nhome) {  // per-cell "masks valid" flags, fetched once per tile
     const int lx = hcell[tid] & 255, ly = (hcell[tid] >> 8) & 255, lz = (hcell[tid] >> 16) & 255;
@@ -727,6 +734,10 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
       generic_cell<T, TI, MODE_FILL>(a.self, hg0, nh, lane);
       continue;
     }
+    // mask words of the first two passes (lane = 8 * atom + word): issued before the table building so that it hides them
+    uint32_t nx_word = 0, nx2_word = 0;
+    if (grp < nh && sbase[hstart + grp] != ~(BaseT)0) nx_word = a.masks[(hg0 + grp) * MASK_WORDS + sub];
+    if (4 + grp < nh && sbase[hstart + 4 + grp] != ~(BaseT)0) nx2_word = a.masks[(hg0 + 4 + grp) * MASK_WORDS + sub];
     build_cell_tables<true>(vstart, VX, VY, lx, ly, lz, lane, tab);
     // lane c < 27: packed periodic shift of stencil cell c and its shift vector cs = cell' * s_loop (contract arithmetic)
     int my_shp = 0;
@@ -739,9 +750,6 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
     }
     __syncwarp();
 
-    // prefetch of the first pass (mask words only: row starts and indices are already in shared memory)
-    uint32_t nx_word = 0;
-    if (grp < nh && sbase[hstart + grp] != ~(BaseT)0) nx_word = a.masks[(hg0 + grp) * MASK_WORDS + sub];
 
     for (int a0 = 0; a0 < nh; a0 += 4) {
       // ---- four atoms at once: lane = 8 * atom + mask word
@@ -752,9 +760,10 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
         my_io = sidx[hstart + a0 + grp];
         my_base = (long long)sbase[hstart + a0 + grp];   // all ones (no row) comes with word == 0
       }
-      nx_word = 0;
-      if (a0 + 4 + grp < nh && sbase[hstart + a0 + 4 + grp] != ~(BaseT)0)  // next pass in flight while this one is expanded
-        nx_word = a.masks[(hg0 + a0 + 4 + grp) * MASK_WORDS + sub];
+      nx_word = nx2_word;
+      nx2_word = 0;
+      if (a0 + 8 + grp < nh && sbase[hstart + a0 + 8 + grp] != ~(BaseT)0)  // two passes ahead
+        nx2_word = a.masks[(hg0 + a0 + 8 + grp) * MASK_WORDS + sub];
       const int pc = __popc(word);
       int incl = pc;
 #pragma unroll
@@ -840,7 +849,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
 template <class T, class TI>
 inline void mask_args(MaskArgs<T, TI>& a, int64_t n, const TI* co, const Records<T>& rec, const Geo<T>& g, const Sinks<T, TI>& sk,
                       const TileShape& ts, uint32_t* masks) {
-  a.rec = rec; a.co = co; a.n = n; a.g = g; a.out = sk; a.masks = masks; a.cellflag = nullptr; a.self = nullptr;
+  a.rec = rec; a.co = co; a.n = n; a.g = g; a.out = sk; a.masks = masks; a.cellflag = nullptr; a.self = nullptr; a.srow = nullptr;
   a.tx = ts.tx; a.ty = ts.ty; a.tz = ts.tz;
   a.ntx = (g.nc[0] + ts.tx - 1) / ts.tx; a.nty = (g.nc[1] + ts.ty - 1) / ts.ty; a.ntz = (g.nc[2] + ts.tz - 1) / ts.tz;
   a.mid = a.hw = a.dguard = 0.f;

@@ -308,11 +308,13 @@ __global__ void __launch_bounds__(TILE_NT, 3) k_tiled(const TiledArgs<T, TI> a) 
 template <class T, class TI, int MODE>
 inline int tiled_traverse(const nl_params*, int64_t n, const TI* co, const Records<T>& rec, const Geo<T>& g, const Sinks<T, TI>& sk,
                           const TileShape& ts, void*, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};  // per device: the attribute belongs to the device's instance of the kernel
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return NL_ERR_CUDA;
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(k_tiled<T, TI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES);
     if (e != cudaSuccess) return NL_ERR_CUDA;
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   TiledArgs<T, TI> a;
   a.rec = rec; a.co = co; a.n = n; a.g = g; a.out = sk;

@@ -98,6 +98,7 @@ struct PairWs {
   void *px, *py, *pz;
   uint32_t *pidx, *pw, *counts, *pgid0, *pkey, *sorted_of;
   void* ra;
+  void* srow;  // fill pass: 0-based row start of every SORTED atom (all ones: no row), TI-wide
   unsigned long long* tsum;
   unsigned long long* total;
   void* tiled;  // tiled-kernel scratch (tile table, hit masks)
@@ -120,6 +121,7 @@ PairWs pair_ws(void* ws, const nl_params* prm, int64_t N) {
   w.pkey = (uint32_t*)take(n1 * 4);
   w.sorted_of = (uint32_t*)take(n1 * 4);
   w.ra = take(n1 * 32);
+  w.srow = take(n1 * 8);
   w.tsum = (unsigned long long*)take((size_t)(scan_tiles((long long)n1) + 1) * 8);
   w.total = (unsigned long long*)take(256);
   w.tiled = take(tiled_scratch_bytes(prm, N));
@@ -231,11 +233,17 @@ inline bool fill_tiled_requested() {
   return v == 1;
 }
 
-template <class F> int set_smem_once(F* fn, int bytes, bool& done) {
-  if (!done) {
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+// Opt-in to > 48 KB of dynamic shared memory.  The attribute is per DEVICE, so the "done" flags are per device too
+// (one process may drive several GPUs); a benign race at worst sets it twice.
+struct SmemOnce { bool done[64] = {}; };
+template <class F> int set_smem_once(F* fn, int bytes, SmemOnce& once) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return cuda_fail(e);
+  if (dev < 0 || dev >= 64 || !once.done[dev]) {
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return cuda_fail(e);
-    done = true;
+    if (dev >= 0 && dev < 64) once.done[dev] = true;
   }
   return NL_OK;
 }
@@ -267,7 +275,7 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
     NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
     const unsigned nblk = (unsigned)((long long)a.ntx * a.nty * a.ntz);
     if constexpr (CM == CM_COUNT || LJ_FAST || LJF_FAST) {
-      static bool done = false;
+      static SmemOnce done;
       int rc = set_smem_once(k_count_mask<T, TI, CM>, cm_smem_bytes(CM), done);
       if (rc) return rc;
       k_count_mask<T, TI, CM><<<nblk, TILE_NT, cm_smem_bytes(CM), st>>>(a);
@@ -299,14 +307,19 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
       NL_LAUNCH_CHECK();
       return NL_OK;
     } else if (MODE == MODE_FILL) {
-      static bool done = false;
+      static SmemOnce done;
       int rc = set_smem_once(k_fill_mask<T, TI>, FILL_SMEM_BYTES, done);
       if (rc) return rc;
+      // row starts in SORTED order: the N random gathers of first[] run here at full memory-level parallelism instead of
+      // inside the (low-occupancy) fill kernel's staging loop
+      a.srow = w.srow;
+      k_row_starts<T, TI><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(w.pidx, sk.first, N, sk.n_rows, (typename FillBase<TI>::type*)w.srow);
+      NL_LAUNCHED(1);
       NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
       k_fill_mask<T, TI><<<nblk, TILE_NT, FILL_SMEM_BYTES, st>>>(a);
     } else {
       // MODE_COUNT: with masks for the fill pass, or (lazy count on a problem the lazy plan rejected) without
-      static bool done = false;
+      static SmemOnce done;
       int rc = set_smem_once(k_count_mask<T, TI, CM_MASK>, cm_smem_bytes(CM_MASK), done);
       if (rc) return rc;
       NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
