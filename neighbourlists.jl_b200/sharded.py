@@ -151,29 +151,34 @@ def neighbour_list_sharded(X_local, gidx_local, cutoff, cell, pbc, *, group=None
     if world > 1:
         dist.all_reduce(hist, group=group)
     ph.mark("bin+hist")
-    plan = plan_slabs(hist.cpu().numpy(), world, halo, bool(geo.pbc[axis]), axis)
+    hist_host = hist.cpu().numpy()
+    plan = plan_slabs(hist_host, world, halo, bool(geo.pbc[axis]), axis)
     ph.mark("plan")
     bounds_t = torch.as_tensor(plan.bounds, device=dev)
 
     # ---- step 0: all-to-all-v to the owners
     if world > 1 and redistribute:
         owner = torch.bucketize(planes, bounds_t[1:], right=True)
-        # atoms already on their owner stay put; only the leavers are sorted by destination and exchanged
         stay = owner == rank
-        leave = (~stay).nonzero().flatten()
-        lo_owner = owner[leave]
-        order = leave[torch.argsort(lo_owner, stable=True)]
-        send_counts = torch.bincount(lo_owner, minlength=world).long()
-        recv_counts = torch.empty_like(send_counts)
-        dist.all_to_all_single(recv_counts, send_counts, group=group)
-        sc, rc = send_counts.cpu().tolist(), recv_counts.cpu().tolist()
-        # the exchanges are collective: every rank takes part even with nothing to send or receive
-        rX, rg, rp = _a2a(X[order], sc, rc, group), _a2a(gidx[order], sc, rc, group), _a2a(planes[order], sc, rc, group)
-        if leave.numel() > 0:                          # compact only if something left; one index for the three arrays
-            keep = stay.nonzero().flatten()
-            X, gidx, planes = X.index_select(0, keep), gidx.index_select(0, keep), planes.index_select(0, keep)
-        if rX.shape[0] > 0:
-            X, gidx, planes = torch.cat([X, rX]), torch.cat([gidx, rg]), torch.cat([planes, rp])
+        # one small all-reduce decides whether ANY rank has atoms to move (spatially pre-distributed inputs: none)
+        n_leave = (~stay).sum().reshape(1)
+        dist.all_reduce(n_leave, group=group)
+        if int(n_leave.item()) > 0:
+            # atoms already on their owner stay put; only the leavers are sorted by destination and exchanged
+            leave = (~stay).nonzero().flatten()
+            lo_owner = owner[leave]
+            order = leave[torch.argsort(lo_owner, stable=True)]
+            send_counts = torch.bincount(lo_owner, minlength=world).long()
+            recv_counts = torch.empty_like(send_counts)
+            dist.all_to_all_single(recv_counts, send_counts, group=group)
+            sc, rc = send_counts.cpu().tolist(), recv_counts.cpu().tolist()
+            # the exchanges are collective: every rank takes part even with nothing to send or receive
+            rX, rg, rp = _a2a(X[order], sc, rc, group), _a2a(gidx[order], sc, rc, group), _a2a(planes[order], sc, rc, group)
+            if leave.numel() > 0:                          # compact only if something left; one index for the three arrays
+                keep = stay.nonzero().flatten()
+                X, gidx, planes = X.index_select(0, keep), gidx.index_select(0, keep), planes.index_select(0, keep)
+            if rX.shape[0] > 0:
+                X, gidx, planes = torch.cat([X, rX]), torch.cat([gidx, rg]), torch.cat([planes, rp])
     n_owned = int(X.shape[0])
     ph.mark("redistribute")
 
@@ -188,11 +193,16 @@ def neighbour_list_sharded(X_local, gidx_local, cutoff, cell, pbc, *, group=None
         has_up, has_dn = 0 <= up_peer < world, 0 <= dn_peer < world
         sel_up = (planes >= hi - halo).nonzero().flatten() if has_up else planes.new_zeros(0)
         sel_dn = (planes < lo + halo).nonzero().flatten() if has_dn else planes.new_zeros(0)
-        # sizes first (tiny all-gather), then the payloads as point-to-point messages
-        mine = torch.tensor([sel_up.numel(), sel_dn.numel()], dtype=torch.long, device=dev)
-        sizes = [torch.empty_like(mine) for _ in range(world)]
-        dist.all_gather(sizes, mine, group=group)
-        sizes = [s.cpu().tolist() for s in sizes]
+        # Message sizes need no exchange: after step 0 every rank holds exactly the atoms of its planes, so the number of
+        # atoms in any rank's boundary planes follows from the all-reduced plane histogram every rank already has.
+        hist_h = hist_host
+        def n_top(r):
+            return int(hist_h[int(plan.bounds[r + 1]) - halo:int(plan.bounds[r + 1])].sum())
+        def n_bottom(r):
+            return int(hist_h[int(plan.bounds[r]):int(plan.bounds[r]) + halo].sum())
+        sizes = [[n_top(r), n_bottom(r)] for r in range(world)]
+        if sel_up.numel() != (sizes[rank][0] if has_up else 0) or sel_dn.numel() != (sizes[rank][1] if has_dn else 0):
+            raise ValueError("atoms are not in this rank's slab (redistribute=False with misplaced atoms?)")
         # Message order matters when both neighbours are the same rank (G = 2, periodic): every rank sends
         # [up, down] and receives [from below, from above], so the k-th send to a peer meets its k-th receive.
         sends, recvs, keep = [], [], []

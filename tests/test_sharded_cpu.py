@@ -41,12 +41,29 @@ def _worker(rank, world, port, case, outdir):
     import neighbourlists_jl_b200  # noqa: F401
     from importlib import import_module
     sh = import_module("neighbourlists_jl_b200.sharded")
-    X, cell, pbc, cutoff = case
+    X, cell, pbc, cutoff = case[:4]
+    mode = case[4] if len(case) > 4 else "by_index"
     N = X.shape[0]
-    # block distribution BY INDEX (not by space): rank r starts with atoms r::world
-    mine = np.arange(rank, N, world)
-    res = sh.neighbour_list_sharded(torch.from_numpy(X[mine]), torch.from_numpy(mine + 1), cutoff, cell, pbc, engine=OracleEngine(),
-                                    with_R=True)
+    if mode == "by_index":
+        # block distribution BY INDEX (not by space): rank r starts with atoms r::world
+        mine = np.arange(rank, N, world)
+        kw = {}
+    else:
+        # spatially pre-distributed: equal-width z slabs of the box (nothing has to move if the plan agrees);
+        # "placed" additionally promises it (redistribute=False), "misplaced" breaks the promise on rank 0
+        z = X[:, 2] / cell[2, 2]
+        slab = np.minimum((z * world).astype(int), world - 1)
+        if mode == "misplaced":
+            slab = (slab + 1) % world
+        mine = np.flatnonzero(slab == rank)
+        kw = {} if mode == "prespatial" else dict(redistribute=False)
+    try:
+        res = sh.neighbour_list_sharded(torch.from_numpy(X[mine]), torch.from_numpy(mine + 1), cutoff, cell, pbc, engine=OracleEngine(),
+                                        with_R=True, **kw)
+    except ValueError as e:
+        open(os.path.join(outdir, f"r{rank}.err"), "w").write(str(e))
+        dist.destroy_process_group()
+        return
     np.savez(os.path.join(outdir, f"r{rank}.npz"), owned=res.owned_index.numpy(), first=res.first.numpy(), i=res.i.numpy(),
              j=res.j.numpy(), S=res.S.numpy(), R=res.R.numpy(), bounds=res.plan.bounds, axis=res.plan.axis, n_halo=res.n_halo)
     dist.destroy_process_group()
@@ -119,3 +136,24 @@ def test_plan_rejects_too_many_ranks():
         sh.plan_slabs(np.ones(5, np.int64), 2, 1, True, 0)
     p = sh.plan_slabs(np.ones(6, np.int64), 2, 1, True, 0)
     assert p.bounds.tolist() == [0, 3, 6]
+
+
+def test_pre_distributed_inputs_skip_the_redistribution():
+    # a uniform grid of atoms: 24 z planes of 3 A, 2 equal slabs = the balanced plan, so no atom has to move
+    cell = np.diag([9.0, 9.0, 72.0])
+    g = np.stack(np.meshgrid(np.arange(6) * 1.5 + 0.3, np.arange(6) * 1.5 + 0.4, np.arange(48) * 1.5 + 0.2, indexing="ij"), -1).reshape(-1, 3)
+    for mode in ("prespatial", "placed"):
+        parts = _run(2, (g, cell, (True, True, True), 3.0, mode))
+        orc = O.sortbased(g, 3.0, cell, (True, True, True))
+        assert parts[0]["bounds"].tolist() == [0, 12, 24]
+        merged = dict(i=np.concatenate([p["i"] for p in parts]), j=np.concatenate([p["j"] for p in parts]), S=np.concatenate([p["S"] for p in parts]))
+        U.assert_same_pairs(merged, orc, mode)
+
+
+def test_misplaced_atoms_without_redistribution_are_an_error():
+    cell = np.diag([9.0, 9.0, 72.0])
+    X = U.rand_in_cell(800, cell, seed=9)
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker, args=(2, _free_port(), (X, cell, (True, True, True), 3.0, "misplaced"), d), nprocs=2, join=True)
+        errs = [f for f in os.listdir(d) if f.endswith(".err")]
+        assert len(errs) == 2 and "not in this rank's slab" in open(os.path.join(d, errs[0])).read()
