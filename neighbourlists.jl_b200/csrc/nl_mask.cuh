@@ -209,7 +209,7 @@ constexpr int CELLTAB_BYTES = MASK_MAXCAND * 3;
 // Builds the tables for home cell (lx, ly, lz) of the tile; returns the number of candidates
 // (tables are valid only if it is <= MASK_MAXCAND).  Lane c < 27 owns neighbour cell
 // c = (dz+1)*9 + (dy+1)*3 + (dx+1); flat order = cell order, then sorted order inside the cell.
-template <bool STORE_STENCIL_INDEX>
+template <bool STORE_STENCIL_INDEX, bool STORE_CV = true>
 __device__ __forceinline__ int build_cell_tables(const int* vstart, int VX, int VY, int lx, int ly, int lz, int lane, const CellTables& t,
                                                  int cap = MASK_MAXCAND) {
   int v = 0, st = 0, cn = 0;
@@ -224,7 +224,10 @@ __device__ __forceinline__ int build_cell_tables(const int* vstart, int VX, int 
     const int pre = incl - cn;
     const int mx = __reduce_max_sync(FULL, cn);
     for (int j = 0; j < mx; j++)
-      if (j < cn) { t.cslot[pre + j] = (uint16_t)(st + j); t.cv[pre + j] = (uint8_t)(STORE_STENCIL_INDEX ? lane : v); }
+      if (j < cn) {
+        t.cslot[pre + j] = (uint16_t)(st + j);
+        if (STORE_CV) t.cv[pre + j] = (uint8_t)(STORE_STENCIL_INDEX ? lane : v);
+      }
   }
   __syncwarp();
   return ncand;
@@ -275,6 +278,9 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : (CM == 
   constexpr int CAPSLOTS = cm_cap(CM);
   static_assert((CM != CM_LJ && CM != CM_LJF) || sizeof(T) == 4, "the fused LJ sinks of this kernel are Float32 only");
   constexpr bool LJ_ANY = CM == CM_LJ || CM == CM_LJF;
+  // Hit words of a chunk: CM_MASK keeps them in the shared-memory rows it has to write out anyway (measured 2.75 vs 2.79 ms);
+  // CM_COUNT needs no rows at all and keeps them in registers (lazy count 3.64 -> 3.39 ms at C5)
+  constexpr bool REGW = CM == CM_COUNT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   int* vstart = (int*)smem_raw;
   int* vgs = vstart + TILE_VPAD;
@@ -379,7 +385,9 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : (CM == 
     const int hstart = vstart[vh], nh = vstart[vh + 1] - hstart;
     if (nh == 0) continue;
     const long long hg0 = vgs[vh];
-    const int ncand = build_cell_tables<false>(vstart, VX, VY, lx, ly, lz, lane, tab, TABCAP);
+    const bool need_gj = (sizeof(T) == 8) && WANT_MASK && a.out.half;  // half lists compare global sorted indices per candidate
+    const int ncand = need_gj ? build_cell_tables<false, true>(vstart, VX, VY, lx, ly, lz, lane, tab, TABCAP)
+                              : build_cell_tables<false, sizeof(T) == 4>(vstart, VX, VY, lx, ly, lz, lane, tab, TABCAP);
     if (WANT_MASK && lane == 0) a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)] = ncand <= TABCAP ? 1 : 0;
     if (ncand > TABCAP) {  // too many candidates for the tables / the 256-bit masks: generic route (the fill pass does the same)
       e_acc += generic_cell<T, TI, GMODE>(a.self, hg0, nh, lane);
@@ -430,14 +438,15 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : (CM == 
         float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f;
         bool cand_bad = false;
         if (valid) {
-          const int slot = tab.cslot[f], v = tab.cv[f];
-          gj = vgs[v] + (slot - vstart[v]);
-          shp = vsh[v];
+          const int slot = tab.cslot[f];
           const float4 q = sq[slot];
           qx = q.x; qy = q.y; qz = q.z;
           if constexpr (sizeof(T) == 8) {
-            cand_bad = q.w != 0.f;
+            cand_bad = q.w != 0.f;  // the candidate's virtual cell (global index, shift) is only looked up on the rare paths below
           } else {
+            const int v = tab.cv[f];
+            gj = vgs[v] + (slot - vstart[v]);
+            shp = vsh[v];
             const uint32_t wj = __float_as_uint(q.w);
             cand_bad = (wj & WIND_OVERFLOW) != 0;
             long long s[3], w0[3], w1[3];
@@ -450,6 +459,7 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : (CM == 
         float lf0 = 0.f, lf1 = 0.f, lf2 = 0.f, lfe = 0.f;  // CM_LJF: what this group's home atoms do to the lane's candidate
         float bmin = 3.0e38f;  // min |t| over this lane's pairs: <= hw means some pair fell in the uncertainty band
         uint32_t* mrow = mkT + (kc & (MASK_WORDS - 1)) * 34;
+        uint32_t myw = 0;  // REGW: lane aa keeps the hit word of home atom aa for this chunk in a register
         const int self_aa = valid ? (int)tab.cslot[f] - (hstart + g0) : -1;  // the home atom this candidate IS under zero shift (CM_LJ)
 
         if constexpr (sizeof(T) == 8) {
@@ -467,7 +477,8 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : (CM == 
             bmin = fminf(bmin, fminf(fabsf(t.x), fabsf(t.y)));
             const unsigned b0 = __ballot_sync(FULL, t.x < -hw);
             const unsigned b1 = __ballot_sync(FULL, t.y < -hw);
-            *(uint2*)(mrow + 2 * pr) = make_uint2(b0, b1);  // every lane stores the same words: no branch
+            if constexpr (REGW) myw = (lane >> 1) == pr ? ((lane & 1) ? b1 : b0) : myw;
+            else *(uint2*)(mrow + 2 * pr) = make_uint2(b0, b1);  // every lane stores the same words: no branch
           }
         } else {
           const float2 qx2 = make_float2(qx, qx), qy2 = make_float2(qy, qy), qz2 = make_float2(qz, qz);
@@ -505,13 +516,22 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : (CM == 
             } else {
               const unsigned b0 = __ballot_sync(FULL, valid && r2x < csqf);
               const unsigned b1 = __ballot_sync(FULL, valid && r2y < csqf);
-              *(uint2*)(mrow + 2 * pr) = make_uint2(b0, b1);
+              if constexpr (REGW) myw = (lane >> 1) == pr ? ((lane & 1) ? b1 : b0) : myw;
+            else *(uint2*)(mrow + 2 * pr) = make_uint2(b0, b1);  // every lane stores the same words: no branch
             }
           }
         }
         __syncwarp();
         // ---- rare: redo this chunk with the exact contract wherever the fast loop cannot be trusted
-        if (__any_sync(FULL, bmin <= hw || cand_bad) || hbad != 0 || slow_group) {
+        const bool rare = __any_sync(FULL, bmin <= hw || cand_bad) || hbad != 0 || slow_group;
+        if constexpr (sizeof(T) == 8) {
+          if ((rare || need_gj) && valid) {
+            const int slot = tab.cslot[f], v = need_gj ? (int)tab.cv[f] : find_vcell(vstart, NV, slot);
+            gj = vgs[v] + (slot - vstart[v]);
+            shp = vsh[v];
+          }
+        }
+        if (rare) {
           for (int aa = 0; aa < ng; aa++) {
             bool hit;
             if constexpr (sizeof(T) == 8) {
@@ -544,7 +564,7 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : (CM == 
             }
             if (!LJ_ANY) {
               const unsigned bal = __ballot_sync(FULL, hit);
-              if (lane == 0) mrow[aa] = bal;
+              if (REGW) { if (lane == aa) myw = bal; } else if (lane == 0) mrow[aa] = bal;
             }
           }
           __syncwarp();
@@ -562,17 +582,23 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : (CM == 
             const int dl = __shfl_sync(FULL, d, l), pl = __shfl_sync(FULL, pos, l);
             if (dl > lane || (dl == lane && pl)) word |= 1u << l;
           }
-          if (lane < ng) mrow[lane] &= word;
+          if (REGW) myw &= word; else if (lane < ng) mrow[lane] &= word;
         }
         // drop the self pair (same atom, zero shift): flat index fh + g0 + aa of home atom aa; accumulate the counts
         if (CM == CM_LJF && valid && (lf0 != 0.f || lf1 != 0.f || lf2 != 0.f || lfe != 0.f)) {
           float* d = (float*)(sF + tab.cslot[f]);  // lanes hold distinct slots; other warps may hit the same slot
           atomicAdd(d, lf0); atomicAdd(d + 1, lf1); atomicAdd(d + 2, lf2); atomicAdd(d + 3, lfe);
         }
-        if (!LJ_ANY && lane < ng) {
+        if (!LJ_ANY) {
           const int fs = fh + g0 + lane;
-          if ((fs >> 5) == kc) mrow[lane] &= ~(1u << (fs & 31));
-          cnt_acc += __popc(mrow[lane]);
+          if constexpr (REGW) {
+            if ((fs >> 5) == kc) myw &= ~(1u << (fs & 31));
+            if (lane >= ng) myw = 0;  // padding lanes (odd group sizes leave a phantom second atom in the last pair)
+            cnt_acc += __popc(myw);
+          } else if (lane < ng) {
+            if ((fs >> 5) == kc) mrow[lane] &= ~(1u << (fs & 31));
+            cnt_acc += __popc(mrow[lane]);
+          }
         }
         if (CM != CM_MASK) __syncwarp();  // the mask rows are a ring of MASK_WORDS chunks
       }
