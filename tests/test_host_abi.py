@@ -56,6 +56,15 @@ def test_params_layout_and_validation():
     assert L.nl_build_cells(big, ptr, 10, ptr, ptr, ptr, ptr, ptr, 64, None) == nl._lib.NL_ERR_UNSUPPORTED
     with pytest.raises(nl.NlError):
         nl._lib.check(nl._lib.NL_ERR_OVERFLOW)
+    # reserved bytes: only the documented flag bits are accepted
+    flg = nl._lib.make_params(geo, np.float64, np.int32)
+    flg.reserved[0] = nl._lib.NL_FLAG_HALF
+    assert L.nl_workspace_bytes(flg, 10, nl._lib.NL_STAGE_PAIRS) > 0
+    flg.reserved[0] = 2
+    assert L.nl_workspace_bytes(flg, 10, nl._lib.NL_STAGE_PAIRS) == 0
+    flg.reserved[0] = 0
+    flg.reserved[3] = 1
+    assert L.nl_build_cells(flg, ptr, 10, ptr, ptr, ptr, ptr, ptr, 64, None) == nl._lib.NL_ERR_BAD_ARG
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
