@@ -183,6 +183,14 @@ NL_API int nl_rows_padded(const nl_params* params, const void* X, int64_t N, con
                           const void* S, const void* rows, int64_t n_sel, int32_t width, void* n_out, void* j_out,
                           void* S_out, void* R_out, void* stream);
 
+/* neighbours(clist, i) for a set of atoms straight from the cell list (src/cell_list.jl:821-833 over for_each_neighbour,
+ * :779-801): no pair list is materialised.  X_orig = clist.X_orig (the caller's order), X_sorted / perm / cell_offsets the
+ * other SortedCellList fields; atoms = n_sel TI (1-based).  Rows come out in the reference's own traversal order (dz, dy, dx,
+ * then sorted slot).  Outputs exactly as nl_rows_padded (n_out = full count, blocks truncated to `width`, zero padding).   */
+NL_API int nl_lazy_neighbours(const nl_params* params, const void* X_orig, const void* X_sorted, int64_t N, const void* perm,
+                              const void* cell_offsets, const void* atoms, int64_t n_sel, int32_t width, void* n_out,
+                              void* j_out, void* S_out, void* R_out, void* stream);
+
 /* Scratch for the two reductions below (256-byte aligned device memory). */
 #define NL_REDUCE_WS_BYTES 32768
 

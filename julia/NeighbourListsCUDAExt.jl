@@ -153,6 +153,18 @@ function sites_padded(nl::DevPairList{T,TI}, rows::CuVector{TI}, width::Integer 
     return n, j, R, S
 end
 
+"neighbours(clist, i) for many atoms at once, straight from the cell list (nothing is materialised)"
+function neighbours_padded(clist::SortedCellList{T,TI,<:CuVector}, atoms::CuVector{TI}, width::Integer) where {T,TI}
+    ns = length(atoms); p = _params(clist.cell, clist.inv_cell, clist.pbc, clist.cutoff, clist.ncells)
+    n = CuVector{TI}(undef, ns); j = CuMatrix{TI}(undef, width, ns)
+    S = CuMatrix{SVec{TI}}(undef, width, ns); R = CuMatrix{SVec{T}}(undef, width, ns)
+    _check(ccall((:nl_lazy_neighbours, libnlcuda), Cint,
+                 (Ref{NlParams}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, Int32,
+                  CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{Cvoid}),
+                 p, clist.X_orig, clist.X, length(clist.X), clist.perm, clist.cell_offsets, atoms, ns, width, n, j, S, R, _stream()))
+    return n, j, R, S
+end
+
 # ---- AtomsBase extension with device positions: the IsolatedCell bounding box (ext/NeighbourListsAtomsBaseExt.jl:17-31)
 function bounding_cell(X::CuVector{SVec{T}}) where {T}
     mm = CuVector{T}(undef, 6); ws = CUDA.zeros(UInt8, 32768)

@@ -47,7 +47,7 @@ _lib = None
 
 EXPORTS = ("nl_version", "nl_strerror", "nl_last_cuda_error", "nl_launch_count", "nl_workspace_bytes", "nl_build_cells", "nl_count_pairs",
            "nl_fill_pairs", "nl_fill_pairs_rows", "nl_cell_ids", "nl_shard_plan", "nl_lazy_count", "nl_lazy_lj_energy", "nl_lazy_lj_forces",
-           "nl_pairs_R", "nl_max_neighbours", "nl_rows_padded", "nl_bounding_box", "nl_max_displacement2")
+           "nl_pairs_R", "nl_max_neighbours", "nl_rows_padded", "nl_lazy_neighbours", "nl_bounding_box", "nl_max_displacement2")
 NL_REDUCE_WS_BYTES = 32768
 
 
@@ -81,9 +81,11 @@ def lib():
         L.nl_pairs_R.argtypes = [pp, vp, i64, vp, vp, vp, i64, i64, vp, vp]
         L.nl_max_neighbours.argtypes = [pp, vp, i64, vp, vp]
         L.nl_rows_padded.argtypes = [pp, vp, i64, vp, vp, vp, vp, i64, C.c_int32, vp, vp, vp, vp, vp]
+        L.nl_lazy_neighbours.argtypes = [pp, vp, vp, i64, vp, vp, vp, i64, C.c_int32, vp, vp, vp, vp, vp]
+        L.nl_lazy_neighbours.restype = C.c_int
         L.nl_bounding_box.argtypes = [C.c_int32, vp, i64, vp, vp, sz, vp]
         L.nl_max_displacement2.argtypes = [C.c_int32, vp, vp, i64, vp, vp, sz, vp]
-        for n in ("nl_pairs_R", "nl_max_neighbours", "nl_rows_padded", "nl_bounding_box", "nl_max_displacement2"):
+        for n in ("nl_pairs_R", "nl_max_neighbours", "nl_rows_padded", "nl_lazy_neighbours", "nl_bounding_box", "nl_max_displacement2"):
             getattr(L, n).restype = C.c_int
         for n in ("nl_build_cells", "nl_count_pairs", "nl_fill_pairs", "nl_fill_pairs_rows", "nl_cell_ids", "nl_shard_plan", "nl_lazy_count",
                   "nl_lazy_lj_energy"):

@@ -420,16 +420,41 @@ def lj_forces(clist: SortedCellList, eps: float, sigma: float):
     return fe[:, :3], fe[:, 3]
 
 
+def neighbours_padded(clist: SortedCellList, atoms, width: int, with_R: bool = True, with_S: bool = True):
+    """neighbours(clist, i) (src/cell_list.jl:821-833) for MANY atoms at once, straight from the cell list -- nothing is
+    materialised (nl_lazy_neighbours).  atoms: 1-based indices.  Returns (n, j, R, S) as sites_padded does; rows are in
+    the reference's traversal order (dz, dy, dx, then sorted slot) and truncated to `width` (n holds the full count)."""
+    N = clist.X.shape[0]
+    dev = clist.X.device
+    it = clist.perm.dtype
+    at = torch.as_tensor(atoms, device=dev).to(it).contiguous().reshape(-1)
+    if at.numel() and (int(at.min()) < 1 or int(at.max()) > N):
+        raise IndexError("atom index out of range")  # BoundsError in the reference
+    n_sel = int(at.numel())
+    with torch.cuda.device(dev):
+        n_out = torch.empty(n_sel, dtype=it, device=dev)
+        j_out = torch.empty((n_sel, width), dtype=it, device=dev)
+        S_out = torch.empty((n_sel, width, 3), dtype=it, device=dev) if with_S else None
+        R_out = torch.empty((n_sel, width, 3), dtype=clist.X.dtype, device=dev) if with_R else None
+        if n_sel > 0:
+            _lib.check(_lib.lib().nl_lazy_neighbours(clist.params, _ptr(clist.X_orig), _ptr(clist.X), N, _ptr(clist.perm),
+                                                     _ptr(clist.cell_offsets), _ptr(at), n_sel, width, _ptr(n_out), _ptr(j_out),
+                                                     _ptr(S_out), _ptr(R_out), _stream(dev)))
+    return n_out, j_out, R_out, S_out
+
+
 def neighbours(nl, i: int):
-    """neighbours(nlist_or_clist, i) -> (j, R, S)  (src/cell_list.jl:606, :821-833)."""
+    """neighbours(nlist_or_clist, i) -> (j, R, S)  (src/cell_list.jl:606, :821-833).  For a SortedCellList this is one
+    warp's traversal of atom i's stencil on the device; no pair list is built."""
     if isinstance(nl, PairList):
         return neigss(nl, i)
-    if nl._pl is None:
-        nl._pl = materialize_pairlist(nl, with_R=True)
-    pl = nl._pl
-    f = pl.first[i - 1:i + 1].tolist()
-    lo, hi = int(f[0]) - 1, int(f[1]) - 1
-    return pl.j[lo:hi], pl.R[lo:hi], pl.S[lo:hi]
+    width = 64
+    while True:
+        n, j, R, S = neighbours_padded(nl, [i], width)
+        k = int(n.item())
+        if k <= width:
+            return j[0, :k], R[0, :k], S[0, :k]
+        width = k
 
 
 def for_each_neighbour(f, clist: SortedCellList, i: int):

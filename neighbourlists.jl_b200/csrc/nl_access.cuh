@@ -100,6 +100,79 @@ __global__ void __launch_bounds__(256) k_rows_padded(const T* __restrict__ X, co
 }
 
 // ---------------------------------------------------------------------------------------------------------
+// neighbours(clist, i) for a SET of atoms straight from the cell list (src/cell_list.jl:821-833 over
+// for_each_neighbour, :779-801 -> _for_each_neighbor_pair, src/gpu_kernels.jl:58-101): nothing is materialised.
+// One warp per atom walks the stencil in the reference's own order (dz outermost, dx innermost, then sorted slot):
+// lanes take 32 consecutive slots of a cell, hits are compacted with ballot/popc, so row CONTENT AND ORDER equal
+// the reference's.  Output blocks as in k_rows_padded.
+template <class T, class TI>
+__global__ void __launch_bounds__(256) k_lazy_neighbours(const T* __restrict__ Xo, const T* __restrict__ Xs, const TI* __restrict__ perm,
+                                                         const TI* __restrict__ co, Geo<T> g, const TI* __restrict__ atoms, long long n_sel,
+                                                         int width, TI* __restrict__ n_out, TI* __restrict__ j_out, TI* __restrict__ S_out,
+                                                         T* __restrict__ R_out) {
+  const long long s = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (s >= n_sel) return;
+  const unsigned lt = (1u << lane) - 1u;
+  const long long i = (long long)atoms[s] - 1;
+  const T xi = Xo[3 * i], yi = Xo[3 * i + 1], zi = Xo[3 * i + 2];
+  int ci[3];
+  long long wi[3];
+  cell_of(g, xi, yi, zi, ci, wi);
+  const long long o0 = s * (long long)width;
+  long long cnt = 0;
+  for (int dz = -g.nxyz[2]; dz <= g.nxyz[2]; dz++) {
+    int cz; long long sz = 0;
+    { const long long v = (long long)ci[2] + dz;
+      if (g.pbc[2]) wrap0(v, g.nc[2], cz, sz); else { if (v < 0 || v >= g.nc[2]) continue; cz = (int)v; } }
+    for (int dy = -g.nxyz[1]; dy <= g.nxyz[1]; dy++) {
+      int cy; long long sy = 0;
+      { const long long v = (long long)ci[1] + dy;
+        if (g.pbc[1]) wrap0(v, g.nc[1], cy, sy); else { if (v < 0 || v >= g.nc[1]) continue; cy = (int)v; } }
+      for (int dx = -g.nxyz[0]; dx <= g.nxyz[0]; dx++) {
+        int cx; long long sx = 0;
+        { const long long v = (long long)ci[0] + dx;
+          if (g.pbc[0]) wrap0(v, g.nc[0], cx, sx); else { if (v < 0 || v >= g.nc[0]) continue; cx = (int)v; } }
+        const long long cl = (long long)cx + (long long)g.nc[0] * ((long long)cy + (long long)g.nc[1] * cz);
+        const long long b0 = (long long)co[cl] - 1, b1 = (long long)co[cl + 1] - 1;
+        const bool zero_shift = (sx == 0 && sy == 0 && sz == 0);
+        for (long long t0 = b0; t0 < b1; t0 += 32) {
+          const long long t = t0 + lane;
+          bool hit = false;
+          long long jo = 0, S[3] = {0, 0, 0};
+          T R[3] = {0, 0, 0};
+          if (t < b1) {
+            jo = (long long)perm[t] - 1;
+            if (!(jo == i && zero_shift)) {  // _is_self_interaction, src/gpu_kernels.jl:30-33
+              const T xj = Xs[3 * t], yj = Xs[3 * t + 1], zj = Xs[3 * t + 2];
+              int cj[3];
+              long long wj[3];
+              cell_of(g, xj, yj, zj, cj, wj);
+              S[0] = sx + wi[0] - wj[0]; S[1] = sy + wi[1] - wj[1]; S[2] = sz + wi[2] - wj[2];
+              hit = pair_r2(g, xi, yi, zi, xj, yj, zj, S, R) < g.cutoff_sq;
+            }
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, hit);
+          const long long pos = cnt + __popc(bal & lt);
+          if (hit && pos < width) {
+            j_out[o0 + pos] = (TI)(jo + 1);
+            if (S_out) { S_out[3 * (o0 + pos)] = (TI)S[0]; S_out[3 * (o0 + pos) + 1] = (TI)S[1]; S_out[3 * (o0 + pos) + 2] = (TI)S[2]; }
+            if (R_out) { R_out[3 * (o0 + pos)] = R[0]; R_out[3 * (o0 + pos) + 1] = R[1]; R_out[3 * (o0 + pos) + 2] = R[2]; }
+          }
+          cnt += __popc(bal);
+        }
+      }
+    }
+  }
+  if (lane == 0) n_out[s] = (TI)cnt;
+  for (long long k = cnt + lane; k < width; k += 32) {
+    j_out[o0 + k] = 0;
+    if (S_out) { S_out[3 * (o0 + k)] = 0; S_out[3 * (o0 + k) + 1] = 0; S_out[3 * (o0 + k) + 2] = 0; }
+    if (R_out) { R_out[3 * (o0 + k)] = 0; R_out[3 * (o0 + k) + 1] = 0; R_out[3 * (o0 + k) + 2] = 0; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------
 // Two-launch reductions over the atoms (partials in caller scratch, then one block).
 constexpr int RED_BLOCKS = 592;  // 4 x 148 SMs
 

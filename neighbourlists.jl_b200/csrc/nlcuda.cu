@@ -446,6 +446,18 @@ int rows_padded_impl(const nl_params* p, const void* X, const void* first, const
   return NL_OK;
 }
 
+template <class T, class TI>
+int lazy_neighbours_impl(const nl_params* p, const void* Xo, const void* Xs, const void* perm, const void* co, const void* atoms, int64_t n_sel,
+                         int32_t width, void* n_out, void* j_out, void* S_out, void* R_out, cudaStream_t st) {
+  Geo<T> g = make_geo<T>(p);
+  k_lazy_neighbours<T, TI><<<(unsigned)((n_sel + 7) / 8), 256, 0, st>>>((const T*)Xo, (const T*)Xs, (const TI*)perm, (const TI*)co, g,
+                                                                         (const TI*)atoms, n_sel, width, (TI*)n_out, (TI*)j_out, (TI*)S_out,
+                                                                         (T*)R_out);
+  NL_LAUNCHED(1);
+  NL_LAUNCH_CHECK();
+  return NL_OK;
+}
+
 template <class T> int bbox_impl(const void* X, int64_t N, void* out, void* ws, cudaStream_t st) {
   const int nb = (int)std::min<long long>(RED_BLOCKS, (N + 255) / 256);
   k_bbox_partial<T><<<nb, 256, 0, st>>>((const T*)X, N, (T*)ws);
@@ -661,6 +673,17 @@ int nl_rows_padded(const nl_params* params, const void* X, int64_t N, const void
   if (n_sel == 0) return NL_OK;
   if (!X || !first || !rows || !n_out || (width > 0 && (!j || !S || !j_out))) return NL_ERR_BAD_ARG;
   return NL_DISPATCH(params, rows_padded_impl, params, X, first, j, S, rows, n_sel, width, n_out, j_out, S_out, R_out, (cudaStream_t)stream);
+}
+
+int nl_lazy_neighbours(const nl_params* params, const void* X_orig, const void* X_sorted, int64_t N, const void* perm, const void* cell_offsets,
+                       const void* atoms, int64_t n_sel, int32_t width, void* n_out, void* j_out, void* S_out, void* R_out, void* stream) {
+  int rc = check_params(params, N);
+  if (rc) return rc;
+  if (n_sel < 0 || width < 0) return NL_ERR_BAD_ARG;
+  if (n_sel == 0) return NL_OK;
+  if (N == 0 || !X_orig || !X_sorted || !perm || !cell_offsets || !atoms || !n_out || (width > 0 && !j_out)) return NL_ERR_BAD_ARG;
+  return NL_DISPATCH(params, lazy_neighbours_impl, params, X_orig, X_sorted, perm, cell_offsets, atoms, n_sel, width, n_out, j_out, S_out, R_out,
+                     (cudaStream_t)stream);
 }
 
 int nl_bounding_box(int32_t float_type, const void* X, int64_t N, void* minmax_out, void* ws, size_t ws_bytes, void* stream) {

@@ -269,3 +269,44 @@ def test_half_list_other_routes(nl, dtype):
     # density beyond the mask path altogether (27 * dens > 200): exact tiled route
     X, C, L = U.rand_config(40000, seed=95, dtype=dtype, density=0.08)
     _check_half(nl, X, C, (True, True, True), 5.0, dtype)
+
+
+@pytest.mark.parametrize("dtype,int_type", [(np.float64, np.int32), (np.float32, np.int64)])
+def test_lazy_neighbours_rows_in_reference_order(nl, dtype, int_type):
+    # neighbours(clist, i) (src/cell_list.jl:821-833): rows straight from the cell list, in the reference's traversal
+    # order (the oracle emits its rows in that order too), bit-exact j / S / R
+    import torch
+    cases = []
+    X, C, L = U.rand_config(4000, seed=101, dtype=dtype)
+    cases.append((X, C, (True, True, True), 5.0))
+    Ct = (U.TRICLINIC * 2.0).astype(dtype)
+    cases.append((U.displace_by_lattice(U.rand_in_cell(3000, Ct, seed=102, dtype=dtype), Ct, (True, False, True)), Ct, (True, False, True), 3.0))
+    Xf, Cf = U.fcc(3.61, (2, 2, 2), dtype=dtype)       # 2 cells per axis: repeated cells, self images
+    cases.append((Xf, Cf, (True, True, True), 5.0))
+    Xf1, Cf1 = U.fcc(3.61, (1, 1, 1), dtype=dtype)     # 1 cell, stencil wider than the box
+    cases.append((Xf1, Cf1, (True, True, True), 4.0))
+    for X, C, pbc, rc in cases:
+        N = X.shape[0]
+        cl = nl.neighbour_list(torch.from_numpy(X).cuda(), rc, C, pbc, lazy=True, int_type=int_type)
+        orc = O.sortbased(X, rc, C, pbc, dtype=dtype, int_type=int_type)
+        f = orc["first"].astype(np.int64)
+        atoms = np.unique(np.concatenate([[1, N], np.random.default_rng(1).integers(1, N + 1, size=200)]))
+        width = int(np.diff(f).max())
+        n, j, R, S = nl.neighbours_padded(cl, atoms, width)
+        n, j, R, S = n.cpu().numpy(), j.cpu().numpy(), R.cpu().numpy(), S.cpu().numpy()
+        for s, a in enumerate(atoms):
+            lo, hi = f[a - 1] - 1, f[a] - 1
+            assert n[s] == hi - lo
+            assert np.array_equal(j[s, :n[s]], orc["j"][lo:hi]) and np.array_equal(S[s, :n[s]], orc["S"][lo:hi])
+            assert np.array_equal(R[s, :n[s]], orc["R"][lo:hi])
+            assert not j[s, n[s]:].any() and not S[s, n[s]:].any() and not R[s, n[s]:].any()
+        # truncation keeps the full count; the single-atom accessor grows its block as needed
+        k5 = min(5, len(atoms))
+        n2, j2, _, _ = nl.neighbours_padded(cl, atoms[:k5], 3, with_R=False, with_S=False)
+        assert np.array_equal(n2.cpu().numpy(), n[:k5]) and j2.shape == (k5, 3)
+        jj, RR, SS = nl.neighbours(cl, int(atoms[0]))
+        lo, hi = f[atoms[0] - 1] - 1, f[atoms[0]] - 1
+        assert np.array_equal(jj.cpu().numpy(), orc["j"][lo:hi]) and np.array_equal(RR.cpu().numpy(), orc["R"][lo:hi])
+        assert cl._pl is None, "no pair list was materialised"
+    with pytest.raises(IndexError):
+        nl.neighbours_padded(cl, [0], 4)

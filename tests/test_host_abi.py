@@ -146,6 +146,9 @@ def test_accessor_entry_points_validate_arguments():
     assert L.nl_rows_padded(p, ptr, 5, ptr, ptr, ptr, ptr, -1, 4, ptr, ptr, ptr, ptr, None) == E.NL_ERR_BAD_ARG
     assert L.nl_rows_padded(p, ptr, 5, ptr, ptr, ptr, None, 2, 4, ptr, ptr, ptr, ptr, None) == E.NL_ERR_BAD_ARG
     assert L.nl_rows_padded(p, ptr, 5, ptr, ptr, ptr, ptr, 0, 4, ptr, ptr, ptr, ptr, None) == E.NL_OK
+    assert L.nl_lazy_neighbours(p, ptr, ptr, 5, ptr, ptr, None, 2, 4, ptr, ptr, ptr, ptr, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_lazy_neighbours(p, ptr, ptr, 5, ptr, ptr, ptr, 0, 4, ptr, ptr, ptr, ptr, None) == E.NL_OK
+    assert L.nl_lazy_neighbours(p, ptr, ptr, 5, ptr, ptr, ptr, 2, -1, ptr, ptr, ptr, ptr, None) == E.NL_ERR_BAD_ARG
     assert L.nl_bounding_box(7, ptr, 5, ptr, ptr, 1 << 20, None) == E.NL_ERR_BAD_ARG
     assert L.nl_bounding_box(E.NL_F64, ptr, 0, ptr, ptr, 1 << 20, None) == E.NL_ERR_BAD_ARG
     assert L.nl_bounding_box(E.NL_F64, ptr, 5, ptr, None, 0, None) == E.NL_ERR_WORKSPACE
