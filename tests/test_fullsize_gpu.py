@@ -119,3 +119,53 @@ def test_config5_lazy_lj_f32(nl):
             e_mat = float((4.0 * (s6 * s6 - s6)).sum().item())
             assert abs(e - e_mat) <= 1e-5 * abs(e_mat), (e, e_mat)
             assert abs(nl.npairs(pl) / N - 4 / 3 * np.pi * 216 * 0.05) < 0.1
+
+
+def test_headline_10m_half_list_accessors_and_forces(nl):
+    """The 8f rows at the headline size, through size-independent properties: the half list holds exactly one pair of every
+    mirror couple of the full list (order-independent fingerprints); pairs_R reproduces the fill pass's R bit for bit;
+    maxneigs / padded rows agree with the CSR; the fused force sink obeys Newton's third law and its energies sum to
+    the fused energy sink."""
+    import torch
+    N, rc = 10_000_000, 5.0
+    rng = np.random.Generator(np.random.PCG64(10))
+    L = (N / 0.05) ** (1 / 3)
+    X = rng.random((N, 3)) * L
+    C = np.eye(3) * L
+    Xd = torch.from_numpy(X).cuda()
+    clist = nl.build_cell_list(Xd, rc, C, (True, True, True))
+    full = nl.materialize_pairlist(clist, with_R=True)
+    P = nl.npairs(full)
+    fi, fj, fS = full.i.long(), full.j.long(), full.S.long()
+    # canonical fingerprint of a mirror couple: min/max of the two orientations' fingerprints, combined symmetrically
+    a = _mix(fi, fj, fS[:, 0], fS[:, 1], fS[:, 2])
+    b = _mix(fj, fi, -fS[:, 0], -fS[:, 1], -fS[:, 2])
+    couple_full = (torch.minimum(a, b) * 31 + torch.maximum(a, b)).sum()
+    del a, b
+    assert torch.equal(nl.pairs_R(full), full.R), "accessor R == fill-pass R"
+    counts = (full.first[1:] - full.first[:-1]).long()
+    w = nl.maxneigs(full)
+    assert w == int(counts.max())
+    rows = torch.randint(1, N + 1, (100_000,), device="cuda", dtype=torch.int32)
+    n, j, R, S = nl.sites_padded(full, rows, w)
+    assert torch.equal(n.long(), counts[rows.long() - 1])
+    k = torch.arange(w, device="cuda")[None, :]
+    valid = k < n.long()[:, None]
+    src = (full.first.long()[rows.long() - 1] - 1)[:, None] + k
+    assert torch.equal(j[valid], full.j[src[valid]]) and torch.equal(R[valid], full.R[src[valid]]) and not bool(j[~valid].any())
+    del n, j, R, S, valid, src, fi, fj, fS
+    Pf = P
+    del full
+    half = nl.materialize_pairlist(clist, half=True)
+    assert nl.npairs(half) * 2 == Pf
+    hi_, hj, hS = half.i.long(), half.j.long(), half.S.long()
+    a = _mix(hi_, hj, hS[:, 0], hS[:, 1], hS[:, 2])
+    b = _mix(hj, hi_, -hS[:, 0], -hS[:, 1], -hS[:, 2])
+    couple_half = (torch.minimum(a, b) * 31 + torch.maximum(a, b)).sum()
+    assert int(couple_half * 2 - couple_full) == 0, "half list = one pair per mirror couple (wrapping int64 fingerprints)"
+    del a, b, half, hi_, hj, hS
+    # fused force sink in Float64 (exact tiled route) at full size
+    F, e = nl.lj_forces(clist, 1.0, 3.4)
+    etot = float(nl.lj_energy(clist, 1.0, 3.4).item())
+    assert abs(float(e.sum().item()) - etot) <= 1e-9 * abs(etot)
+    assert float(F.sum(0).abs().max()) <= 1e-9 * float(F.abs().sum())
