@@ -37,6 +37,29 @@ __global__ void write_rows(const int* __restrict__ first, const int* __restrict_
   }
 }
 
+// Variant A (ALIGNED): every row padded to a multiple of 8 entries, so each stream segment starts and ends on a 32-byte sector.
+// Variant B (INTERIOR): the real, unaligned rows, but only the sectors a row covers COMPLETELY are written (the partial head /
+// tail sectors, shared with the neighbouring rows, are skipped).  Both isolate the cost of partial-sector writes.
+template <int VARIANT>
+__global__ void write_rows_sect(const int* __restrict__ first, const int* __restrict__ order, int n, int* io, int* jo, int* So, double* Ro) {
+  const int lane = threadIdx.x & 31;
+  const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+  for (long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n; w += nw) {
+    const int row = order ? order[w] : (int)w;
+    long long b = first[row], e = first[row + 1];
+    if (VARIANT == 0) {  // padded rows: first[] was built with multiples of 8
+      const int cnt = (int)(e - b);
+      for (int r = lane; r < cnt; r += 32) { io[b + r] = row; jo[b + r] = r; }
+      for (int x = lane; x < 3 * cnt; x += 32) { So[3 * b + x] = x; Ro[3 * b + x] = (double)x; }
+    } else {
+      // element ranges rounded inwards to sector boundaries, per stream (4-byte elements: 8 per sector; doubles: 4 per sector)
+      { const long long lo = (b + 7) & ~7ll, hi = e & ~7ll; for (long long r = lo + lane; r < hi; r += 32) { io[r] = row; jo[r] = (int)r; } }
+      { const long long lo = (3 * b + 7) & ~7ll, hi = (3 * e) & ~7ll; for (long long x = lo + lane; x < hi; x += 32) So[x] = (int)x; }
+      { const long long lo = (3 * b + 3) & ~3ll, hi = (3 * e) & ~3ll; for (long long x = lo + lane; x < hi; x += 32) Ro[x] = (double)x; }
+    }
+  }
+}
+
 int main() {
   const int n = 10000000;
   std::mt19937 rng(1);
@@ -92,6 +115,28 @@ int main() {
     for (int it = 0; it < 5; it++) { cudaEventRecord(e0); cudaMemsetAsync(Ro, 1, P * 24); cudaMemsetAsync(So, 1, P * 12); cudaMemsetAsync(io, 1, P * 4); cudaMemsetAsync(jo, 1, P * 4);
       cudaEventRecord(e1); cudaEventSynchronize(e1); float ms; cudaEventElapsedTime(&ms, e0, e1); best = std::min(best, ms); }
     printf("cudaMemset of the same 44 B/pair: %.3f ms (%.0f GB/s)\n", best, (double)P * 44 / best / 1e6);
+  }
+  // partial-sector experiments
+  {
+    std::vector<int> first8(n + 1);
+    first8[0] = 0;
+    for (int i = 0; i < n; i++) first8[i + 1] = first8[i] + ((first[i + 1] - first[i] + 7) / 8) * 8;
+    const long long P8 = first8[n];
+    int *d_first8, *io8, *jo8, *So8; double* Ro8;
+    CK(cudaMalloc(&d_first8, (n + 1) * 4)); CK(cudaMemcpy(d_first8, first8.data(), (n + 1) * 4, cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&io8, P8 * 4)); CK(cudaMalloc(&jo8, P8 * 4)); CK(cudaMalloc(&So8, P8 * 12)); CK(cudaMalloc(&Ro8, P8 * 24));
+    for (int mode = 0; mode < 2; mode++) {
+      float best = 1e9;
+      for (int it = 0; it < 5; it++) { cudaEventRecord(e0); write_rows_sect<0><<<148 * 8, 256>>>(d_first8, mode ? d_perm : nullptr, n, io8, jo8, So8, Ro8); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1); best = std::min(best, ms); }
+      printf("ALIGNED rows (padded to 8 entries, P8=%lld), %s: %.3f ms (%.0f GB/s)\n", P8, mode ? "RANDOM order" : "sequential", best, (double)P8 * 44 / best / 1e6);
+    }
+    for (int mode = 0; mode < 2; mode++) {
+      float best = 1e9;
+      for (int it = 0; it < 5; it++) { cudaEventRecord(e0); write_rows_sect<1><<<148 * 8, 256>>>(d_first, mode ? d_perm : nullptr, n, io, jo, So, Ro); cudaEventRecord(e1); CK(cudaEventSynchronize(e1));
+        float ms; cudaEventElapsedTime(&ms, e0, e1); best = std::min(best, ms); }
+      printf("INTERIOR sectors only (unaligned rows, partial head/tail sectors skipped), %s: %.3f ms\n", mode ? "RANDOM order" : "sequential", best);
+    }
   }
   return 0;
 }
