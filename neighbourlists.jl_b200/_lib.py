@@ -46,7 +46,7 @@ class NlError(RuntimeError):
 _lib = None
 
 EXPORTS = ("nl_version", "nl_strerror", "nl_last_cuda_error", "nl_launch_count", "nl_workspace_bytes", "nl_build_cells", "nl_count_pairs",
-           "nl_fill_pairs", "nl_fill_pairs_rows", "nl_cell_ids", "nl_shard_plan", "nl_lazy_count", "nl_lazy_lj_energy", "nl_lazy_lj_forces",
+           "nl_fill_pairs", "nl_fill_pairs_rows", "nl_count_pairs_window", "nl_fill_pairs_window", "nl_cell_ids", "nl_shard_plan", "nl_lazy_count", "nl_lazy_lj_energy", "nl_lazy_lj_forces",
            "nl_pairs_R", "nl_max_neighbours", "nl_rows_padded", "nl_lazy_neighbours", "nl_bounding_box", "nl_max_displacement2")
 NL_REDUCE_WS_BYTES = 32768
 
@@ -71,6 +71,10 @@ def lib():
         L.nl_count_pairs.argtypes = [pp, vp, i64, vp, vp, vp, C.POINTER(C.c_int64), vp, sz, vp]
         L.nl_fill_pairs.argtypes = [pp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, sz, vp]
         L.nl_fill_pairs_rows.argtypes = [pp, vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, sz, vp]
+        L.nl_count_pairs_window.argtypes = [pp, vp, i64, vp, vp, vp, C.POINTER(C.c_int64), vp, vp, sz, vp]
+        L.nl_fill_pairs_window.argtypes = [pp, vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, sz, vp]
+        L.nl_count_pairs_window.restype = C.c_int
+        L.nl_fill_pairs_window.restype = C.c_int
         L.nl_cell_ids.argtypes = [pp, vp, i64, vp, vp]
         L.nl_shard_plan.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, vp]
         L.nl_shard_plan.restype = C.c_int
@@ -87,7 +91,7 @@ def lib():
         L.nl_max_displacement2.argtypes = [C.c_int32, vp, vp, i64, vp, vp, sz, vp]
         for n in ("nl_pairs_R", "nl_max_neighbours", "nl_rows_padded", "nl_lazy_neighbours", "nl_bounding_box", "nl_max_displacement2"):
             getattr(L, n).restype = C.c_int
-        for n in ("nl_build_cells", "nl_count_pairs", "nl_fill_pairs", "nl_fill_pairs_rows", "nl_cell_ids", "nl_shard_plan", "nl_lazy_count",
+        for n in ("nl_build_cells", "nl_count_pairs", "nl_fill_pairs", "nl_fill_pairs_rows", "nl_count_pairs_window", "nl_fill_pairs_window", "nl_cell_ids", "nl_shard_plan", "nl_lazy_count",
                   "nl_lazy_lj_energy"):
             getattr(L, n).restype = C.c_int
         _lib = L

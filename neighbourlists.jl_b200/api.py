@@ -153,12 +153,16 @@ def build_cell_list(X, cutoff, cell=None, pbc=None, *, int_type=np.int32, device
 
 
 def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers: Optional[dict] = None,
-                         n_rows: Optional[int] = None, index_map: Optional[torch.Tensor] = None, half: bool = False) -> PairList:
+                         n_rows: Optional[int] = None, index_map: Optional[torch.Tensor] = None, half: bool = False,
+                         plane_active: Optional[np.ndarray] = None) -> PairList:
     """materialize_pairlist(clist) -> PairList  (src/gpu_kernels.jl:299-364).  with_R additionally
     stores R = X[j] - X[i] + C' S per pair (what the reference recomputes in _getR).
 
     Shard mode (sharded.py): with n_rows, only the first n_rows atoms get rows (`first` has n_rows+1
     entries) and i/j are written through index_map (global 1-based indices, one per local atom).
+
+    plane_active (slab shards cut along z): uint8 per z plane of cells, nonzero where the local set may have atoms; the
+    caller promises all other planes are empty and only those tile layers are launched (nl_*_window).
 
     half=True stores one pair of every mirror couple (i, j, S) / (j, i, -S) (NL_FLAG_HALF, include/nlcuda.h): half the
     pairs, half the output traffic; which of the two is kept is unspecified."""
@@ -178,8 +182,18 @@ def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers:
         if timers is not None:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
-        _lib.check(L.nl_count_pairs(params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
-                                    C.byref(total), _ptr(ws), ws.numel(), _stream(dev)))
+        pa = None
+        if plane_active is not None:
+            pa = np.ascontiguousarray(plane_active, dtype=np.uint8)
+            if pa.shape != (int(clist.ncells[2]),):
+                raise ValueError("plane_active must have one entry per z plane of cells")
+        pa_ptr = None if pa is None else pa.ctypes.data
+        if pa is None:
+            _lib.check(L.nl_count_pairs(params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
+                                        C.byref(total), _ptr(ws), ws.numel(), _stream(dev)))
+        else:
+            _lib.check(L.nl_count_pairs_window(params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
+                                               C.byref(total), pa_ptr, _ptr(ws), ws.numel(), _stream(dev)))
         P = int(total.value)
         if n_rows is not None:
             if not 0 <= n_rows <= N:
@@ -193,7 +207,14 @@ def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers:
         R = torch.empty((P, 3), dtype=clist.X.dtype, device=dev) if with_R else None
         if timers is not None:
             ev[2].record()
-        if P > 0 and n_rows is None and index_map is None:
+        if P > 0 and pa is not None:
+            if index_map is not None:
+                index_map = index_map.to(device=dev, dtype=it).contiguous()
+                assert index_map.shape[0] == N
+            _lib.check(L.nl_fill_pairs_window(params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
+                                              N if n_rows is None else n_rows, _ptr(index_map), pa_ptr, _ptr(i), _ptr(j), _ptr(S), _ptr(R),
+                                              _ptr(ws), ws.numel(), _stream(dev)))
+        elif P > 0 and n_rows is None and index_map is None:
             _lib.check(L.nl_fill_pairs(params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
                                        _ptr(i), _ptr(j), _ptr(S), _ptr(R), _ptr(ws), ws.numel(), _stream(dev)))
         elif P > 0:

@@ -69,6 +69,7 @@ template <class T, class TI> struct MaskArgs {
   int tx, ty, tz, ntx, nty, ntz;
   float mid, hw, dguard;
   const void* srow;   // fill pass: row start per sorted atom (k_row_starts)
+  const int* zlayers; // launched tile layers along z (slab shards: the layers that can hold atoms); null = all ntz layers
   const MaskArgs<T, TI>* self;  // this struct in GLOBAL memory: the rare out-of-line paths read their inputs from there, so the
                                 // kernels never copy their parameters onto the local-memory stack (measured: that copy cost
                                 // 77 KB of local stores per CTA, 9 GB per launch on a slab of an 8x larger global grid)
@@ -303,7 +304,8 @@ __global__ void __launch_bounds__(TILE_NT, CM == CM_MASK ? NL_CNT_MINB : (CM == 
   double e_acc = 0.0;                                                       // CM_LJ: this lane's share of the energy
 
   const int b = blockIdx.x;
-  const int hx0 = (b % a.ntx) * a.tx, hy0 = ((b / a.ntx) % a.nty) * a.ty, hz0 = (b / (a.ntx * a.nty)) * a.tz;
+  const int bz = b / (a.ntx * a.nty);
+  const int hx0 = (b % a.ntx) * a.tx, hy0 = ((b / a.ntx) % a.nty) * a.ty, hz0 = (a.zlayers ? a.zlayers[bz] : bz) * a.tz;
   const int hxn = min(a.tx, g.nc[0] - hx0), hyn = min(a.ty, g.nc[1] - hy0), hzn = min(a.tz, g.nc[2] - hz0);
   const int VX = hxn + 2, VY = hyn + 2, VZ = hzn + 2, NV = VX * VY * VZ;
   {  // quick reject: tiles without a single home atom (a slab shard sees the global grid, mostly empty) cost two loads per row
@@ -701,7 +703,8 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
   T* cst = (T*)(wb + CELLTAB_BYTES + 4 * MASK_MAXCAND + 32 * 3 * 4 + 32 * 3 * 8);  // [27][3] cell' * s_loop per stencil cell
 
   const int b = blockIdx.x;
-  const int hx0 = (b % a.ntx) * a.tx, hy0 = ((b / a.ntx) % a.nty) * a.ty, hz0 = (b / (a.ntx * a.nty)) * a.tz;
+  const int bz = b / (a.ntx * a.nty);
+  const int hx0 = (b % a.ntx) * a.tx, hy0 = ((b / a.ntx) % a.nty) * a.ty, hz0 = (a.zlayers ? a.zlayers[bz] : bz) * a.tz;
   const int hxn = min(a.tx, g.nc[0] - hx0), hyn = min(a.ty, g.nc[1] - hy0), hzn = min(a.tz, g.nc[2] - hz0);
   const int VX = hxn + 2, VY = hyn + 2, VZ = hzn + 2, NV = VX * VY * VZ;
   {  // quick reject: tiles without a single home atom (a slab shard sees the global grid, mostly empty) cost two loads per row
@@ -875,7 +878,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_FILL_MINB) k_fill_mask(const MaskA
 template <class T, class TI>
 inline void mask_args(MaskArgs<T, TI>& a, int64_t n, const TI* co, const Records<T>& rec, const Geo<T>& g, const Sinks<T, TI>& sk,
                       const TileShape& ts, uint32_t* masks) {
-  a.rec = rec; a.co = co; a.n = n; a.g = g; a.out = sk; a.masks = masks; a.cellflag = nullptr; a.self = nullptr; a.srow = nullptr;
+  a.rec = rec; a.co = co; a.n = n; a.g = g; a.out = sk; a.masks = masks; a.cellflag = nullptr; a.self = nullptr; a.srow = nullptr; a.zlayers = nullptr;
   a.tx = ts.tx; a.ty = ts.ty; a.tz = ts.tz;
   a.ntx = (g.nc[0] + ts.tx - 1) / ts.tx; a.nty = (g.nc[1] + ts.ty - 1) / ts.ty; a.ntz = (g.nc[2] + ts.tz - 1) / ts.tz;
   a.mid = a.hw = a.dguard = 0.f;

@@ -35,6 +35,7 @@ template <class T, class TI> struct Sinks {
   double* energy;        // MODE_LJ: device scalar
   double lj_eps, lj_sigma2;
   int half;              // MODE_COUNT / MODE_FILL of a materialisation: keep one pair of each mirror couple (see half_keep)
+  const uint8_t* plane_active;  // HOST pointer (read by the launcher only): per z plane of cells, may hold atoms; null = all
   T* fe;                 // MODE_LJF: N x 4 (force x, y, z, energy) per ORIGINAL atom, accumulated with atomics
 };
 

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
 
 #include "nl_build.cuh"
 #include "nl_common.cuh"
@@ -99,6 +100,7 @@ struct PairWs {
   uint32_t *pidx, *pw, *counts, *pgid0, *pkey, *sorted_of;
   void* ra;
   void* srow;  // fill pass: 0-based row start of every SORTED atom (all ones: no row), TI-wide
+  int* zlayers; // tile layers along z that a windowed (slab shard) call launches
   unsigned long long* tsum;
   unsigned long long* total;
   void* tiled;  // tiled-kernel scratch (tile table, hit masks)
@@ -122,6 +124,7 @@ PairWs pair_ws(void* ws, const nl_params* prm, int64_t N) {
   w.sorted_of = (uint32_t*)take(n1 * 4);
   w.ra = take(n1 * 32);
   w.srow = take(n1 * 8);
+  w.zlayers = (int*)take(((size_t)prm->ncells[2] + 1) * 4);
   w.tsum = (unsigned long long*)take((size_t)(scan_tiles((long long)n1) + 1) * 8);
   w.total = (unsigned long long*)take(256);
   w.tiled = take(tiled_scratch_bytes(prm, N));
@@ -256,6 +259,26 @@ TiledScratch tiled_scratch(void* base, int64_t N) {
   return t;
 }
 
+// Slab shards (nl_*_window): only the tile layers along z that contain an active cell plane are launched.  The rest of a
+// shard's view of the GLOBAL grid is empty; launching it cost 1.1 ms per list at 8 ranks (scripts/exp_slab_tiles.py).
+template <class T, class TI>
+int apply_plane_window(MaskArgs<T, TI>& a, const uint8_t* plane_active, int* zl_dev, unsigned& nblk, cudaStream_t st) {
+  nblk = (unsigned)((long long)a.ntx * a.nty * a.ntz);
+  if (!plane_active) return NL_OK;
+  std::vector<int> layers;
+  for (int k = 0; k < a.ntz; k++) {
+    bool on = false;
+    for (int z = k * a.tz; z < std::min((k + 1) * a.tz, a.g.nc[2]) && !on; z++) on = plane_active[z] != 0;
+    if (on) layers.push_back(k);
+  }
+  if ((int)layers.size() == a.ntz) return NL_OK;
+  if (layers.empty()) layers.push_back(0);
+  NL_CUDA(cudaMemcpyAsync(zl_dev, layers.data(), layers.size() * sizeof(int), cudaMemcpyHostToDevice, st));  // pageable source: staged before return
+  a.zlayers = zl_dev;
+  nblk = (unsigned)((long long)a.ntx * a.nty * (long long)layers.size());
+  return NL_OK;
+}
+
 // MODE_COUNT with want_mask (materialisation) or without (lazy count), MODE_FILL, MODE_LJ.
 template <class T, class TI, int MODE>
 int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, const Geo<T>& g, const Sinks<T, TI>& sk, bool want_mask,
@@ -287,7 +310,11 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
     mask_args<T, TI>(a, N, (const TI*)co, rec, g, sk, MODE == MODE_FILL ? pl.ts_fill : pl.ts_count, tsx.masks);
     a.cellflag = tsx.cellflag;
     a.mid = pl.th.mid; a.hw = pl.th.hw; a.dguard = pl.th.dguard;
-    const unsigned nblk = (unsigned)((long long)a.ntx * a.nty * a.ntz);
+    unsigned nblk = 0;
+    {
+      int rcw = apply_plane_window<T, TI>(a, sk.plane_active, w.zlayers, nblk, st);
+      if (rcw) return rcw;
+    }
     static_assert(sizeof(MaskArgs<T, TI>) <= 1024, "argument block");
     a.self = (const MaskArgs<T, TI>*)((char*)w.hdr + (MODE == MODE_FILL ? 2048 : (want_mask ? 0 : 3072)));
     if (MODE == MODE_FILL && !fill_tiled_requested()) {
@@ -339,7 +366,7 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
 
 template <class T, class TI>
 int count_pairs_impl(const nl_params* p, const void* Xs, int64_t N, const void* perm, const void* co, void* first, int64_t* total_host,
-                     void* ws, cudaStream_t st) {
+                     void* ws, const uint8_t* plane_active, cudaStream_t st) {
   Geo<T> g = make_geo<T>(p);
   PairWs w = pair_ws(ws, p, N);
   unsigned long long total = 0;
@@ -349,6 +376,7 @@ int count_pairs_impl(const nl_params* p, const void* Xs, int64_t N, const void* 
     Sinks<T, TI> sk = {};
     sk.counts = w.counts;
     sk.half = p->reserved[0] & NL_FLAG_HALF;
+    sk.plane_active = plane_active;
     rc = traverse<T, TI, MODE_COUNT>(p, N, co, w, g, sk, true, st);
     if (rc) return rc;
     exclusive_scan<uint32_t, unsigned long long, TI>(w.counts, N, (TI*)first, 1ull, true, w.tsum, w.total, st);
@@ -366,7 +394,7 @@ int count_pairs_impl(const nl_params* p, const void* Xs, int64_t N, const void* 
 
 template <class T, class TI>
 int fill_pairs_impl(const nl_params* p, int64_t N, const void* co, const void* first, void* io, void* jo, void* So, void* Ro, void* ws,
-                    int64_t n_rows, const void* gmap, cudaStream_t st) {
+                    int64_t n_rows, const void* gmap, const uint8_t* plane_active, cudaStream_t st) {
   Geo<T> g = make_geo<T>(p);
   PairWs w = pair_ws(ws, p, N);
   Sinks<T, TI> sk = {};
@@ -374,6 +402,7 @@ int fill_pairs_impl(const nl_params* p, int64_t N, const void* co, const void* f
   sk.io = (TI*)io; sk.jo = (TI*)jo; sk.So = (TI*)So; sk.Ro = (T*)Ro;
   sk.n_rows = n_rows; sk.gmap = (const TI*)gmap;
   sk.half = p->reserved[0] & NL_FLAG_HALF;
+  sk.plane_active = plane_active;
   if (gmap && N > 0) {
     k_make_pgid<TI><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(w.pidx, (const TI*)gmap, N, w.pgid0);
     NL_LAUNCHED(1);
@@ -550,7 +579,7 @@ int nl_count_pairs(const nl_params* params, const void* X_sorted, int64_t N, con
   if (!first || !total_pairs_host || !cell_offsets || (N > 0 && (!X_sorted || !perm))) return NL_ERR_BAD_ARG;
   rc = check_ws(ws, ws_bytes, pair_ws(nullptr, params, N).total_bytes);
   if (rc) return rc;
-  return NL_DISPATCH(params, count_pairs_impl, params, X_sorted, N, perm, cell_offsets, first, total_pairs_host, ws, (cudaStream_t)stream);
+  return NL_DISPATCH(params, count_pairs_impl, params, X_sorted, N, perm, cell_offsets, first, total_pairs_host, ws, nullptr, (cudaStream_t)stream);
 }
 
 int nl_fill_pairs(const nl_params* params, const void* X_sorted, int64_t N, const void* perm, const void* cell_offsets, const void* first,
@@ -561,7 +590,7 @@ int nl_fill_pairs(const nl_params* params, const void* X_sorted, int64_t N, cons
   if (!first || !cell_offsets || !X_sorted || !perm || !i_out || !j_out || !S_out) return NL_ERR_BAD_ARG;
   rc = check_ws(ws, ws_bytes, pair_ws(nullptr, params, N).total_bytes);
   if (rc) return rc;
-  return NL_DISPATCH(params, fill_pairs_impl, params, N, cell_offsets, first, i_out, j_out, S_out, R_out, ws, N, nullptr, (cudaStream_t)stream);
+  return NL_DISPATCH(params, fill_pairs_impl, params, N, cell_offsets, first, i_out, j_out, S_out, R_out, ws, N, nullptr, nullptr, (cudaStream_t)stream);
 }
 
 int nl_fill_pairs_rows(const nl_params* params, const void* X_sorted, int64_t N, const void* perm, const void* cell_offsets, const void* first,
@@ -574,7 +603,32 @@ int nl_fill_pairs_rows(const nl_params* params, const void* X_sorted, int64_t N,
   if (!first || !cell_offsets || !X_sorted || !perm || !i_out || !j_out || !S_out) return NL_ERR_BAD_ARG;
   rc = check_ws(ws, ws_bytes, pair_ws(nullptr, params, N).total_bytes);
   if (rc) return rc;
-  return NL_DISPATCH(params, fill_pairs_impl, params, N, cell_offsets, first, i_out, j_out, S_out, R_out, ws, n_rows, index_map,
+  return NL_DISPATCH(params, fill_pairs_impl, params, N, cell_offsets, first, i_out, j_out, S_out, R_out, ws, n_rows, index_map, nullptr,
+                     (cudaStream_t)stream);
+}
+
+int nl_count_pairs_window(const nl_params* params, const void* X_sorted, int64_t N, const void* perm, const void* cell_offsets, void* first,
+                          int64_t* total_pairs_host, const uint8_t* plane_active, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_params(params, N);
+  if (rc) return rc;
+  if (!first || !total_pairs_host || !cell_offsets || (N > 0 && (!X_sorted || !perm))) return NL_ERR_BAD_ARG;
+  rc = check_ws(ws, ws_bytes, pair_ws(nullptr, params, N).total_bytes);
+  if (rc) return rc;
+  return NL_DISPATCH(params, count_pairs_impl, params, X_sorted, N, perm, cell_offsets, first, total_pairs_host, ws, plane_active,
+                     (cudaStream_t)stream);
+}
+
+int nl_fill_pairs_window(const nl_params* params, const void* X_sorted, int64_t N, const void* perm, const void* cell_offsets, const void* first,
+                         int64_t n_rows, const void* index_map, const uint8_t* plane_active, void* i_out, void* j_out, void* S_out, void* R_out,
+                         void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_params(params, N);
+  if (rc) return rc;
+  if (N == 0 || n_rows == 0) return NL_OK;
+  if (n_rows < 0 || n_rows > N) return NL_ERR_BAD_ARG;
+  if (!first || !cell_offsets || !X_sorted || !perm || !i_out || !j_out || !S_out) return NL_ERR_BAD_ARG;
+  rc = check_ws(ws, ws_bytes, pair_ws(nullptr, params, N).total_bytes);
+  if (rc) return rc;
+  return NL_DISPATCH(params, fill_pairs_impl, params, N, cell_offsets, first, i_out, j_out, S_out, R_out, ws, n_rows, index_map, plane_active,
                      (cudaStream_t)stream);
 }
 

@@ -90,10 +90,10 @@ class CudaEngine:
         from . import api
         return api.cell_ids(X, cutoff, cell, pbc, int_type=np.int64).long()
 
-    def build(self, X_all, n_owned, gmap, cutoff, cell, pbc, int_type, with_R):
+    def build(self, X_all, n_owned, gmap, cutoff, cell, pbc, int_type, with_R, plane_active=None):
         from . import api
         clist = api.build_cell_list(X_all, cutoff, cell, pbc, int_type=int_type)
-        pl = api.materialize_pairlist(clist, with_R=with_R, n_rows=n_owned, index_map=gmap, timers=self.timers)
+        pl = api.materialize_pairlist(clist, with_R=with_R, n_rows=n_owned, index_map=gmap, timers=self.timers, plane_active=plane_active)
         return dict(first=pl.first, i=pl.i, j=pl.j, S=pl.S, R=pl.R)
 
 
@@ -235,7 +235,18 @@ def neighbour_list_sharded(X_local, gidx_local, cutoff, cell, pbc, *, group=None
     ph.mark("halo")
 
     # ---- step 2: the unchanged single-GPU pipeline on owned + halo atoms, global geometry
-    res = engine.build(X_all, n_owned, g_all, cutoff, cell, pbc, int_type, with_R)
+    # z slabs: tell the local stage which cell planes can hold atoms (owned planes + halo planes), so that it launches only
+    # those tile layers of the global grid
+    plane_active = None
+    if world > 1 and axis == 2:
+        plane_active = np.zeros(nc[2], dtype=np.uint8)
+        lo, hi = int(plan.bounds[rank]), int(plan.bounds[rank + 1])
+        for z in range(lo - halo, hi + halo):
+            if 0 <= z < nc[2]:
+                plane_active[z] = 1
+            elif plan.periodic:
+                plane_active[z % nc[2]] = 1
+    res = engine.build(X_all, n_owned, g_all, cutoff, cell, pbc, int_type, with_R, plane_active=plane_active)
     ph.mark("local build")
     ph.report(rank)
     return ShardedPairList(owned_index=gidx, X_owned=X, first=res["first"], i=res["i"], j=res["j"], S=res["S"], R=res["R"],

@@ -350,3 +350,41 @@ def test_randomised_geometries(nl):
         lens = np.abs(np.linalg.det(A)) / np.array([np.linalg.norm(np.cross(A[(k + 1) % 3], A[(k + 2) % 3])) for k in range(3)])
         cutoff = float(rng.choice([0.25, 0.45, 0.9, 1.3]) * lens.min())
         check_case(nl, X, cutoff, cell, pbc, dtype=dtype, int_type=int_type, msg=f"fuzz case {case}: N={N} pbc={pbc} rc={cutoff:.3f}")
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_plane_window_equals_full_launch(nl, dtype):
+    """nl_count_pairs_window / nl_fill_pairs_window: a slab shard promises which z planes of cells can hold atoms and only
+    those tile layers are launched.  The result must equal the full launch and the oracle (contiguous and wrapped windows)."""
+    import torch
+    rng = np.random.default_rng(17)
+    L = 60.0
+    C = (np.eye(3) * L).astype(dtype)
+    pbc = (True, True, True)
+    for zr in ([(0.30, 0.55)], [(0.0, 0.12), (0.9, 1.0)]):
+        parts = []
+        for lo, hi in zr:
+            f = rng.random((6000, 3))
+            f[:, 2] = lo + f[:, 2] * (hi - lo)
+            parts.append(f)
+        X = (np.concatenate(parts) * L).astype(dtype)
+        Xd = torch.from_numpy(X).cuda()
+        cl = nl.build_cell_list(Xd, 5.0, C, pbc)
+        nz = int(cl.ncells[2])
+        zc = ((cl.cell_id.long() - 1) // int(cl.ncells[0] * cl.ncells[1])).cpu().numpy()
+        pa = np.zeros(nz, np.uint8)
+        pa[np.unique(zc)] = 1
+        assert 0 < pa.sum() < nz
+        full = nl.materialize_pairlist(cl, with_R=True).cpu()
+        win = nl.materialize_pairlist(cl, with_R=True, plane_active=pa).cpu()
+        for k in ("first", "i", "j", "S", "R"):
+            assert np.array_equal(full[k], win[k]), k
+        U.assert_engine_matches_oracle(win, O.sortbased(X, 5.0, C, pbc, dtype=dtype), RTOL[np.dtype(dtype)], msg="window")
+        # shard-style call: rows for the first half of the atoms only, global indices
+        gmap = torch.arange(100, 100 + X.shape[0], device="cuda", dtype=torch.int32)
+        a = nl.materialize_pairlist(cl, n_rows=3000, index_map=gmap).cpu()
+        b = nl.materialize_pairlist(cl, n_rows=3000, index_map=gmap, plane_active=pa).cpu()
+        for k in ("first", "i", "j", "S"):
+            assert np.array_equal(a[k], b[k]), k
+    with pytest.raises(ValueError):
+        nl.materialize_pairlist(cl, plane_active=np.ones(3, np.uint8))

@@ -26,7 +26,12 @@ class OracleEngine:
         ids[r["perm"] - 1] = r["cell_id"]
         return torch.from_numpy(ids)
 
-    def build(self, X_all, n_owned, gmap, cutoff, cell, pbc, int_type, with_R):
+    def build(self, X_all, n_owned, gmap, cutoff, cell, pbc, int_type, with_R, plane_active=None):
+        if plane_active is not None:  # the promise made to the windowed entry points: no local atom outside the active planes
+            ids = self.cell_ids(X_all, cutoff, cell, pbc).numpy() - 1
+            g = O.analyze_cell(cell, cutoff, X_all.numpy().dtype)
+            nc = [int(v) for v in g["ncells"]]
+            assert plane_active.shape == (nc[2],) and plane_active[ids // (nc[0] * nc[1])].all()
         Xn = X_all.numpy()
         r = O.sortbased(Xn, cutoff, cell, pbc, dtype=Xn.dtype, int_type=int_type)
         P = int(r["first"][n_owned]) - 1
