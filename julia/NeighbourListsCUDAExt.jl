@@ -63,9 +63,14 @@ function NeighbourLists._build_sorted_celllist(X::CuVector{SVec{T}}, cell::SMat{
 end
 
 # ---- stage override 2: materialize_pairlist (src/gpu_kernels.jl:299-364)
-function NeighbourLists.materialize_pairlist(clist::SortedCellList{T,TI,<:CuVector}; backend = nothing) where {T,TI}
+# `half = true` (not a reference feature) stores one pair of every mirror couple (i, j, S) / (j, i, -S): NL_FLAG_HALF
+_with_flags(p::NlParams, flags::UInt8) = NlParams(p.float_type, p.int_type, p.cell, p.inv_cell, p.cutoff, p.ncells, p.nxyz, p.pbc,
+                                                  (flags, 0x00, 0x00, 0x00, 0x00))
+
+function NeighbourLists.materialize_pairlist(clist::SortedCellList{T,TI,<:CuVector}; backend = nothing, half::Bool = false) where {T,TI}
     nat = length(clist.X)
     p = _params(clist.cell, clist.inv_cell, clist.pbc, clist.cutoff, clist.ncells)
+    half && (p = _with_flags(p, 0x01))
     first = CuVector{TI}(undef, nat + 1)
     ws = _ws(p, nat, 1)
     total = Ref{Int64}(0)
@@ -163,6 +168,28 @@ function neighbours_padded(clist::SortedCellList{T,TI,<:CuVector}, atoms::CuVect
                   CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{Cvoid}),
                  p, clist.X_orig, clist.X, length(clist.X), clist.perm, clist.cell_offsets, atoms, ns, width, n, j, S, R, _stream()))
     return n, j, R, S
+end
+
+# ---- slab shards (multi-GPU driver): rows of the first n_rows local atoms only, i / j through index_map (global indices);
+# plane_active :: Vector{UInt8} (host, one byte per z plane of cells) promises where the local atoms are, so that only
+# those tile layers of the global grid are launched
+function shard_pairlist(clist::SortedCellList{T,TI,<:CuVector}, n_rows::Integer, index_map::CuVector{TI},
+                        plane_active::Union{Nothing,Vector{UInt8}} = nothing) where {T,TI}
+    nat = length(clist.X); p = _params(clist.cell, clist.inv_cell, clist.pbc, clist.cutoff, clist.ncells)
+    first = CuVector{TI}(undef, nat + 1); ws = _ws(p, nat, 1); total = Ref{Int64}(0)
+    pa = plane_active === nothing ? C_NULL : pointer(plane_active)
+    GC.@preserve plane_active begin
+        _check(ccall((:nl_count_pairs_window, libnlcuda), Cint,
+                     (Ref{NlParams}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Ref{Int64}, Ptr{UInt8}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                     p, clist.X, nat, clist.perm, clist.cell_offsets, first, total, pa, ws, length(ws), _stream()))
+        P = Int(Array(first[n_rows+1:n_rows+1])[1]) - 1
+        i = CuVector{TI}(undef, P); j = CuVector{TI}(undef, P); S = CuVector{SVec{TI}}(undef, P)
+        P > 0 && _check(ccall((:nl_fill_pairs_window, libnlcuda), Cint,
+                     (Ref{NlParams}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Ptr{UInt8},
+                      CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                     p, clist.X, nat, clist.perm, clist.cell_offsets, first, n_rows, index_map, pa, i, j, S, CU_NULL, ws, length(ws), _stream()))
+    end
+    return first[1:n_rows+1], i, j, S
 end
 
 # ---- AtomsBase extension with device positions: the IsolatedCell bounding box (ext/NeighbourListsAtomsBaseExt.jl:17-31)

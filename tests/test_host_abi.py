@@ -149,6 +149,11 @@ def test_accessor_entry_points_validate_arguments():
     assert L.nl_lazy_neighbours(p, ptr, ptr, 5, ptr, ptr, None, 2, 4, ptr, ptr, ptr, ptr, None) == E.NL_ERR_BAD_ARG
     assert L.nl_lazy_neighbours(p, ptr, ptr, 5, ptr, ptr, ptr, 0, 4, ptr, ptr, ptr, ptr, None) == E.NL_OK
     assert L.nl_lazy_neighbours(p, ptr, ptr, 5, ptr, ptr, ptr, 2, -1, ptr, ptr, ptr, ptr, None) == E.NL_ERR_BAD_ARG
+    total = C.c_int64(0)
+    assert L.nl_count_pairs_window(p, ptr, 10, ptr, ptr, ptr, C.byref(total), None, None, 0, None) == E.NL_ERR_WORKSPACE
+    assert L.nl_count_pairs_window(p, None, 10, ptr, ptr, ptr, C.byref(total), None, ptr, 1 << 30, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_fill_pairs_window(p, ptr, 10, ptr, ptr, ptr, 11, None, None, ptr, ptr, ptr, None, ptr, 1 << 30, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_fill_pairs_window(p, ptr, 10, ptr, ptr, ptr, 0, None, None, ptr, ptr, ptr, None, ptr, 1 << 30, None) == E.NL_OK
     assert L.nl_bounding_box(7, ptr, 5, ptr, ptr, 1 << 20, None) == E.NL_ERR_BAD_ARG
     assert L.nl_bounding_box(E.NL_F64, ptr, 0, ptr, ptr, 1 << 20, None) == E.NL_ERR_BAD_ARG
     assert L.nl_bounding_box(E.NL_F64, ptr, 5, ptr, None, 0, None) == E.NL_ERR_WORKSPACE
