@@ -162,3 +162,11 @@ def test_misplaced_atoms_without_redistribution_are_an_error():
         mp.spawn(_worker, args=(2, _free_port(), (X, cell, (True, True, True), 3.0, "misplaced"), d), nprocs=2, join=True)
         errs = [f for f in os.listdir(d) if f.endswith(".err")]
         assert len(errs) == 2 and "not in this rank's slab" in open(os.path.join(d, errs[0])).read()
+
+
+def test_three_ranks_z_slabs_open_axis_plane_window():
+    # slabs along an OPEN z axis: the plane window of the end ranks is clipped (no wrap); OracleEngine.build asserts the promise
+    cell = np.diag([10.0, 10.0, 60.0])
+    X = U.rand_in_cell(1500, cell, seed=11)
+    parts = _check(3, X, cell, (True, True, False), 2.5)
+    assert all(int(p["axis"]) == 2 for p in parts)
