@@ -13,6 +13,7 @@
 #include "nl_tiled.cuh"
 #include "nl_mask.cuh"
 #include "nl_fillrows.cuh"
+#include "nl_fill2.cuh"
 #include "nl_access.cuh"
 
 namespace {
@@ -104,6 +105,9 @@ struct PairWs {
   unsigned long long* tsum;
   unsigned long long* total;
   void* tiled;  // tiled-kernel scratch (tile table, hit masks)
+  unsigned char* parkA;  // fill pass: parked row ends, 128 B per row (j head | j tail | S head | S tail)
+  unsigned char* parkR;  //            64 B per row (R head | R tail)
+  void* stamp;           // what nl_count_pairs left in this workspace (WsStamp); nl_fill_pairs* check it
   size_t total_bytes;
 };
 PairWs pair_ws(void* ws, const nl_params* prm, int64_t N) {
@@ -128,6 +132,9 @@ PairWs pair_ws(void* ws, const nl_params* prm, int64_t N) {
   w.tsum = (unsigned long long*)take((size_t)(scan_tiles((long long)n1) + 1) * 8);
   w.total = (unsigned long long*)take(256);
   w.tiled = take(tiled_scratch_bytes(prm, N));
+  w.parkA = (unsigned char*)take(n1 * PARK_A_BYTES);
+  w.parkR = (unsigned char*)take(n1 * PARK_R_BYTES);
+  w.stamp = take(256);
   w.total_bytes = o;
   return w;
 }
@@ -190,7 +197,8 @@ template <class T> Records<T> records_of(const PairWs& w) {
 enum { PATH_GENERIC = 0, PATH_TILED = 1, PATH_MASK = 2 };
 template <class T> struct Plan {
   int path;
-  TileShape ts_exact, ts_count, ts_fill;
+  TileShape ts_exact, ts_count, ts_fill, ts_fill2;
+  int fill2_ok;         // the 512-thread parked-boundary fill (nl_fill2.cuh) has a tile for this density
   MaskThresholds th;
   int lazy_ok;          // the packed counting kernel can serve the lazy sinks (count; LJ for Float32)
   TileShape ts_lazy;
@@ -205,6 +213,7 @@ template <class T, class TI> Plan<T> make_plan(const nl_params* p, const Geo<T>&
   pl.th_lazy = pl.th;
   pl.lazy_ok = 0;
   pl.ljf_ok = 0;
+  pl.fill2_ok = 0;
   if (N <= 0) return pl;
   if (!tiled_applicable<T>(p, g, N, tile_cap<T>(), pl.ts_exact)) return pl;
   pl.path = PATH_TILED;
@@ -223,6 +232,7 @@ template <class T, class TI> Plan<T> make_plan(const nl_params* p, const Geo<T>&
     pl.th = mask_thresholds(p->cell, p->ncells, pl.ts_count, (double)g.cutoff_sq);
     if (!pl.th.ok) return pl;
   }
+  pl.fill2_ok = pick_tile<T>(g, N, f2_cap<T, TI>(), pl.ts_fill2) ? 1 : 0;
   pl.path = PATH_MASK;
   return pl;
 }
@@ -234,6 +244,32 @@ inline bool fill_tiled_requested() {
   static int v = -1;
   if (v < 0) { const char* e = getenv("NL_FILL_ROWS"); v = (e && e[0] == '1') ? 0 : 1; }
   return v == 1;
+}
+
+// NL_FILL=legacy selects round 1's k_fill_mask (every element written in place by the mask expansion) for A/B measurements;
+// it is also what runs when an output pointer is not 32-byte aligned.
+// NL_FILL=park selects the experiment variant of the round-2 kernel that writes only complete sectors in place and parks the row
+// ends for k_fix_boundaries (nl_fill2.cuh; measured slower than the default: the parking costs more instructions than the
+// read-modify-writes it removes).
+inline int fill_variant() {  // 0 legacy k_fill_mask, 1 lean in-place k_fill_park<false> (default), 2 parked k_fill_park<true>
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NL_FILL"); v = !e ? 1 : (e[0] == 'l' ? 0 : (e[0] == 'p' ? 2 : 1)); }
+  return v;
+}
+
+// What nl_count_pairs leaves in the workspace for nl_fill_pairs* to check (include/nlcuda.h: NL_ERR_WORKSPACE).
+struct WsStamp {
+  unsigned long long magic;
+  long long N, nct;
+  unsigned long long total;
+  int float_type, int_type, flags, windowed;
+};
+constexpr unsigned long long WS_MAGIC = 0x4e4c57535f523032ull;  // "NLWS_R02"
+
+inline int fill_prefetch() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NL_FILL_PREFETCH"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v;
 }
 
 // Opt-in to > 48 KB of dynamic shared memory.  The attribute is per DEVICE, so the "done" flags are per device too
@@ -282,7 +318,7 @@ int apply_plane_window(MaskArgs<T, TI>& a, const uint8_t* plane_active, int* zl_
 // MODE_COUNT with want_mask (materialisation) or without (lazy count), MODE_FILL, MODE_LJ.
 template <class T, class TI, int MODE>
 int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, const Geo<T>& g, const Sinks<T, TI>& sk, bool want_mask,
-             cudaStream_t st) {
+             cudaStream_t st, unsigned long long total_pairs = 0) {
   if (N <= 0) return NL_OK;
   Records<T> rec = records_of<T>(w);
   const Plan<T> pl = make_plan<T, TI>(p, g, N);
@@ -307,7 +343,10 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
   } else if (pl.path == PATH_MASK && (MODE == MODE_COUNT || MODE == MODE_FILL)) {
     TiledScratch tsx = tiled_scratch(w.tiled, N);
     MaskArgs<T, TI> a;
-    mask_args<T, TI>(a, N, (const TI*)co, rec, g, sk, MODE == MODE_FILL ? pl.ts_fill : pl.ts_count, tsx.masks);
+    const bool out_aligned = MODE == MODE_FILL && (((uintptr_t)sk.io | (uintptr_t)sk.jo | (uintptr_t)sk.So | (uintptr_t)sk.Ro) & 31) == 0;
+    const int fvar = fill_variant();
+    const bool use_park = MODE == MODE_FILL && pl.fill2_ok && out_aligned && fvar != 0 && fill_tiled_requested();
+    mask_args<T, TI>(a, N, (const TI*)co, rec, g, sk, MODE == MODE_FILL ? (use_park ? pl.ts_fill2 : pl.ts_fill) : pl.ts_count, tsx.masks);
     a.cellflag = tsx.cellflag;
     a.mid = pl.th.mid; a.hw = pl.th.hw; a.dguard = pl.th.dguard;
     unsigned nblk = 0;
@@ -333,6 +372,25 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
       }
       NL_LAUNCH_CHECK();
       return NL_OK;
+    } else if (MODE == MODE_FILL && use_park) {
+      // round-2 fill: complete sectors in place + parked row ends (k_fill_park), boundary sectors in original row order
+      // (k_fix_boundaries), i stream from first[] alone (k_expand_rows)
+      static SmemOnce done, done_p;
+      int rc = fvar == 2 ? set_smem_once(k_fill_park<T, TI, true>, F2_SMEM_BYTES, done_p) : set_smem_once(k_fill_park<T, TI, false>, F2_SMEM_BYTES, done);
+      if (rc) return rc;
+      a.srow = w.srow;
+      k_row_starts<T, TI><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(w.pidx, sk.first, N, sk.n_rows, (typename FillBase<TI>::type*)w.srow);
+      NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
+      if (fvar == 2) {
+        k_fill_park<T, TI, true><<<nblk, F2_NT, F2_SMEM_BYTES, st>>>(a, w.parkA, w.parkR, 0);
+        k_fix_boundaries<T, TI><<<(unsigned)((sk.n_rows + 255) / 256), 256, 0, st>>>(sk.first, sk.n_rows, sk.jo, sk.So, sk.Ro, w.parkA, w.parkR);
+        NL_LAUNCHED(1);
+      } else {
+        k_fill_park<T, TI, false><<<nblk, F2_NT, F2_SMEM_BYTES, st>>>(a, nullptr, nullptr, fill_prefetch());
+      }
+      if (total_pairs > 0 && sk.n_rows > 0)
+        k_expand_rows<TI><<<(unsigned)((sk.n_rows + EXP_RB - 1) / EXP_RB), EXP_NT, 0, st>>>(sk.first, sk.n_rows, sk.gmap, sk.io);
+      NL_LAUNCHED(2);
     } else if (MODE == MODE_FILL) {
       static SmemOnce done;
       int rc = set_smem_once(k_fill_mask<T, TI>, FILL_SMEM_BYTES, done);
@@ -389,6 +447,10 @@ int count_pairs_impl(const nl_params* p, const void* Xs, int64_t N, const void* 
   NL_CUDA(cudaStreamSynchronize(st));
   *total_host = (int64_t)total;
   if (sizeof(TI) == 4 && total + 1 > 2147483647ull) return NL_ERR_OVERFLOW;
+  if (N > 0) {
+    WsStamp s = {WS_MAGIC, (long long)N, (long long)g.nct, total, p->float_type, p->int_type, p->reserved[0], plane_active ? 1 : 0};
+    NL_CUDA(cudaMemcpyAsync(w.stamp, &s, sizeof(s), cudaMemcpyHostToDevice, st));  // pageable source: staged before the call returns
+  }
   return NL_OK;
 }
 
@@ -403,13 +465,20 @@ int fill_pairs_impl(const nl_params* p, int64_t N, const void* co, const void* f
   sk.n_rows = n_rows; sk.gmap = (const TI*)gmap;
   sk.half = p->reserved[0] & NL_FLAG_HALF;
   sk.plane_active = plane_active;
+  // the workspace must be the one nl_count_pairs filled for this very problem (masks, counts, records live in it)
+  WsStamp s = {};
+  NL_CUDA(cudaMemcpyAsync(&s, w.stamp, sizeof(s), cudaMemcpyDeviceToHost, st));
+  NL_CUDA(cudaStreamSynchronize(st));
+  if (s.magic != WS_MAGIC || s.N != (long long)N || s.nct != (long long)g.nct || s.float_type != p->float_type || s.int_type != p->int_type ||
+      s.flags != p->reserved[0] || s.windowed != (plane_active ? 1 : 0))
+    return NL_ERR_WORKSPACE;
   if (gmap && N > 0) {
     k_make_pgid<TI><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(w.pidx, (const TI*)gmap, N, w.pgid0);
     NL_LAUNCHED(1);
     NL_LAUNCH_CHECK();
     sk.pgid0 = w.pgid0;
   }
-  return traverse<T, TI, MODE_FILL>(p, N, co, w, g, sk, true, st);
+  return traverse<T, TI, MODE_FILL>(p, N, co, w, g, sk, true, st, s.total);
 }
 
 template <class TI> __global__ void k_counts_to_ti(const uint32_t* __restrict__ c, long long n, TI* __restrict__ out) {
