@@ -51,12 +51,14 @@ def hbm_peak():
         return FALLBACK_HBM_GBS, "fallback"
 
 
-def fill_traffic(n_atoms):
-    """dram__bytes_read + dram__bytes_write of one fill launch, from the committed ncu capture (10 M-atom workload only)."""
+def fill_traffic_profiled(n_atoms, world):
+    """dram__bytes_read + dram__bytes_write of one fill launch from the COMMITTED ncu capture of this build (profiles/).  It is a
+    citation of that capture, not a measurement of this run, so it is reported beside `roofline.traffic` (null), never as it."""
+    if n_atoms != 10_000_000 or world != 1:
+        return None
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_fill_traffic.json")) as f:
-            t = json.load(f)
-        return t["traffic_bytes_per_launch"] if n_atoms == 10_000_000 else None
+        with open(os.path.join(ROOT, "profiles", "r02_fill_traffic.json")) as f:
+            return json.load(f)
     except Exception:
         return None
 
@@ -110,37 +112,61 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def cpu_baseline_run(n_atoms, steps, warmup):
+def host_threads():
+    """Threads the CPU arm may use: every core this process is allowed on.  torchrun exports OMP_NUM_THREADS=1 to its
+    workers, which is not a statement about the machine, so the count is passed to the oracle explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_baseline_run(n_atoms, steps, warmup, cores=None):
     """The oracle (a C++ restatement of the reference's sort-based CPU path: serial binning / sort /
     offsets, count + fill parallel over atoms like the KA CPU backend) with every host thread."""
     from oracle import nl_oracle as O
     X, C, L = make_positions(n_atoms, SEED)
-    cores = O.max_threads()
+    cores = cores or host_threads()
     times, P = [], 0
     for s in range(warmup + steps):
         t = time.perf_counter()
         r = O.sortbased(X, CUTOFF, C, (True, True, True), nthreads=cores, want_R=False)
         dt = time.perf_counter() - t
         P = r["npairs"]
+        del r
         if s >= warmup:
             times.append(dt)
     return P, times, cores
+
+
+def pick_cpu_atoms(requested, steps, warmup, budget_s, cores):
+    """Largest workload of the headline ladder whose (warmup + steps) runs fit `budget_s` seconds of CPU time, estimated
+    from one 500 k-atom probe (the path is linear in N at fixed density)."""
+    _, t, _ = cpu_baseline_run(500_000, 1, 1, cores)
+    per_atom = 1.5 * t[0] / 500_000   # larger workloads run somewhat slower per atom (cache misses of the random gathers)
+    for n in (10_000_000, 5_000_000, 2_000_000, 1_000_000, 500_000):
+        if n <= requested and per_atom * n * (steps + warmup) <= budget_s:
+            return n
+    return min(requested, 200_000)
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.cpu_atoms
-    P, times, cores = cpu_baseline_run(n, args.steps, min(args.warmup, 1))
+    cores = host_threads()
+    n = args.cpu_atoms if args.cpu_atoms > 0 else pick_cpu_atoms(args.atoms, args.steps, args.warmup, args.cpu_budget, cores)
+    P, times, cores = cpu_baseline_run(n, args.steps, args.warmup, cores)
     ms = 1e3 * float(np.mean(times))
     val = P / (ms * 1e-3)
+    same = n == args.atoms
     sample = f"{n} atoms, rho={DENSITY}, rc={CUTOFF}, pbc TTT, Float64/Int32, seed {SEED} ({P} pairs per step)"
     print(json.dumps({
         "impl": "reference", "metric": "neighbour pairs/s (build_cell_list + materialize_pairlist)", "value": val, "unit": "pairs/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": ms, "higher_is_better": True,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"headline density/cutoff on a bounded CPU sample: {sample}",
+        "config": {"workload": ("the headline workload: " if same else "headline density / cutoff on the largest CPU sample that fits the time budget: ") + sample,
+                   "same_workload_as_gpu_arm": same, "cpu_budget_s": args.cpu_budget,
                    "note": "C++/OpenMP restatement of the reference's CPU path (oracle/); Julia is not installed so julia -t N cannot run"},
         "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -300,7 +326,7 @@ def run_ours(args):
                        "step_roofline": {"bytes": step_bytes, "formula": "24 N + 48 P", "gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,
                                          "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak}},
             "roofline": {"bound": "hbm", "kernel": "pair fill (nl_fill_pairs: k_fill_mask)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": fill_traffic(n_atoms), "peak_source": which,
+                         "frac": achieved / peak, "traffic": None, "traffic_profiled": fill_traffic_profiled(n_atoms, world), "peak_source": which,
                          "bytes_per_launch": fill_bytes, "formula": "44 P + 36 N"},
             "e2e": {"value": P_total / (e2e_ms * 1e-3), "unit": "pairs/s",
                     "h2d_bytes_per_step": int(X_host.numel() * 8 + (0 if world == 1 else n_atoms * 8)),
@@ -310,9 +336,10 @@ def run_ours(args):
             "clocks": clocks,
         }
         if world == 1 and not args.no_cpu_baseline:
-            Pc, times, cores = cpu_baseline_run(args.cpu_atoms, 1, 1)
+            n_cpu = args.cpu_atoms if args.cpu_atoms > 0 else 1_000_000
+            Pc, times, cores = cpu_baseline_run(n_cpu, 1, 1)
             out["cpu_baseline"] = {"value": Pc / float(np.mean(times)), "unit": "pairs/s", "cores": cores, "kind": "port",
-                                   "sample": f"{args.cpu_atoms} atoms of the same workload ({Pc} pairs), C++/OpenMP restatement of the "
+                                   "sample": f"{n_cpu} atoms of the same workload ({Pc} pairs), C++/OpenMP restatement of the "
                                              "reference CPU path (not Julia)"}
         print(json.dumps(out))
     if world > 1:
@@ -326,7 +353,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--atoms", type=int, default=10_000_000)
-    ap.add_argument("--cpu-atoms", type=int, default=1_000_000)
+    ap.add_argument("--cpu-atoms", type=int, default=0,
+                    help="atoms of the CPU arm (0: --impl reference takes the largest headline-ladder size that fits --cpu-budget; "
+                         "the cpu_baseline leg of the GPU arm uses 1 M)")
+    ap.add_argument("--cpu-budget", type=float, default=200.0, help="seconds of CPU time the reference arm may spend in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

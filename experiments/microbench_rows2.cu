@@ -247,7 +247,12 @@ __global__ void __launch_bounds__(256) k_rows_prefetch(const int* __restrict__ f
       const bool partial = (lane & 1) ? (B1 & 31) != 0 : (B0 & 31) != 0;
       if (partial) {
         if (HOW == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + a));
-        else { unsigned tmp; asm volatile("ld.global.cg.b32 %0, [%1];" : "=r"(tmp) : "l"(base + a)); }   // one 32-byte sector
+        else if (HOW == 1) { unsigned tmp; asm volatile("ld.global.cg.b32 %0, [%1];" : "=r"(tmp) : "l"(base + a)); }   // one 32-byte sector
+        else if (HOW == 2) { unsigned tmp; asm volatile("ld.global.cg.L2::64B.b32 %0, [%1];" : "=r"(tmp) : "l"(base + a)); }
+        else if (HOW == 3) { unsigned tmp; asm volatile("ld.global.cg.L2::128B.b32 %0, [%1];" : "=r"(tmp) : "l"(base + a)); }
+        else if (HOW == 4) { asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(base + a)); }
+        else if (HOW == 5) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], 32;" ::"l"(base + a)); }
+        else if (HOW == 6) { asm volatile("cp.async.bulk.prefetch.L2.global [%0], 64;" ::"l"(base + (a & ~63ll))); }
       }
     }
   };
@@ -422,8 +427,16 @@ int main(int argc, char** argv) {
     printf("%-64s %7.3f ms\n", mode ? "RANDOM rows, scalar in place + L2 prefetch one row AHEAD" : "sequential rows, scalar in place + L2 prefetch one row AHEAD", t);
     t = time_best([&] { k_rows_prefetch<false, 1><<<148 * 8, 256>>>(d_first, ord, n, o); });
     printf("%-64s %7.3f ms\n", mode ? "RANDOM rows, scalar in place + ld.cg of boundary sectors" : "sequential rows, scalar in place + ld.cg of boundary sectors", t);
-    t = time_best([&] { k_rows_prefetch<true, 1><<<148 * 8, 256>>>(d_first, ord, n, o); });
-    printf("%-64s %7.3f ms\n", mode ? "RANDOM rows, scalar in place + ld.cg one row AHEAD" : "sequential rows, scalar in place + ld.cg one row AHEAD", t);
+    t = time_best([&] { k_rows_prefetch<false, 2><<<148 * 8, 256>>>(d_first, ord, n, o); });
+    printf("%-64s %7.3f ms\n", mode ? "RANDOM rows, scalar in place + ld.cg.L2::64B of boundary sectors" : "sequential rows, + ld.cg.L2::64B", t);
+    t = time_best([&] { k_rows_prefetch<false, 3><<<148 * 8, 256>>>(d_first, ord, n, o); });
+    printf("%-64s %7.3f ms\n", mode ? "RANDOM rows, scalar in place + ld.cg.L2::128B of boundary sectors" : "sequential rows, + ld.cg.L2::128B", t);
+    t = time_best([&] { k_rows_prefetch<false, 5><<<148 * 8, 256>>>(d_first, ord, n, o); });
+    printf("%-64s %7.3f ms\n", mode ? "RANDOM rows, scalar in place + cp.async.bulk.prefetch.L2 32 B" : "sequential rows, + bulk prefetch 32 B", t);
+    t = time_best([&] { k_rows_prefetch<false, 6><<<148 * 8, 256>>>(d_first, ord, n, o); });
+    printf("%-64s %7.3f ms\n", mode ? "RANDOM rows, scalar in place + cp.async.bulk.prefetch.L2 64 B" : "sequential rows, + bulk prefetch 64 B", t);
+    t = time_best([&] { k_rows_prefetch<false, 4><<<148 * 8, 256>>>(d_first, ord, n, o); });
+    printf("%-64s %7.3f ms\n", mode ? "RANDOM rows, scalar in place + prefetch.L2::evict_last" : "sequential rows, + prefetch.L2::evict_last", t);
   }
   // correctness of the park + fix-up scheme (both store styles) and of the cp_mask variant
   for (int variant = 0; variant < 3; variant++) {

@@ -176,14 +176,18 @@ __global__ void __launch_bounds__(256) k_lazy_neighbours(const T* __restrict__ X
 // Two-launch reductions over the atoms (partials in caller scratch, then one block).
 constexpr int RED_BLOCKS = 592;  // 4 x 148 SMs
 
+// min / max that PROPAGATE NaN, like Julia's minimum / maximum (a NaN position must not pass for a valid bounding box or
+// for "nothing moved": the host then sees NaN and raises / rebuilds)
+template <class T> __device__ __forceinline__ T nan_max(T a, T b) { return a != a ? a : (b != b ? b : (b > a ? b : a)); }
+template <class T> __device__ __forceinline__ T nan_min(T a, T b) { return a != a ? a : (b != b ? b : (b < a ? b : a)); }
 template <class T> __device__ __forceinline__ T warp_min(T v) {
 #pragma unroll
-  for (int o = 16; o; o >>= 1) { const T t = __shfl_xor_sync(0xffffffffu, v, o); v = t < v ? t : v; }
+  for (int o = 16; o; o >>= 1) { const T t = __shfl_xor_sync(0xffffffffu, v, o); v = nan_min(v, t); }
   return v;
 }
 template <class T> __device__ __forceinline__ T warp_max(T v) {
 #pragma unroll
-  for (int o = 16; o; o >>= 1) { const T t = __shfl_xor_sync(0xffffffffu, v, o); v = t > v ? t : v; }
+  for (int o = 16; o; o >>= 1) { const T t = __shfl_xor_sync(0xffffffffu, v, o); v = nan_max(v, t); }
   return v;
 }
 
@@ -198,7 +202,7 @@ template <class T> __device__ __forceinline__ void block_minmax3(T mn[3], T mx[3
     T v = sm[0][threadIdx.x];
     for (int q = 1; q < (int)(blockDim.x >> 5); q++) {
       const T t = sm[q][threadIdx.x];
-      v = threadIdx.x < 3 ? (t < v ? t : v) : (t > v ? t : v);
+      v = threadIdx.x < 3 ? nan_min(v, t) : nan_max(v, t);
     }
     part[threadIdx.x] = v;
   }
@@ -213,8 +217,8 @@ template <class T> __global__ void __launch_bounds__(256) k_bbox_partial(const T
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       const T v = X[3 * i + k];
-      mn[k] = v < mn[k] ? v : mn[k];
-      mx[k] = v > mx[k] ? v : mx[k];
+      mn[k] = nan_min(mn[k], v);
+      mx[k] = nan_max(mx[k], v);
     }
   }
   block_minmax3(mn, mx, part + 6 * blockIdx.x);
@@ -225,8 +229,8 @@ template <class T> __global__ void __launch_bounds__(256) k_bbox_final(const T* 
   for (int b = threadIdx.x; b < nb; b += blockDim.x)
     for (int k = 0; k < 3; k++) {
       const T a = part[6 * b + k], c = part[6 * b + 3 + k];
-      mn[k] = a < mn[k] ? a : mn[k];
-      mx[k] = c > mx[k] ? c : mx[k];
+      mn[k] = nan_min(mn[k], a);
+      mx[k] = nan_max(mx[k], c);
     }
   block_minmax3(mn, mx, out);
 }
@@ -238,26 +242,26 @@ __global__ void __launch_bounds__(256) k_maxdisp_partial(const T* __restrict__ X
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const T dx = sub_rn(X[3 * i], Y[3 * i]), dy = sub_rn(X[3 * i + 1], Y[3 * i + 1]), dz = sub_rn(X[3 * i + 2], Y[3 * i + 2]);
     const T d2 = add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
-    m = d2 > m ? d2 : m;
+    m = nan_max(m, d2);
   }
   m = warp_max(m);
   __shared__ T sm[8];
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int k = 1; k < (int)(blockDim.x >> 5); k++) m = sm[k] > m ? sm[k] : m;
+    for (int k = 1; k < (int)(blockDim.x >> 5); k++) m = nan_max(m, sm[k]);
     part[blockIdx.x] = m;
   }
 }
 template <class T> __global__ void __launch_bounds__(256) k_max_final(const T* __restrict__ part, int nb, T* __restrict__ out) {
   T m = 0;
-  for (int b = threadIdx.x; b < nb; b += blockDim.x) m = part[b] > m ? part[b] : m;
+  for (int b = threadIdx.x; b < nb; b += blockDim.x) m = nan_max(m, part[b]);
   m = warp_max(m);
   __shared__ T sm[8];
   if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
   __syncthreads();
   if (threadIdx.x == 0) {
-    for (int k = 1; k < (int)(blockDim.x >> 5); k++) m = sm[k] > m ? sm[k] : m;
+    for (int k = 1; k < (int)(blockDim.x >> 5); k++) m = nan_max(m, sm[k]);
     out[0] = m;
   }
 }

@@ -21,6 +21,12 @@ inline std::atomic<long long>& launch_counter() {
 }
 inline void note_launch(int n = 1) { launch_counter().fetch_add(n, std::memory_order_relaxed); }
 
+// Last cudaError_t seen by this thread's library calls (nl_last_cuda_error()).
+inline int& last_cuda_slot() {
+  thread_local int e = 0;
+  return e;
+}
+
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }

@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(F2_NT, 2) k_fill_park(const MaskArgs<T, TI> a,
         if (sub >= o) incl += t;
       }
       const int my_nhit = __shfl_sync(FULL, incl, 7, 8);
-      if (!PARK && prefetch && my_nhit > 0 && sub < (has_R ? 6 : 4)) {
+      if (!PARK && prefetch && my_nhit > 0 && sub < (has_R ? 6 : 4) && sub >= (prefetch >= 3 ? (prefetch == 3 ? 4 : 2) : 0)) {  // 3: R only, 4: S and R (experiments)
         // In place, the partial 32-byte sectors at both ends of a row segment are shared with the neighbouring rows, which
         // other warps write at other times: evicted half-written, each costs a DRAM read-modify-write.  Prefetching them
         // into L2 now makes the partial write land on a fully valid sector, which is later written back whole
@@ -312,7 +312,11 @@ __global__ void __launch_bounds__(F2_NT, 2) k_fill_park(const MaskArgs<T, TI> a,
         const long long eb = st == 0 ? (long long)sizeof(TI) : (st == 1 ? 3ll * sizeof(TI) : 3ll * sizeof(T));
         const char* gb = st == 0 ? (const char*)a.out.jo : (st == 1 ? (const char*)a.out.So : (const char*)a.out.Ro);
         const long long B = ((long long)my_base + ((sub & 1) ? my_nhit : 0)) * eb;
-        if (B & 31) asm volatile("prefetch.global.L2 [%0];" ::"l"(gb + ((sub & 1) ? ((B - 1) & ~31ll) : (B & ~31ll))));
+        if (B & 31) {
+          const char* sec = gb + ((sub & 1) ? ((B - 1) & ~31ll) : (B & ~31ll));
+          if (prefetch == 2) asm volatile("cp.async.bulk.prefetch.L2.global [%0], 32;" ::"l"(sec));  // exactly the sector, but issued lane by lane
+          else asm volatile("prefetch.global.L2 [%0];" ::"l"(sec));                                  // one instruction, fetches the 128-byte line
+        }
       }
       __syncwarp();
       {

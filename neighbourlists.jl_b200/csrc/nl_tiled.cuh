@@ -310,10 +310,13 @@ inline int tiled_traverse(const nl_params*, int64_t n, const TI* co, const Recor
                           const TileShape& ts, void*, cudaStream_t st) {
   static bool attr_set[64] = {};  // per device: the attribute belongs to the device's instance of the kernel
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return NL_ERR_CUDA;
+  {
+    cudaError_t e0 = cudaGetDevice(&dev);
+    if (e0 != cudaSuccess) { last_cuda_slot() = (int)e0; return NL_ERR_CUDA; }
+  }
   if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     cudaError_t e = cudaFuncSetAttribute(k_tiled<T, TI, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TILE_SMEM_BYTES);
-    if (e != cudaSuccess) return NL_ERR_CUDA;
+    if (e != cudaSuccess) { last_cuda_slot() = (int)e; return NL_ERR_CUDA; }
     if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   TiledArgs<T, TI> a;

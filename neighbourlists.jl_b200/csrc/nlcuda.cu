@@ -20,12 +20,11 @@ namespace {
 
 using namespace nl;
 
-thread_local int g_last_cuda = 0;
 
 static_assert(sizeof(nl_params) == 192, "nl_params layout is part of the ABI");
 
 inline int cuda_fail(cudaError_t e) {
-  g_last_cuda = (int)e;
+  last_cuda_slot() = (int)e;
   return NL_ERR_CUDA;
 }
 #define NL_CUDA(expr)                          \
@@ -102,6 +101,7 @@ struct PairWs {
   void* ra;
   void* srow;  // fill pass: 0-based row start of every SORTED atom (all ones: no row), TI-wide
   int* zlayers; // tile layers along z that a windowed (slab shard) call launches
+  uint8_t* planes;  // device copy of the caller's plane_active promise (checked against cell_offsets)
   unsigned long long* tsum;
   unsigned long long* total;
   void* tiled;  // tiled-kernel scratch (tile table, hit masks)
@@ -129,6 +129,7 @@ PairWs pair_ws(void* ws, const nl_params* prm, int64_t N) {
   w.ra = take(n1 * 32);
   w.srow = take(n1 * 8);
   w.zlayers = (int*)take(((size_t)prm->ncells[2] + 1) * 4);
+  w.planes = (uint8_t*)take((size_t)prm->ncells[2]);
   w.tsum = (unsigned long long*)take((size_t)(scan_tiles((long long)n1) + 1) * 8);
   w.total = (unsigned long long*)take(256);
   w.tiled = take(tiled_scratch_bytes(prm, N));
@@ -268,7 +269,7 @@ constexpr unsigned long long WS_MAGIC = 0x4e4c57535f523032ull;  // "NLWS_R02"
 
 inline int fill_prefetch() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("NL_FILL_PREFETCH"); v = (e && e[0] == '0') ? 0 : 1; }
+  if (v < 0) { const char* e = getenv("NL_FILL_PREFETCH"); v = !e ? 1 : (e[0] >= '0' && e[0] <= '4' ? e[0] - '0' : 1); }
   return v;
 }
 
@@ -422,12 +423,20 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
   return NL_OK;
 }
 
+// Windowed calls: the caller promises that every z plane of cells it did not mark active is empty.  A broken promise would
+// leave atoms without counts (their tile layers are never launched), so it is checked against cell_offsets: flag = 1.
+template <class TI>
+__global__ void k_check_planes(const TI* __restrict__ co, long long nxy, int nz, const uint8_t* __restrict__ active, unsigned long long* __restrict__ flag) {
+  const int z = blockIdx.x * blockDim.x + threadIdx.x;
+  if (z < nz && !active[z] && co[(long long)(z + 1) * nxy] != co[(long long)z * nxy]) *flag = 1ull;
+}
+
 template <class T, class TI>
 int count_pairs_impl(const nl_params* p, const void* Xs, int64_t N, const void* perm, const void* co, void* first, int64_t* total_host,
                      void* ws, const uint8_t* plane_active, cudaStream_t st) {
   Geo<T> g = make_geo<T>(p);
   PairWs w = pair_ws(ws, p, N);
-  unsigned long long total = 0;
+  unsigned long long tot2[2] = {0, 0};   // pair total | "plane_active promise broken" flag
   if (N > 0) {
     int rc = prep_impl<T, TI>(p, Xs, N, perm, w, g, st);
     if (rc) return rc;
@@ -435,17 +444,26 @@ int count_pairs_impl(const nl_params* p, const void* Xs, int64_t N, const void* 
     sk.counts = w.counts;
     sk.half = p->reserved[0] & NL_FLAG_HALF;
     sk.plane_active = plane_active;
+    NL_CUDA(cudaMemsetAsync(w.total, 0, 16, st));
+    if (plane_active) {
+      NL_CUDA(cudaMemsetAsync(w.counts, 0, (size_t)N * 4, st));  // atoms outside the launched layers (there must be none) count zero
+      NL_CUDA(cudaMemcpyAsync(w.planes, plane_active, (size_t)g.nc[2], cudaMemcpyHostToDevice, st));
+      k_check_planes<TI><<<(unsigned)((g.nc[2] + 255) / 256), 256, 0, st>>>((const TI*)co, (long long)g.nc[0] * g.nc[1], g.nc[2], w.planes, w.total + 1);
+      NL_LAUNCHED(1);
+    }
     rc = traverse<T, TI, MODE_COUNT>(p, N, co, w, g, sk, true, st);
     if (rc) return rc;
     exclusive_scan<uint32_t, unsigned long long, TI>(w.counts, N, (TI*)first, 1ull, true, w.tsum, w.total, st);
     NL_LAUNCH_CHECK();
-    NL_CUDA(cudaMemcpyAsync(&total, w.total, sizeof(total), cudaMemcpyDeviceToHost, st));
+    NL_CUDA(cudaMemcpyAsync(tot2, w.total, sizeof(tot2), cudaMemcpyDeviceToHost, st));
   } else {
     TI one = 1;
     NL_CUDA(cudaMemcpyAsync(first, &one, sizeof(TI), cudaMemcpyHostToDevice, st));
   }
   NL_CUDA(cudaStreamSynchronize(st));
+  const unsigned long long total = tot2[0];
   *total_host = (int64_t)total;
+  if (tot2[1]) return NL_ERR_BAD_ARG;  // atoms in a cell plane the caller declared empty
   if (sizeof(TI) == 4 && total + 1 > 2147483647ull) return NL_ERR_OVERFLOW;
   if (N > 0) {
     WsStamp s = {WS_MAGIC, (long long)N, (long long)g.nct, total, p->float_type, p->int_type, p->reserved[0], plane_active ? 1 : 0};
@@ -620,7 +638,7 @@ const char* nl_strerror(int code) {
   }
 }
 
-int nl_last_cuda_error(void) { return g_last_cuda; }
+int nl_last_cuda_error(void) { return nl::last_cuda_slot(); }
 
 long long nl_launch_count(void) { return nl::launch_counter().load(); }
 

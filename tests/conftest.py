@@ -13,7 +13,12 @@ def pytest_configure(config):
 
 def pytest_sessionstart(session):
     """The shared library is a build artefact (git-ignored): compile it once if a fresh checkout lacks it.
-    (nvcc cross-compiles sm_100a without a GPU; on the GPU box the prebuilt .so travels with the snapshot.)"""
+    (nvcc cross-compiles sm_100a without a GPU; on the GPU box the prebuilt .so travels with the snapshot.)
+    A checkout without nvcc still runs the tests that do not need the library (oracle KATs, golden vectors, gloo sharding):
+    the build failure is reported once and the ABI / GPU tests then fail on their own import of the library."""
     so = os.path.join(ROOT, "neighbourlists.jl_b200", "libnlcuda.so")
     if not os.path.exists(so):
-        subprocess.check_call(["bash", os.path.join(ROOT, "neighbourlists.jl_b200", "csrc", "build.sh")])
+        try:
+            subprocess.check_call(["bash", os.path.join(ROOT, "neighbourlists.jl_b200", "csrc", "build.sh")])
+        except (OSError, subprocess.CalledProcessError) as e:
+            print(f"[conftest] could not build libnlcuda.so ({e}); tests that load it will fail", file=sys.stderr)

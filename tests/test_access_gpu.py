@@ -310,3 +310,17 @@ def test_lazy_neighbours_rows_in_reference_order(nl, dtype, int_type):
         assert cl._pl is None, "no pair list was materialised"
     with pytest.raises(IndexError):
         nl.neighbours_padded(cl, [0], 4)
+
+
+def test_reductions_propagate_nan(nl):
+    """maximum / minimum in the reference propagate NaN (ext/NeighbourListsAtomsBaseExt.jl:17-31); so do the device
+    reductions: a NaN position must neither pass for a valid bounding box nor for "nothing moved" (SkinList then rebuilds)."""
+    import torch
+    X, C, L = U.rand_config(3000, seed=5)
+    Xd = torch.from_numpy(X).cuda()
+    Y = Xd.clone()
+    Y[1234, 1] = float("nan")
+    assert np.isnan(nl.max_displacement2(Y, Xd).cpu().numpy()[0])
+    assert not np.isnan(nl.max_displacement2(Xd, Xd).cpu().numpy()[0])
+    bb = nl.bounding_box(Y).cpu().numpy()   # (min x, min y, min z, max x, max y, max z)
+    assert np.isnan(bb[1]) and np.isnan(bb[4]) and not np.isnan(bb[0]) and not np.isnan(bb[5])

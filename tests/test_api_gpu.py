@@ -80,3 +80,53 @@ def test_host_inputs_and_errors(nl):
         nl.neighbour_list(torch.zeros((5, 3), dtype=torch.float16).cuda(), 1.0, C, (True, True, True))
     with pytest.raises(nl.NlError):
         nl.build_cell_list(torch.from_numpy(X).cuda(), 1e-4, C * 1000, (True, True, True))  # too many cells for Int32
+
+
+def test_fill_rejects_a_workspace_count_did_not_stamp():
+    """include/nlcuda.h: nl_fill_pairs* return NL_ERR_WORKSPACE when the workspace is not the one nl_count_pairs filled for
+    this very problem (the hit masks, counts and records of the count pass live in it)."""
+    import ctypes as C
+    import torch
+    import neighbourlists_jl_b200 as nl
+    from neighbourlists_jl_b200 import _lib, api
+    X, cell, _ = U.rand_config(5000, seed=11)
+    clist = nl.build_cell_list(torch.from_numpy(X).cuda(), 5.0, cell, (True, True, True))
+    pl = nl.materialize_pairlist(clist)          # a good list, for the sizes
+    L = _lib.lib()
+    N, P = clist.X.shape[0], nl.npairs(pl)
+    dev = clist.X.device
+    need = L.nl_workspace_bytes(clist.params, N, _lib.NL_STAGE_PAIRS)
+    i = torch.empty(P, dtype=torch.int32, device=dev)
+    j = torch.empty(P, dtype=torch.int32, device=dev)
+    S = torch.empty((P, 3), dtype=torch.int32, device=dev)
+
+    def fill(ws, params=clist.params, n=N):
+        return L.nl_fill_pairs(params, api._ptr(clist.X), n, api._ptr(clist.perm), api._ptr(clist.cell_offsets), api._ptr(pl.first),
+                               api._ptr(i), api._ptr(j), api._ptr(S), None, api._ptr(ws), ws.numel(), api._stream(dev))
+
+    fresh = torch.zeros(need, dtype=torch.uint8, device=dev)          # never seen by nl_count_pairs
+    assert fill(fresh) == _lib.NL_ERR_WORKSPACE
+    assert fill(clist._ws) == _lib.NL_OK                                # the stamped one works (and again: fill is repeatable)
+    torch.cuda.synchronize()
+    assert torch.equal(i, pl.i) and torch.equal(j, pl.j) and torch.equal(S, pl.S)
+    half = type(clist.params).from_buffer_copy(clist.params)           # same workspace, different problem (half-list flag)
+    half.reserved[0] = _lib.NL_FLAG_HALF
+    assert fill(clist._ws, params=half) == _lib.NL_ERR_WORKSPACE
+
+
+def test_window_promise_is_checked():
+    """nl_count_pairs_window: atoms in a z plane of cells the caller declared empty -> NL_ERR_BAD_ARG, not a silently
+    wrong list."""
+    import torch
+    import neighbourlists_jl_b200 as nl
+    X, cell, _ = U.rand_config(20000, seed=12)
+    clist = nl.build_cell_list(torch.from_numpy(X).cuda(), 5.0, cell, (True, True, True))
+    nz = int(clist.ncells[2])
+    ok = np.ones(nz, dtype=np.uint8)
+    pl = nl.materialize_pairlist(clist, plane_active=ok)
+    ref = nl.materialize_pairlist(clist)
+    assert torch.equal(pl.first, ref.first)
+    bad = ok.copy()
+    bad[nz // 2] = 0                                                    # that plane is full of atoms
+    with pytest.raises(nl.NlError):
+        nl.materialize_pairlist(clist, plane_active=bad)
