@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define NL_VERSION 100 /* 0.1.0 */
+#define NL_VERSION 200 /* 0.2.0 */
 
 #if defined(__GNUC__)
 #define NL_API __attribute__((visibility("default")))
@@ -50,7 +50,8 @@ enum {
   NL_ERR_WORKSPACE = -2,   /* ws too small / misaligned, or fill called with a ws count did not stamp */
   NL_ERR_CUDA = -3,        /* a CUDA call failed; nl_last_cuda_error() holds the cudaError_t          */
   NL_ERR_OVERFLOW = -4,    /* pair count does not fit int_type (reference: silent Int32 wrap)         */
-  NL_ERR_UNSUPPORTED = -5  /* N or prod(ncells) >= 2^31 - 1 (keys are 32-bit internally)              */
+  NL_ERR_UNSUPPORTED = -5, /* N or prod(ncells) >= 2^31 - 1 (keys are 32-bit internally)              */
+  NL_ERR_NCCL = -6         /* NCCL is not loadable in this process, or an NCCL call failed            */
 };
 
 /* Geometry of one neighbour-list problem, filled by the caller.
@@ -148,6 +149,53 @@ NL_API int nl_cell_ids(const nl_params* params, const void* X, int64_t N, void* 
  * halo = nxyz of the slab axis; every slab gets at least 2*halo+1 planes (1 if nranks == 1).
  * bounds_out[nranks+1]: rank r owns planes [bounds[r], bounds[r+1]).  NL_ERR_BAD_ARG if the planes do not suffice. */
 NL_API int nl_shard_plan(const int64_t* plane_hist, int32_t nplanes, int32_t nranks, int32_t halo, int64_t* bounds_out);
+
+/* ---- Multi-GPU: 1-D slabs of whole cell planes with a cutoff-wide halo.  One process per GPU; the reference has
+ * no multi-GPU code.  The slab axis is the axis with the most cells (ties: z, the slowest key axis) of the reference's OWN
+ * cell grid (src/cell_list.jl:83-86, widths :94-95), so the unchanged single-GPU stages run on every rank's local set with the
+ * GLOBAL params.  Call sequence per list (all on `stream`, the current device being this rank's GPU):
+ *     nl_shard_prepare   -> info (host): slab bounds, n_owned, halo sizes, every send / receive count.  ONE host read.
+ *     caller allocates X_all, gidx_all with info.n_owned + info.n_halo_dn + info.n_halo_up rows
+ *     nl_shard_exchange  -> X_all / gidx_all = [owned atoms | halo from the rank below | halo from the rank above]
+ *     nl_build_cells(X_all) ; nl_count_pairs_window ; nl_fill_pairs_window(n_rows = info.n_owned, index_map = gidx_all)
+ * Each rank then holds the CSR rows of its owned atoms with GLOBAL i / j and global shifts S; concatenating the ranks' rows by
+ * global i reproduces the single-device list.  `comm` is an ncclComm_t of the NCCL instance loaded in this process (bound with
+ * dlopen at first use: libnlcuda.so itself does not link NCCL); nl_nccl_* below create one when the host has none. */
+#define NL_MAX_RANKS 64
+typedef struct nl_shard_info {
+  int32_t axis, halo, periodic, nranks, rank, nplanes; /* slab axis, halo width in planes (= nxyz[axis]), pbc[axis], ... */
+  int32_t has_dn, has_up, dn_peer, up_peer;             /* neighbours along the slab axis (ring if periodic)             */
+  int64_t n_local;                /* atoms this rank passed in                                                            */
+  int64_t n_owned;                /* atoms of its slab after the redistribution                                           */
+  int64_t n_halo_dn, n_halo_up;   /* halo atoms it receives from the rank below / above                                   */
+  int64_t n_send_dn, n_send_up;   /* owned atoms it sends as halo to the rank below / above                               */
+  int64_t bounds[NL_MAX_RANKS + 1];    /* rank r owns planes [bounds[r], bounds[r+1])                                     */
+  int64_t send_count[NL_MAX_RANKS];    /* local atoms owned by rank d (send_count[rank]: atoms that stay)                 */
+  int64_t recv_count[NL_MAX_RANKS];    /* atoms rank s holds that this rank owns                                          */
+} nl_shard_info;
+
+/* Scratch for nl_shard_prepare / nl_shard_exchange with at most n_max atoms on either side of the redistribution
+ * (n_max >= max(n_local, info.n_owned)). */
+NL_API size_t nl_shard_workspace_bytes(const nl_params* params, int64_t n_max, int32_t nranks);
+
+/* Bins the n local atoms (X: n x 3 T, ANY subset of the system per rank) to cell planes of the slab axis, all-gathers the
+ * per-rank plane histograms and plans the slabs (nl_shard_plan: balanced by atom count, >= 2 * halo + 1 planes each).
+ * Synchronises `stream` once.  NL_ERR_BAD_ARG when the planes do not suffice for nranks slabs (use fewer ranks / replicas). */
+NL_API int nl_shard_prepare(const nl_params* params, const void* X, int64_t n, void* comm, int32_t rank, int32_t nranks,
+                            nl_shard_info* info_out, void* ws, size_t ws_bytes, void* stream);
+
+/* Moves every atom (position + global 1-based index gidx: n TI) to its owner and exchanges the halos; fully asynchronous.
+ * plane_active_out (HOST, ncells[2] bytes, may be NULL) receives the plane window for nl_*_window when the slab axis is z
+ * (all ones otherwise). */
+NL_API int nl_shard_exchange(const nl_params* params, const nl_shard_info* info, const void* X, const void* gidx, int64_t n,
+                             void* comm, void* X_all, void* gidx_all, uint8_t* plane_active_out, void* ws, size_t ws_bytes,
+                             void* stream);
+
+/* Communicator helpers for hosts without an NCCL binding of their own: rank 0 calls nl_nccl_unique_id, ships the 128 bytes to
+ * the other ranks by any means, then every rank calls nl_nccl_comm_init (collective). */
+NL_API int nl_nccl_unique_id(void* id128_out);
+NL_API int nl_nccl_comm_init(void** comm_out, int32_t nranks, const void* id128, int32_t rank);
+NL_API int nl_nccl_comm_destroy(void* comm);
 
 /* Lazy mode: fused for_each_neighbour traversals (src/cell_list.jl:779-801) with fixed sinks.
  * nl_lazy_count: counts_out[m] (N TI, original order) = count_neighbours(clist, m) (:808-814).

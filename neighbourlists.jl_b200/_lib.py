@@ -14,7 +14,8 @@ NL_F32, NL_F64 = 0, 1
 NL_I32, NL_I64 = 0, 1
 NL_STAGE_BUILD, NL_STAGE_PAIRS = 0, 1
 NL_FLAG_HALF = 1
-NL_OK, NL_ERR_BAD_ARG, NL_ERR_WORKSPACE, NL_ERR_CUDA, NL_ERR_OVERFLOW, NL_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+NL_OK, NL_ERR_BAD_ARG, NL_ERR_WORKSPACE, NL_ERR_CUDA, NL_ERR_OVERFLOW, NL_ERR_UNSUPPORTED, NL_ERR_NCCL = 0, -1, -2, -3, -4, -5, -6
+NL_MAX_RANKS = 64
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("NLCUDA_LIB") or os.path.join(_HERE, "libnlcuda.so")  # NLCUDA_LIB: A/B testing of kernel builds
@@ -35,6 +36,17 @@ class NlParams(C.Structure):
     ]
 
 
+class NlShardInfo(C.Structure):
+    """struct nl_shard_info (include/nlcuda.h): what nl_shard_prepare tells the host about this rank's slab."""
+    _fields_ = [
+        ("axis", C.c_int32), ("halo", C.c_int32), ("periodic", C.c_int32), ("nranks", C.c_int32), ("rank", C.c_int32), ("nplanes", C.c_int32),
+        ("has_dn", C.c_int32), ("has_up", C.c_int32), ("dn_peer", C.c_int32), ("up_peer", C.c_int32),
+        ("n_local", C.c_int64), ("n_owned", C.c_int64), ("n_halo_dn", C.c_int64), ("n_halo_up", C.c_int64),
+        ("n_send_dn", C.c_int64), ("n_send_up", C.c_int64),
+        ("bounds", C.c_int64 * (NL_MAX_RANKS + 1)), ("send_count", C.c_int64 * NL_MAX_RANKS), ("recv_count", C.c_int64 * NL_MAX_RANKS),
+    ]
+
+
 class NlError(RuntimeError):
     """Mirrors the reference's ErrorException convention (src/cell_list.jl:656-658)."""
 
@@ -47,7 +59,8 @@ _lib = None
 
 EXPORTS = ("nl_version", "nl_strerror", "nl_last_cuda_error", "nl_launch_count", "nl_workspace_bytes", "nl_build_cells", "nl_count_pairs",
            "nl_fill_pairs", "nl_fill_pairs_rows", "nl_count_pairs_window", "nl_fill_pairs_window", "nl_cell_ids", "nl_shard_plan", "nl_lazy_count", "nl_lazy_lj_energy", "nl_lazy_lj_forces",
-           "nl_pairs_R", "nl_max_neighbours", "nl_rows_padded", "nl_lazy_neighbours", "nl_bounding_box", "nl_max_displacement2")
+           "nl_pairs_R", "nl_max_neighbours", "nl_rows_padded", "nl_lazy_neighbours", "nl_bounding_box", "nl_max_displacement2",
+           "nl_shard_workspace_bytes", "nl_shard_prepare", "nl_shard_exchange", "nl_nccl_unique_id", "nl_nccl_comm_init", "nl_nccl_comm_destroy")
 NL_REDUCE_WS_BYTES = 32768
 
 
@@ -89,7 +102,18 @@ def lib():
         L.nl_lazy_neighbours.restype = C.c_int
         L.nl_bounding_box.argtypes = [C.c_int32, vp, i64, vp, vp, sz, vp]
         L.nl_max_displacement2.argtypes = [C.c_int32, vp, vp, i64, vp, vp, sz, vp]
-        for n in ("nl_pairs_R", "nl_max_neighbours", "nl_rows_padded", "nl_lazy_neighbours", "nl_bounding_box", "nl_max_displacement2"):
+        ps = C.POINTER(NlShardInfo)
+        L.nl_shard_workspace_bytes.restype = sz
+        L.nl_shard_workspace_bytes.argtypes = [pp, i64, C.c_int32]
+        L.nl_shard_prepare.argtypes = [pp, vp, i64, vp, C.c_int32, C.c_int32, ps, vp, sz, vp]
+        L.nl_shard_exchange.argtypes = [pp, ps, vp, vp, i64, vp, vp, vp, vp, vp, sz, vp]
+        L.nl_nccl_unique_id.argtypes = [vp]
+        L.nl_nccl_comm_init.argtypes = [C.POINTER(vp), C.c_int32, vp, C.c_int32]
+        L.nl_nccl_comm_destroy.argtypes = [vp]
+        for n in ("nl_shard_prepare", "nl_shard_exchange", "nl_nccl_unique_id", "nl_nccl_comm_init", "nl_nccl_comm_destroy"):
+            getattr(L, n).restype = C.c_int
+        for n in ("nl_pairs_R", "nl_max_neighbours", "nl_rows_padded", "nl_lazy_neighbours", "nl_bounding_box", "nl_max_displacement2",
+           "nl_shard_workspace_bytes", "nl_shard_prepare", "nl_shard_exchange", "nl_nccl_unique_id", "nl_nccl_comm_init", "nl_nccl_comm_destroy"):
             getattr(L, n).restype = C.c_int
         for n in ("nl_build_cells", "nl_count_pairs", "nl_fill_pairs", "nl_fill_pairs_rows", "nl_count_pairs_window", "nl_fill_pairs_window", "nl_cell_ids", "nl_shard_plan", "nl_lazy_count",
                   "nl_lazy_lj_energy"):

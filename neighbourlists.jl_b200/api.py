@@ -195,10 +195,10 @@ def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers:
             _lib.check(L.nl_count_pairs_window(params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
                                                C.byref(total), pa_ptr, _ptr(ws), ws.numel(), _stream(dev)))
         P = int(total.value)
-        if n_rows is not None:
-            if not 0 <= n_rows <= N:
-                raise ValueError("n_rows out of range")
-            P = int(first[n_rows].item()) - 1
+        if n_rows is not None and not 0 <= n_rows <= N:
+            raise ValueError("n_rows out of range")
+        # shard mode: the owned rows hold first[n_rows] - 1 <= total pairs.  The arrays are allocated for `total` and trimmed
+        # AFTER the fill has been enqueued, so that this second host read does not leave the GPU idle between the two passes.
         if timers is not None:
             ev[1].record()
         i = torch.empty(P, dtype=it, device=dev)
@@ -224,11 +224,14 @@ def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers:
             _lib.check(L.nl_fill_pairs_rows(params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
                                             N if n_rows is None else n_rows, _ptr(index_map), _ptr(i), _ptr(j), _ptr(S), _ptr(R),
                                             _ptr(ws), ws.numel(), _stream(dev)))
-        if n_rows is not None:
-            first = first[:n_rows + 1]
         if timers is not None:
             ev[3].record()
             timers.setdefault("events", []).append(ev)
+        if n_rows is not None:
+            Pr = int(first[n_rows].item()) - 1
+            first = first[:n_rows + 1]
+            i, j, S = i[:Pr], j[:Pr], S[:Pr]
+            R = None if R is None else R[:Pr]
     return PairList(X=clist.X_orig, C=clist.cell, cutoff=clist.cutoff, i=i, j=j, S=S, first=first, R=R, params=clist.params, half=half)
 
 

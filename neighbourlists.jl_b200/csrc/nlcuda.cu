@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "nl_build.cuh"
@@ -14,6 +15,7 @@
 #include "nl_mask.cuh"
 #include "nl_fillrows.cuh"
 #include "nl_fill2.cuh"
+#include "nl_shard.cuh"
 #include "nl_access.cuh"
 
 namespace {
@@ -22,6 +24,7 @@ using namespace nl;
 
 
 static_assert(sizeof(nl_params) == 192, "nl_params layout is part of the ABI");
+static_assert(sizeof(nl_shard_info) == 1632, "nl_shard_info layout is part of the ABI");
 
 inline int cuda_fail(cudaError_t e) {
   last_cuda_slot() = (int)e;
@@ -608,6 +611,178 @@ int lazy_ljf_impl(const nl_params* p, const void* Xs, int64_t N, const void* per
   return traverse<T, TI, MODE_LJF>(p, N, co, w, g, sk, false, st);
 }
 
+// ---------------------------------------------------------------- multi-GPU slabs (nl_shard.cuh)
+#define NL_NCCL(expr)                         \
+  do {                                        \
+    if ((expr) != 0) return NL_ERR_NCCL;      \
+  } while (0)
+
+inline int slab_axis(const nl_params* p) {  // most planes; ties go to the SLOWEST key axis (z), so that a slab is one range of keys
+  int axis = 2;
+  if (p->ncells[1] > p->ncells[axis]) axis = 1;
+  if (p->ncells[0] > p->ncells[axis]) axis = 0;
+  return axis;
+}
+
+template <class T, class TI>
+int shard_prepare_impl(const nl_params* p, const void* X, int64_t n, void* comm, int rank, int nranks, nl_shard_info* info, void* ws,
+                       cudaStream_t st) {
+  Geo<T> g = make_geo<T>(p);
+  const int axis = slab_axis(p), nplanes = p->ncells[axis], halo = p->nxyz[axis];
+  ShardWs w = shard_ws(ws, n, nplanes, nranks, sizeof(T), sizeof(TI));
+  NL_CUDA(cudaMemsetAsync(w.hist_local, 0, (size_t)nplanes * 8, st));
+  if (n > 0) {
+    const unsigned nb = (unsigned)std::min<long long>((n + 255) / 256, 148 * 8);
+    k_shard_planes<T><<<nb, 256, 0, st>>>((const T*)X, n, g, axis, nplanes, w.planes, w.hist_local);
+    NL_LAUNCHED(1);
+    NL_LAUNCH_CHECK();
+  }
+  if (nranks > 1) {
+    if (!nccl().ok || !comm) return NL_ERR_NCCL;
+    NL_NCCL(nccl().AllGather(w.hist_local, w.hist_all, (size_t)nplanes, NCCL_UINT64, comm, st));
+  } else {
+    NL_CUDA(cudaMemcpyAsync(w.hist_all, w.hist_local, (size_t)nplanes * 8, cudaMemcpyDeviceToDevice, st));
+  }
+  std::vector<unsigned long long> h((size_t)nplanes * nranks);
+  NL_CUDA(cudaMemcpyAsync(h.data(), w.hist_all, h.size() * 8, cudaMemcpyDeviceToHost, st));
+  NL_CUDA(cudaStreamSynchronize(st));
+  std::vector<int64_t> tot(nplanes, 0);
+  for (int r = 0; r < nranks; r++)
+    for (int q = 0; q < nplanes; q++) tot[q] += (int64_t)h[(size_t)r * nplanes + q];
+  nl_shard_info& f = *info;
+  f = nl_shard_info{};
+  f.axis = axis; f.halo = halo; f.periodic = p->pbc[axis] ? 1 : 0; f.nranks = nranks; f.rank = rank; f.nplanes = nplanes;
+  f.n_local = n;
+  int rc = nl_shard_plan(tot.data(), nplanes, nranks, halo, f.bounds);
+  if (rc) return rc;
+  auto sum = [&](const unsigned long long* row, int64_t a, int64_t b) { int64_t s = 0; for (int64_t q = a; q < b; q++) s += (int64_t)row[q]; return s; };
+  auto sumt = [&](int64_t a, int64_t b) { int64_t s = 0; for (int64_t q = a; q < b; q++) s += tot[q]; return s; };
+  for (int d = 0; d < nranks; d++) f.send_count[d] = sum(&h[(size_t)rank * nplanes], f.bounds[d], f.bounds[d + 1]);
+  for (int r = 0; r < nranks; r++) f.recv_count[r] = sum(&h[(size_t)r * nplanes], f.bounds[rank], f.bounds[rank + 1]);
+  f.n_owned = sumt(f.bounds[rank], f.bounds[rank + 1]);
+  f.up_peer = rank + 1; f.dn_peer = rank - 1;
+  if (f.periodic) { f.up_peer = (rank + 1) % nranks; f.dn_peer = (rank + nranks - 1) % nranks; }
+  f.has_up = nranks > 1 && f.up_peer >= 0 && f.up_peer < nranks;
+  f.has_dn = nranks > 1 && f.dn_peer >= 0 && f.dn_peer < nranks;
+  const int64_t lo = f.bounds[rank], hi = f.bounds[rank + 1];
+  if (f.has_dn) { f.n_send_dn = sumt(lo, lo + halo); f.n_halo_dn = sumt(f.bounds[f.dn_peer + 1] - halo, f.bounds[f.dn_peer + 1]); }
+  if (f.has_up) { f.n_send_up = sumt(hi - halo, hi); f.n_halo_up = sumt(f.bounds[f.up_peer], f.bounds[f.up_peer] + halo); }
+  return NL_OK;
+}
+
+template <class T, class TI>
+int shard_exchange_impl(const nl_params* p, const nl_shard_info* info, const void* X, const void* gidx, int64_t n, void* comm, void* X_all,
+                        void* g_all, uint8_t* plane_active_out, void* ws, cudaStream_t st) {
+  const nl_shard_info& f = *info;
+  Geo<T> g = make_geo<T>(p);
+  const int G = f.nranks, me = f.rank;
+  const int64_t n_max = std::max<int64_t>(n, f.n_owned);
+  ShardWs w = shard_ws(ws, n_max, f.nplanes, G, sizeof(T), sizeof(TI));
+  T* Xa = (T*)X_all;
+  TI* ga = (TI*)g_all;
+  if (plane_active_out) {
+    const int nz = p->ncells[2];
+    if (f.axis != 2 || G == 1) {
+      for (int z = 0; z < nz; z++) plane_active_out[z] = 1;
+    } else {
+      for (int z = 0; z < nz; z++) plane_active_out[z] = 0;
+      for (int64_t z = f.bounds[me] - f.halo; z < f.bounds[me + 1] + f.halo; z++) {
+        if (z >= 0 && z < nz) plane_active_out[z] = 1;
+        else if (f.periodic) plane_active_out[((z % nz) + nz) % nz] = 1;
+      }
+    }
+  }
+  if (G == 1) {
+    if (n > 0) {
+      NL_CUDA(cudaMemcpyAsync(Xa, X, (size_t)n * 3 * sizeof(T), cudaMemcpyDeviceToDevice, st));
+      NL_CUDA(cudaMemcpyAsync(ga, gidx, (size_t)n * sizeof(TI), cudaMemcpyDeviceToDevice, st));
+    }
+    return NL_OK;
+  }
+  if (!nccl().ok || !comm) return NL_ERR_NCCL;
+  // ---- owners, stable partition by destination
+  const uint32_t* order = nullptr;
+  if (n > 0) {
+    NL_CUDA(cudaMemsetAsync(w.hist_local, 0, (size_t)f.nplanes * 8, st));
+    k_shard_planes<T><<<(unsigned)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, st>>>((const T*)X, n, g, f.axis, f.nplanes, w.planes, w.hist_local);
+    NL_CUDA(cudaMemcpyAsync(w.bounds, f.bounds, (size_t)(G + 1) * 8, cudaMemcpyHostToDevice, st));
+    k_shard_owner<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.planes, n, w.bounds, G, w.keyA);
+    const int where = radix_sort_pairs(w.keyA, w.valA, w.keyB, w.valB, n, key_bits(G), w.rs_scratch, st);
+    order = where ? w.valB : w.valA;
+    k_shard_gather<T, TI><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(order, 0, n, (const T*)X, (const TI*)gidx, w.planes, (T*)w.sendX, (TI*)w.sendg, w.sendp);
+    NL_LAUNCHED(3);
+    NL_LAUNCH_CHECK();
+  }
+  // ---- all-to-all-v straight into the local arrays: [atoms that stay | from rank 0 | from rank 1 | ...]
+  std::vector<int64_t> soff(G + 1, 0), roff(G, 0);
+  for (int d = 0; d < G; d++) soff[d + 1] = soff[d] + f.send_count[d];
+  {
+    int64_t o = f.send_count[me];
+    for (int s = 0; s < G; s++) if (s != me) { roff[s] = o; o += f.recv_count[s]; }
+    if (o != f.n_owned || soff[G] != n) return NL_ERR_BAD_ARG;  // info does not belong to these atoms
+  }
+  if (f.send_count[me] > 0) {
+    const int64_t k0 = soff[me], c = f.send_count[me];
+    NL_CUDA(cudaMemcpyAsync(Xa, (const T*)w.sendX + 3 * k0, (size_t)c * 3 * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    NL_CUDA(cudaMemcpyAsync(ga, (const TI*)w.sendg + k0, (size_t)c * sizeof(TI), cudaMemcpyDeviceToDevice, st));
+    NL_CUDA(cudaMemcpyAsync(w.planes_owned, w.sendp + k0, (size_t)c * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  bool any = false;
+  for (int r = 0; r < G; r++) any = any || (r != me && (f.send_count[r] > 0 || f.recv_count[r] > 0));
+  if (any) {
+    NL_NCCL(nccl().GroupStart());
+    for (int r = 0; r < G; r++) {
+      if (r == me) continue;
+      if (f.send_count[r] > 0) {
+        const int64_t k0 = soff[r], c = f.send_count[r];
+        NL_NCCL(nccl().Send((const T*)w.sendX + 3 * k0, (size_t)c * 3 * sizeof(T), NCCL_INT8, r, comm, st));
+        NL_NCCL(nccl().Send((const TI*)w.sendg + k0, (size_t)c * sizeof(TI), NCCL_INT8, r, comm, st));
+        NL_NCCL(nccl().Send(w.sendp + k0, (size_t)c * 4, NCCL_INT8, r, comm, st));
+      }
+      if (f.recv_count[r] > 0) {
+        const int64_t k0 = roff[r], c = f.recv_count[r];
+        NL_NCCL(nccl().Recv(Xa + 3 * k0, (size_t)c * 3 * sizeof(T), NCCL_INT8, r, comm, st));
+        NL_NCCL(nccl().Recv(ga + k0, (size_t)c * sizeof(TI), NCCL_INT8, r, comm, st));
+        NL_NCCL(nccl().Recv(w.planes_owned + k0, (size_t)c * 4, NCCL_INT8, r, comm, st));
+      }
+    }
+    NL_NCCL(nccl().GroupEnd());
+  }
+  // ---- halos: bottom planes to the rank below, top planes to the rank above
+  const int64_t no = f.n_owned, ns = f.n_send_dn + f.n_send_up;
+  if (no > 0 && ns > 0) {
+    k_shard_halo_class<<<(unsigned)((no + 255) / 256), 256, 0, st>>>(w.planes_owned, no, f.bounds[me], f.bounds[me + 1], f.halo, f.has_dn, f.has_up, w.keyA);
+    const int where = radix_sort_pairs(w.keyA, w.valA, w.keyB, w.valB, no, 2, w.rs_scratch, st);
+    const uint32_t* order2 = where ? w.valB : w.valA;
+    k_shard_gather<T, TI><<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(order2, 0, ns, Xa, ga, nullptr, (T*)w.sendX, (TI*)w.sendg, nullptr);
+    NL_LAUNCHED(2);
+    NL_LAUNCH_CHECK();
+  }
+  if (ns > 0 || f.n_halo_dn > 0 || f.n_halo_up > 0) {
+    // message order matters when both neighbours are the same rank (2 ranks, periodic): everyone sends [up, down] and
+    // receives [from below, from above], so the k-th send to a peer meets its k-th receive
+    NL_NCCL(nccl().GroupStart());
+    if (f.has_up && f.n_send_up > 0) {
+      NL_NCCL(nccl().Send((const T*)w.sendX + 3 * f.n_send_dn, (size_t)f.n_send_up * 3 * sizeof(T), NCCL_INT8, f.up_peer, comm, st));
+      NL_NCCL(nccl().Send((const TI*)w.sendg + f.n_send_dn, (size_t)f.n_send_up * sizeof(TI), NCCL_INT8, f.up_peer, comm, st));
+    }
+    if (f.has_dn && f.n_send_dn > 0) {
+      NL_NCCL(nccl().Send((const T*)w.sendX, (size_t)f.n_send_dn * 3 * sizeof(T), NCCL_INT8, f.dn_peer, comm, st));
+      NL_NCCL(nccl().Send((const TI*)w.sendg, (size_t)f.n_send_dn * sizeof(TI), NCCL_INT8, f.dn_peer, comm, st));
+    }
+    if (f.has_dn && f.n_halo_dn > 0) {
+      NL_NCCL(nccl().Recv(Xa + 3 * no, (size_t)f.n_halo_dn * 3 * sizeof(T), NCCL_INT8, f.dn_peer, comm, st));
+      NL_NCCL(nccl().Recv(ga + no, (size_t)f.n_halo_dn * sizeof(TI), NCCL_INT8, f.dn_peer, comm, st));
+    }
+    if (f.has_up && f.n_halo_up > 0) {
+      NL_NCCL(nccl().Recv(Xa + 3 * (no + f.n_halo_dn), (size_t)f.n_halo_up * 3 * sizeof(T), NCCL_INT8, f.up_peer, comm, st));
+      NL_NCCL(nccl().Recv(ga + no + f.n_halo_dn, (size_t)f.n_halo_up * sizeof(TI), NCCL_INT8, f.up_peer, comm, st));
+    }
+    NL_NCCL(nccl().GroupEnd());
+  }
+  return NL_OK;
+}
+
 #define NL_DISPATCH(p, FN, ...)                                                              \
   ((p)->float_type == NL_F64                                                                 \
        ? ((p)->int_type == NL_I64 ? FN<double, int64_t>(__VA_ARGS__) : FN<double, int32_t>(__VA_ARGS__)) \
@@ -634,6 +809,7 @@ const char* nl_strerror(int code) {
     case NL_ERR_CUDA: return "nlcuda: CUDA error (see nl_last_cuda_error())";
     case NL_ERR_OVERFLOW: return "nlcuda: number of pairs overflows int_type; use a 64-bit int_type";
     case NL_ERR_UNSUPPORTED: return "nlcuda: N or prod(ncells) >= 2^31 - 1 is not supported (use a larger cutoff or a smaller simulation cell)";
+    case NL_ERR_NCCL: return "nlcuda: NCCL is not loadable in this process (libnccl.so.2) or an NCCL call failed";
     default: return "nlcuda: unknown error code";
   }
 }
@@ -740,6 +916,52 @@ int nl_shard_plan(const int64_t* plane_hist, int32_t nplanes, int32_t nranks, in
   }
   bounds_out[nranks] = nplanes;
   return NL_OK;
+}
+
+size_t nl_shard_workspace_bytes(const nl_params* params, int64_t n_max, int32_t nranks) {
+  if (check_params(params, n_max) != NL_OK || nranks < 1 || nranks > NL_MAX_RANKS) return 0;
+  return shard_ws(nullptr, n_max, params->ncells[slab_axis(params)], nranks, fsize(params), params->int_type == NL_I64 ? 8 : 4).total;
+}
+
+int nl_shard_prepare(const nl_params* params, const void* X, int64_t n, void* comm, int32_t rank, int32_t nranks, nl_shard_info* info_out,
+                     void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_params(params, n);
+  if (rc) return rc;
+  if (!info_out || nranks < 1 || nranks > NL_MAX_RANKS || rank < 0 || rank >= nranks || (n > 0 && !X)) return NL_ERR_BAD_ARG;
+  rc = check_ws(ws, ws_bytes, nl_shard_workspace_bytes(params, n, nranks));
+  if (rc) return rc;
+  return NL_DISPATCH(params, shard_prepare_impl, params, X, n, comm, rank, nranks, info_out, ws, (cudaStream_t)stream);
+}
+
+int nl_shard_exchange(const nl_params* params, const nl_shard_info* info, const void* X, const void* gidx, int64_t n, void* comm, void* X_all,
+                      void* gidx_all, uint8_t* plane_active_out, void* ws, size_t ws_bytes, void* stream) {
+  int rc = check_params(params, n);
+  if (rc) return rc;
+  if (!info || info->nranks < 1 || info->nranks > NL_MAX_RANKS || info->n_local != n || (n > 0 && (!X || !gidx))) return NL_ERR_BAD_ARG;
+  if (info->n_owned + info->n_halo_dn + info->n_halo_up > 0 && (!X_all || !gidx_all)) return NL_ERR_BAD_ARG;
+  rc = check_ws(ws, ws_bytes, nl_shard_workspace_bytes(params, std::max<int64_t>(n, info->n_owned), info->nranks));
+  if (rc) return rc;
+  return NL_DISPATCH(params, shard_exchange_impl, params, info, X, gidx, n, comm, X_all, gidx_all, plane_active_out, ws, (cudaStream_t)stream);
+}
+
+int nl_nccl_unique_id(void* id128_out) {
+  if (!id128_out) return NL_ERR_BAD_ARG;
+  if (!nccl().ok) return NL_ERR_NCCL;
+  return nccl().GetUniqueId((NcclUid*)id128_out) == 0 ? NL_OK : NL_ERR_NCCL;
+}
+
+int nl_nccl_comm_init(void** comm_out, int32_t nranks, const void* id128, int32_t rank) {
+  if (!comm_out || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return NL_ERR_BAD_ARG;
+  if (!nccl().ok) return NL_ERR_NCCL;
+  NcclUid id;
+  memcpy(&id, id128, sizeof(id));
+  return nccl().CommInitRank(comm_out, nranks, id, rank) == 0 ? NL_OK : NL_ERR_NCCL;
+}
+
+int nl_nccl_comm_destroy(void* comm) {
+  if (!comm) return NL_OK;
+  if (!nccl().ok) return NL_ERR_NCCL;
+  return nccl().CommDestroy(comm) == 0 ? NL_OK : NL_ERR_NCCL;
 }
 
 int nl_cell_ids(const nl_params* params, const void* X, int64_t N, void* cell_id_out, void* stream) {

@@ -251,3 +251,67 @@ def neighbour_list_sharded(X_local, gidx_local, cutoff, cell, pbc, *, group=None
     ph.report(rank)
     return ShardedPairList(owned_index=gidx, X_owned=X, first=res["first"], i=res["i"], j=res["j"], S=res["S"], R=res["R"],
                            n_halo=n_halo, plan=plan)
+
+
+# ------------------------------------------------------------------ native driver: nl_shard_prepare / nl_shard_exchange (NCCL inside the library)
+def make_nccl_comm(group=None):
+    """ncclComm_t (ctypes.c_void_p) over the ranks of `group`, created by the LIBRARY (nl_nccl_comm_init) in the NCCL instance
+    this process has loaded; the 128-byte unique id travels over torch.distributed (any backend).  The current CUDA device
+    must be this rank's GPU.  Collective."""
+    import ctypes as C
+    from . import _lib
+    L = _lib.lib()
+    rank = dist.get_rank(group)
+    world = dist.get_world_size(group)
+    buf = (C.c_char * 128)()
+    if rank == 0:
+        _lib.check(L.nl_nccl_unique_id(C.cast(buf, C.c_void_p)))
+    t = torch.frombuffer(bytearray(bytes(buf)), dtype=torch.uint8).clone()
+    on_gpu = dist.get_backend(group) == "nccl"
+    if on_gpu:
+        t = t.cuda()
+    src = dist.get_global_rank(group, 0) if group is not None else 0
+    dist.broadcast(t, src=src, group=group)
+    idb = (C.c_char * 128).from_buffer_copy(bytes(t.cpu().numpy().tobytes()))
+    comm = C.c_void_p()
+    _lib.check(L.nl_nccl_comm_init(C.byref(comm), world, C.cast(idb, C.c_void_p), rank))
+    return comm
+
+
+def neighbour_list_sharded_native(X_local, gidx_local, cutoff, cell, pbc, comm, rank: int, world: int, *, int_type=np.int32,
+                                  with_R=False, timers=None) -> ShardedPairList:
+    """The same list as neighbour_list_sharded, driven entirely through the C ABI: nl_shard_prepare (bin, all-gathered plane
+    histograms, slab plan: ONE host read), nl_shard_exchange (owner partition, all-to-all-v and halo exchange with ncclSend /
+    ncclRecv inside the library) and the unchanged local stages.  This is the call sequence a Julia driver makes."""
+    import ctypes as C
+    from . import _lib, api
+    L = _lib.lib()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    X = api._as_device_positions(X_local, dev)
+    it = api._int_dtype(int_type)
+    gidx = torch.as_tensor(gidx_local).to(device=dev, dtype=it).contiguous()
+    fdt = np.dtype(api._T2N[X.dtype])
+    geo = geometry(cell, cutoff, pbc, fdt)
+    params = _lib.make_params(geo, fdt, api._T2N[it])
+    n = int(X.shape[0])
+    st = api._stream(dev)
+    with torch.cuda.device(dev):
+        ws = torch.empty(max(L.nl_shard_workspace_bytes(params, n, world), 256), dtype=torch.uint8, device=dev)
+        info = _lib.NlShardInfo()
+        _lib.check(L.nl_shard_prepare(params, api._ptr(X), n, comm, rank, world, C.byref(info), api._ptr(ws), ws.numel(), st))
+        n_owned, n_all = int(info.n_owned), int(info.n_owned + info.n_halo_dn + info.n_halo_up)
+        need = L.nl_shard_workspace_bytes(params, max(n, n_owned), world)
+        if need > ws.numel():
+            ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        X_all = torch.empty((n_all, 3), dtype=X.dtype, device=dev)
+        g_all = torch.empty(n_all, dtype=it, device=dev)
+        plane_active = np.ones(int(geo.ncells[2]), dtype=np.uint8)
+        _lib.check(L.nl_shard_exchange(params, C.byref(info), api._ptr(X), api._ptr(gidx), n, comm, api._ptr(X_all), api._ptr(g_all),
+                                       plane_active.ctypes.data, api._ptr(ws), ws.numel(), st))
+        clist = api.build_cell_list(X_all, cutoff, cell, pbc, int_type=int_type)
+        pl = api.materialize_pairlist(clist, with_R=with_R, n_rows=n_owned, index_map=g_all, timers=timers,
+                                      plane_active=plane_active if (world > 1 and info.axis == 2) else None)
+    plan = SlabPlan(axis=int(info.axis), bounds=np.asarray(list(info.bounds[:world + 1]), dtype=np.int64), halo=int(info.halo),
+                    periodic=bool(info.periodic))
+    return ShardedPairList(owned_index=g_all[:n_owned], X_owned=X_all[:n_owned], first=pl.first, i=pl.i, j=pl.j, S=pl.S, R=pl.R,
+                           n_halo=n_all - n_owned, plan=plan)

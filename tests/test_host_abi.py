@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert len(syms) >= 9 and set(syms) == set(nl._lib.EXPORTS)
     for s in syms:
         assert hasattr(L, s), s
-    assert L.nl_version() == 100
+    assert L.nl_version() == 200
     assert b"workspace" in L.nl_strerror(nl._lib.NL_ERR_WORKSPACE)
     assert L.nl_strerror(0) == b"ok"
 
