@@ -193,27 +193,35 @@ def run_ours(args):
     n_atoms = args.atoms
     pbc = (True, True, True)
     it = torch.int32
-    if world == 1:
-        X, C, L = make_positions(n_atoms, SEED)
-        gidx = None
-    else:
-        # weak scaling: ONE global box of world * n_atoms atoms; rank r generates the atoms of its own
-        # equal-width slab along the slab axis (z).  neighbour_list_sharded still bins, balances the slabs
-        # by atom count, moves boundary atoms to their owners (all-to-all-v) and exchanges the halos.
-        n_total = n_atoms * world
+    sharded = comm = None
+    if world > 1:
+        sharded = __import__("importlib").import_module("neighbourlists_jl_b200.sharded")
+        comm = sharded.make_nccl_comm()
+
+    def make_inputs(n_per_rank, mode):
+        """(X, cell, gidx): one rank's share of ONE global box of world * n_per_rank atoms (weak scaling).
+        by-index: rank r holds the block [r n, (r+1) n) of the global index range, positions anywhere in the box, so the
+                  all-to-all-v of nl_shard_exchange moves (1 - 1/world) of all atoms every list (the worst case);
+        slabbed : rank r generates the atoms of its own equal-width z slab (a domain-decomposed MD code: almost nothing moves)."""
+        if world == 1:
+            X, C, L = make_positions(n_per_rank, SEED)
+            return X, C, None
+        n_total = n_per_rank * world
         L = (n_total / DENSITY) ** (1.0 / 3.0)
         C = np.eye(3) * L
         rng = np.random.Generator(np.random.PCG64(SEED + rank))
-        X = rng.random((n_atoms, 3))
-        X[:, 2] = (X[:, 2] + rank) / world
+        X = rng.random((n_per_rank, 3))
+        if mode == "slabbed":
+            X[:, 2] = (X[:, 2] + rank) / world
         X *= L
-        gidx = torch.arange(rank * n_atoms + 1, (rank + 1) * n_atoms + 1, dtype=torch.int64)
+        return X, C, torch.arange(rank * n_per_rank + 1, (rank + 1) * n_per_rank + 1, dtype=it)
+
+    X, C, gidx = make_inputs(n_atoms, args.input)
     X_host = torch.from_numpy(X).pin_memory()
     X_dev = X_host.to(dev)
     if gidx is not None:
         gidx_host = gidx.pin_memory()
         gidx_dev = gidx_host.to(dev)
-        sharded = __import__("importlib").import_module("neighbourlists_jl_b200.sharded")
     torch.cuda.synchronize()
 
     def barrier():
@@ -223,12 +231,14 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident throughput ("value") + stage / kernel timings
-    def step(timers=None):
+    def step(timers=None, Xd=None, gd=None, cell=None):
+        Xd = X_dev if Xd is None else Xd
+        cell = C if cell is None else cell
         if world == 1:
-            clist = nl.build_cell_list(X_dev, CUTOFF, C, pbc)
+            clist = nl.build_cell_list(Xd, CUTOFF, cell, pbc)
             return nl.materialize_pairlist(clist, with_R=True, timers=timers)
-        return sharded.neighbour_list_sharded(X_dev, gidx_dev, CUTOFF, C, pbc, with_R=True,
-                                              engine=sharded.CudaEngine(dev, timers=timers))
+        return sharded.neighbour_list_sharded_native(Xd, gidx_dev if gd is None else gd, CUTOFF, cell, pbc, comm, rank, world,
+                                                     with_R=True, timers=timers)
 
     def npairs_of(pl):
         return int(pl.i.shape[0])
@@ -272,8 +282,8 @@ def run_ours(args):
         if world == 1:
             pl = nl.neighbour_list(X_host, CUTOFF, C, pbc, device=dev)  # pinned H2D inside; reference layout (no R)
         else:
-            pl = sharded.neighbour_list_sharded(X_host.to(dev, non_blocking=True), gidx_host.to(dev, non_blocking=True), CUTOFF, C, pbc,
-                                                engine=sharded.CudaEngine(dev))
+            pl = sharded.neighbour_list_sharded_native(X_host.to(dev, non_blocking=True), gidx_host.to(dev, non_blocking=True), CUTOFF, C, pbc,
+                                                       comm, rank, world)
         nf, npr = pl.first.shape[0], pl.i.shape[0]
         h_first[:nf].copy_(pl.first, non_blocking=True)
         h_i[:npr].copy_(pl.i, non_blocking=True)
@@ -294,6 +304,39 @@ def run_ours(args):
     barrier()
     e2e_ms = e0.elapsed_time(e1) / e2e_steps
     assert int(h_first[nf - 1]) - 1 == npr == P
+
+    # ---------------- multi-GPU extras: the other input distribution, and BASELINE config 4 (100 M atoms) at 8 ranks
+    def timed_steps(Xd, gd, cell, nsteps=3, nwarm=2):
+        for _ in range(nwarm):
+            p_ = step(None, Xd, gd, cell); Pn = npairs_of(p_); del p_
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(nsteps):
+            p_ = step(None, Xd, gd, cell); Pn = npairs_of(p_); del p_
+        b.record()
+        barrier()
+        return a.elapsed_time(b) / nsteps, Pn
+
+    extras = {}
+    if world > 1:
+        del h_i, h_j, h_S, h_first
+        torch.cuda.empty_cache()
+        other = "slabbed" if args.input == "by-index" else "by-index"
+        Xo, Co, go = make_inputs(n_atoms, other)
+        ms_o, P_o = timed_steps(torch.from_numpy(Xo).to(dev), go.to(dev), Co)
+        extras[other] = [ms_o, float(P_o)]
+        if world == 8 and not args.no_c4:
+            Xc, Cc, gc = make_inputs(12_500_000, args.input)
+            ms_c, P_c = timed_steps(torch.from_numpy(Xc).to(dev), gc.to(dev), Cc)
+            extras["c4"] = [ms_c, float(P_c)]
+            del Xc, gc
+        for k in list(extras):
+            t = torch.tensor(extras[k], dtype=torch.float64, device=dev)
+            tmax, tsum = t.clone(), t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            extras[k] = {"ms_per_step": float(tmax[0]), "pairs_per_s": float(tsum[1]) / (float(tmax[0]) * 1e-3), "pairs": float(tsum[1])}
 
     # ---------------- max over ranks
     ms_per_step = total_ms / args.steps
@@ -320,7 +363,15 @@ def run_ours(args):
             "config": {"workload": f"{n_atoms} atoms per GPU, random cubic box rho={DENSITY} A^-3, rc={CUTOFF} A, pbc TTT, Float64/Int32, "
                                    f"seed {SEED}+rank; output (i,j,S,R) = 44 B/pair",
                        "pairs_per_gpu": P, "parallelism": "single GPU" if world == 1 else
-                       f"{world} spatial slabs along z of one {n_atoms * world}-atom box, all-to-all-v + cutoff-wide halo exchange (NCCL)",
+                       f"{world} spatial slabs along z of one {n_atoms * world}-atom box; nl_shard_prepare / nl_shard_exchange: all-to-all-v + "
+                       "cutoff-wide halo exchange with ncclSend / ncclRecv inside libnlcuda.so",
+                       "input": None if world == 1 else
+                       (args.input + (": every rank holds a block of the global INDEX range, positions anywhere in the box -> the all-to-all-v "
+                                      "moves (1 - 1/N) of all atoms inside the timed region" if args.input == "by-index" else
+                                      ": every rank holds the atoms of its own equal-width z slab (almost nothing moves)")),
+                       "other_input": {k: v for k, v in extras.items() if k != "c4"} or None,
+                       "c4": (dict(extras["c4"], workload="BASELINE config 4: 100 M atoms (12.5 M per GPU), same density / cutoff, "
+                                   f"{args.input} input, with R") if "c4" in extras else None),
                        "l2": "inputs (240 MB) and outputs (>11 GB) exceed the 126 MB L2; no explicit flush",
                        "stage_ms": {"count_stage": count_mean, "fill_kernel": fill_mean},
                        "step_roofline": {"bytes": step_bytes, "formula": "24 N + 48 P", "gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,
@@ -343,6 +394,7 @@ def run_ours(args):
                                              "reference CPU path (not Julia)"}
         print(json.dumps(out))
     if world > 1:
+        nl._lib.check(L_.nl_nccl_comm_destroy(comm))
         dist.destroy_process_group()
 
 
@@ -358,6 +410,9 @@ def main():
                          "the cpu_baseline leg of the GPU arm uses 1 M)")
     ap.add_argument("--cpu-budget", type=float, default=200.0, help="seconds of CPU time the reference arm may spend in total")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--input", default="by-index", choices=["by-index", "slabbed"],
+                    help="multi-GPU only: how the atoms are distributed over the ranks before the list is built")
+    ap.add_argument("--no-c4", action="store_true", help="skip the extra 100 M-atom record at 8 GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -295,10 +295,13 @@ def neighbour_list_sharded_native(X_local, gidx_local, cutoff, cell, pbc, comm, 
     params = _lib.make_params(geo, fdt, api._T2N[it])
     n = int(X.shape[0])
     st = api._stream(dev)
+    ph = _Phases(_PROFILE)
+    ph.mark("start")
     with torch.cuda.device(dev):
         ws = torch.empty(max(L.nl_shard_workspace_bytes(params, n, world), 256), dtype=torch.uint8, device=dev)
         info = _lib.NlShardInfo()
         _lib.check(L.nl_shard_prepare(params, api._ptr(X), n, comm, rank, world, C.byref(info), api._ptr(ws), ws.numel(), st))
+        ph.mark("prepare")
         n_owned, n_all = int(info.n_owned), int(info.n_owned + info.n_halo_dn + info.n_halo_up)
         need = L.nl_shard_workspace_bytes(params, max(n, n_owned), world)
         if need > ws.numel():
@@ -308,9 +311,13 @@ def neighbour_list_sharded_native(X_local, gidx_local, cutoff, cell, pbc, comm, 
         plane_active = np.ones(int(geo.ncells[2]), dtype=np.uint8)
         _lib.check(L.nl_shard_exchange(params, C.byref(info), api._ptr(X), api._ptr(gidx), n, comm, api._ptr(X_all), api._ptr(g_all),
                                        plane_active.ctypes.data, api._ptr(ws), ws.numel(), st))
+        ph.mark("exchange")
         clist = api.build_cell_list(X_all, cutoff, cell, pbc, int_type=int_type)
+        ph.mark("build")
         pl = api.materialize_pairlist(clist, with_R=with_R, n_rows=n_owned, index_map=g_all, timers=timers,
                                       plane_active=plane_active if (world > 1 and info.axis == 2) else None)
+        ph.mark("count+fill")
+    ph.report(rank)
     plan = SlabPlan(axis=int(info.axis), bounds=np.asarray(list(info.bounds[:world + 1]), dtype=np.int64), halo=int(info.halo),
                     periodic=bool(info.periodic))
     return ShardedPairList(owned_index=g_all[:n_owned], X_owned=X_all[:n_owned], first=pl.first, i=pl.i, j=pl.j, S=pl.S, R=pl.R,
