@@ -169,3 +169,71 @@ def test_headline_10m_half_list_accessors_and_forces(nl):
     etot = float(nl.lj_energy(clist, 1.0, 3.4).item())
     assert abs(float(e.sum().item()) - etot) <= 1e-9 * abs(etot)
     assert float(F.sum(0).abs().max()) <= 1e-9 * float(F.abs().sum())
+
+
+def _row_fingerprints_np(first, j, S):
+    """per-row sums of the pair fingerprints (wrapping uint64), numpy side: rows are contiguous in the CSR"""
+    with np.errstate(over="ignore"):
+        row = np.repeat(np.arange(1, first.shape[0], dtype=np.uint64), np.diff(first.astype(np.int64)))
+        h = (row * np.uint64(0x9E3779B97F4A7C15) + j.astype(np.int64).astype(np.uint64) * np.uint64(0x4F1BBCDCBFA53E0B)
+             + (S[:, 0].astype(np.int64) + 7).astype(np.uint64) * np.uint64(0x1000193)
+             + (S[:, 1].astype(np.int64) + 7).astype(np.uint64) * np.uint64(0x27D4EB2F)
+             + (S[:, 2].astype(np.int64) + 7).astype(np.uint64) * np.uint64(0x165667B1))
+        h ^= (h.view(np.int64) >> np.int64(29)).view(np.uint64)   # arithmetic shift, as torch's int64 >> in _mix
+        h *= np.uint64(0x2545F4914F6CDD1D)
+        c = np.concatenate([[np.uint64(0)], np.cumsum(h, dtype=np.uint64)])
+        f0 = first.astype(np.int64) - 1
+        return c[f0[1:]] - c[f0[:-1]]
+
+
+def test_headline_10m_list_against_oracle(nl):
+    """The reference's bar (test/test_gpu.jl:41-68: GPU list == CPU list) at the BASELINE size: `first` exactly, and an
+    order-independent fingerprint of the (j, S) multiset of EVERY row, against the CPU oracle on the same 10 M atoms; R
+    against the oracle's own R on the rows of a sample of atoms."""
+    import torch
+    N, rc = 10_000_000, 5.0
+    rng = np.random.Generator(np.random.PCG64(10))
+    L = (N / 0.05) ** (1 / 3)
+    X = rng.random((N, 3)) * L
+    C = np.eye(3) * L
+    pbc = (True, True, True)
+    orc = O.sortbased(X, rc, C, pbc, want_R=False)
+    pl = nl.neighbour_list(torch.from_numpy(X).cuda(), rc, C, pbc, with_R=True)
+    first = pl.first.cpu().numpy()
+    assert np.array_equal(first, orc["first"]), "CSR offsets"
+    P = int(first[-1]) - 1
+    assert P == orc["npairs"] == nl.npairs(pl)
+    fo = _row_fingerprints_np(orc["first"], orc["j"], orc["S"])
+    # engine side on the device: the same wrapping arithmetic in int64
+    i, j, S = pl.i.long(), pl.j.long(), pl.S.long()
+    assert torch.equal(i, torch.repeat_interleave(torch.arange(1, N + 1, device="cuda"), (pl.first[1:] - pl.first[:-1]).long()))
+    h = _mix(i, j, S[:, 0], S[:, 1], S[:, 2])          # _mix's logical shift: emulate >> on the unsigned value
+    del i, j, S
+    c = torch.cumsum(h, 0)
+    f0 = pl.first.long() - 1
+    cz = torch.cat([torch.zeros(1, dtype=torch.int64, device="cuda"), c])
+    fe = (cz[f0[1:]] - cz[f0[:-1]]).cpu().numpy().view(np.uint64)
+    assert np.array_equal(fe, fo), "per-row (j, S) multisets differ from the oracle"
+    # R on the rows of 50 000 sampled atoms against the oracle's contract arithmetic
+    sel = np.sort(np.random.default_rng(1).choice(N, 50_000, replace=False))
+    lo, hi = first[sel] - 1, first[sel + 1] - 1
+    idx = np.concatenate([np.arange(a, b) for a, b in zip(lo, hi)])
+    it = torch.from_numpy(idx).cuda()
+    sub = dict(i=pl.i[it].cpu().numpy(), j=pl.j[it].cpu().numpy(), S=pl.S[it].cpu().numpy())
+    Rref = O.pairs_R(X, sub["i"], sub["j"], sub["S"], C, np.float64)
+    assert np.array_equal(pl.R[it].cpu().numpy(), Rref), "R == (X[j] - X[i]) + C' S in the contract's association"
+
+
+def test_config5_10m_counts_against_oracle(nl):
+    """BASELINE config 5 (10 M atoms, Float32, rc = 6) per-atom neighbour counts of the lazy sink against the oracle's CSR."""
+    import torch
+    N = 10_000_000
+    rng = np.random.Generator(np.random.PCG64(10))
+    L = (N / 0.05) ** (1 / 3)
+    X = (rng.random((N, 3)) * L).astype(np.float32)
+    C = (np.eye(3) * L).astype(np.float32)
+    clist = nl.neighbour_list(torch.from_numpy(X).cuda(), 6.0, C, (True, True, True), lazy=True)
+    counts = nl.count_neighbours(clist).cpu().numpy()
+    orc = O.sortbased(X, 6.0, C, (True, True, True), dtype=np.float32, want_R=False)
+    assert np.array_equal(counts, np.diff(orc["first"]))
+    assert np.array_equal(clist.perm.cpu().numpy(), orc["perm"])
