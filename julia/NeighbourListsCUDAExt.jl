@@ -10,6 +10,7 @@ using NeighbourLists
 using NeighbourLists: SVec, SMat, SortedCellList, PairList, analyze_cell, lengths
 using CUDA
 using StaticArrays
+import AtomsBase, Unitful      # only the AtomsBase overloads at the end of this file need them
 
 const libnlcuda = get(ENV, "NLCUDA_LIB", "libnlcuda.so")
 
@@ -25,6 +26,7 @@ struct NlParams
     pbc::NTuple{3,UInt8}
     reserved::NTuple{5,UInt8}
 end
+@assert sizeof(NlParams) == 192 "NlParams must match struct nl_params (include/nlcuda.h)"
 
 _ftag(::Type{Float32}) = Int32(0); _ftag(::Type{Float64}) = Int32(1)
 _itag(::Type{Int32}) = Int32(0);   _itag(::Type{Int64}) = Int32(1)
@@ -41,8 +43,20 @@ function _params(cell::SMat{T}, inv_cell::SMat{T}, pbc::SVec{Bool}, cutoff::T, n
              Tuple(Int32.(ncells)), Tuple(nxyz), Tuple(UInt8.(pbc)), ntuple(_ -> 0x00, 5))
 end
 
-_ws(p, N, stage) = CUDA.zeros(UInt8, max(256, ccall((:nl_workspace_bytes, libnlcuda), Csize_t,
-                                                    (Ref{NlParams}, Int64, Cint), p, N, stage)))
+# Scratch is uninitialised device memory (the library never reads what it has not written) and is CACHED per cell list:
+# materialize_pairlist / the lazy sinks of one SortedCellList reuse one pair workspace instead of allocating 1.2 GB per call.
+_ws_bytes(p, N, stage) = max(256, Int(ccall((:nl_workspace_bytes, libnlcuda), Csize_t, (Ref{NlParams}, Int64, Cint), p, N, stage)))
+_ws(p, N, stage) = CuVector{UInt8}(undef, _ws_bytes(p, N, stage))
+const _PAIR_WS = WeakKeyDict{Any,CuVector{UInt8}}()            # keyed by clist.perm (unique per SortedCellList)
+function _pair_ws(clist, p)
+    need = _ws_bytes(p, length(clist.X), 1)
+    ws = get(_PAIR_WS, clist.perm, nothing)
+    if ws === nothing || length(ws) < need
+        ws = CuVector{UInt8}(undef, need)
+        _PAIR_WS[clist.perm] = ws
+    end
+    return ws
+end
 _stream() = Base.unsafe_convert(Ptr{Cvoid}, CUDA.stream().handle)
 
 # ---- stage override 1: _build_sorted_celllist (src/cell_list.jl:647-679)
@@ -72,7 +86,7 @@ function NeighbourLists.materialize_pairlist(clist::SortedCellList{T,TI,<:CuVect
     p = _params(clist.cell, clist.inv_cell, clist.pbc, clist.cutoff, clist.ncells)
     half && (p = _with_flags(p, 0x01))
     first = CuVector{TI}(undef, nat + 1)
-    ws = _ws(p, nat, 1)
+    ws = _pair_ws(clist, p)
     total = Ref{Int64}(0)
     _check(ccall((:nl_count_pairs, libnlcuda), Cint,
                  (Ref{NlParams}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Ref{Int64}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
@@ -91,7 +105,7 @@ end
 # ---- fused lazy sinks (for_each_neighbour with fixed bodies, src/cell_list.jl:779-814)
 function count_neighbours_all(clist::SortedCellList{T,TI,<:CuVector}) where {T,TI}
     nat = length(clist.X); p = _params(clist.cell, clist.inv_cell, clist.pbc, clist.cutoff, clist.ncells)
-    out = CUDA.zeros(TI, nat); ws = _ws(p, nat, 1)
+    out = CUDA.zeros(TI, nat); ws = _pair_ws(clist, p)
     _check(ccall((:nl_lazy_count, libnlcuda), Cint,
                  (Ref{NlParams}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
                  p, clist.X, nat, clist.perm, clist.cell_offsets, out, ws, length(ws), _stream()))
@@ -100,7 +114,7 @@ end
 
 function lj_energy(clist::SortedCellList{T,TI,<:CuVector}, eps, sigma) where {T,TI}
     nat = length(clist.X); p = _params(clist.cell, clist.inv_cell, clist.pbc, clist.cutoff, clist.ncells)
-    e = CUDA.zeros(Float64, 1); ws = _ws(p, nat, 1)
+    e = CUDA.zeros(Float64, 1); ws = _pair_ws(clist, p)
     _check(ccall((:nl_lazy_lj_energy, libnlcuda), Cint,
                  (Ref{NlParams}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, Float64, Float64, CuPtr{Float64}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
                  p, clist.X, nat, clist.perm, clist.cell_offsets, Float64(eps), Float64(sigma), e, ws, length(ws), _stream()))
@@ -110,7 +124,7 @@ end
 "(F, e): per-atom LJ forces and energies from one fused traversal; fe is N x 4 (F_x, F_y, F_z, e)"
 function lj_forces(clist::SortedCellList{T,TI,<:CuVector}, eps, sigma) where {T,TI}
     nat = length(clist.X); p = _params(clist.cell, clist.inv_cell, clist.pbc, clist.cutoff, clist.ncells)
-    fe = CUDA.zeros(T, 4, nat); ws = _ws(p, nat, 1)
+    fe = CUDA.zeros(T, 4, nat); ws = _pair_ws(clist, p)
     _check(ccall((:nl_lazy_lj_forces, libnlcuda), Cint,
                  (Ref{NlParams}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, Float64, Float64, CuPtr{Cvoid}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
                  p, clist.X, nat, clist.perm, clist.cell_offsets, Float64(eps), Float64(sigma), fe, ws, length(ws), _stream()))
@@ -135,7 +149,8 @@ function pairs_R(nl::DevPairList{T,TI}, lo::Integer = 1, hi::Integer = length(nl
 end
 
 function NeighbourLists.neigss(nl::DevPairList, i0::Integer)
-    n1, n2 = CUDA.@allowscalar(nl.first[i0]), CUDA.@allowscalar(nl.first[i0+1]) - 1
+    f = Array(@view nl.first[i0:i0+1])                     # one 2-element copy instead of two scalar reads
+    n1, n2 = Int(f[1]), Int(f[2]) - 1
     return (@view nl.j[n1:n2]), pairs_R(nl, n1, n2), (@view nl.S[n1:n2])
 end
 
@@ -176,7 +191,7 @@ end
 function shard_pairlist(clist::SortedCellList{T,TI,<:CuVector}, n_rows::Integer, index_map::CuVector{TI},
                         plane_active::Union{Nothing,Vector{UInt8}} = nothing) where {T,TI}
     nat = length(clist.X); p = _params(clist.cell, clist.inv_cell, clist.pbc, clist.cutoff, clist.ncells)
-    first = CuVector{TI}(undef, nat + 1); ws = _ws(p, nat, 1); total = Ref{Int64}(0)
+    first = CuVector{TI}(undef, nat + 1); ws = _pair_ws(clist, p); total = Ref{Int64}(0)
     pa = plane_active === nothing ? C_NULL : pointer(plane_active)
     GC.@preserve plane_active begin
         _check(ccall((:nl_count_pairs_window, libnlcuda), Cint,
@@ -194,7 +209,7 @@ end
 
 # ---- AtomsBase extension with device positions: the IsolatedCell bounding box (ext/NeighbourListsAtomsBaseExt.jl:17-31)
 function bounding_cell(X::CuVector{SVec{T}}) where {T}
-    mm = CuVector{T}(undef, 6); ws = CUDA.zeros(UInt8, 32768)
+    mm = CuVector{T}(undef, 6); ws = CuVector{UInt8}(undef, 32768)
     _check(ccall((:nl_bounding_box, libnlcuda), Cint, (Int32, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
                  _ftag(T), X, length(X), mm, ws, length(ws), _stream()))
     m = Array(mm)
@@ -203,11 +218,87 @@ end
 
 # ---- skin list: max squared displacement since the list was built
 function max_displacement2(X::CuVector{SVec{T}}, Xref::CuVector{SVec{T}}) where {T}
-    d2 = CuVector{T}(undef, 1); ws = CUDA.zeros(UInt8, 32768)
+    d2 = CuVector{T}(undef, 1); ws = CuVector{UInt8}(undef, 32768)
     _check(ccall((:nl_max_displacement2, libnlcuda), Cint,
                  (Int32, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
                  _ftag(T), X, Xref, length(X), d2, ws, length(ws), _stream()))
     return Array(d2)[1]
+end
+
+# ---- AtomsBase systems with DEVICE positions (ext/NeighbourListsAtomsBaseExt.jl:50-140 always builds a CPU Vector, :54-56).
+# These overloads take the positions as a CuVector (already stripped to `length_unit`), so nothing touches the host except the
+# six numbers of the IsolatedCell bounding box; they mirror PairList / build_cell_list / neighbour_list of the extension.
+# (Loaded only when AtomsBase and Unitful are: guard with Requires / a package extension in the real package.)
+function _device_cell_matrix(ab, X::CuVector{SVec{T}}, length_unit) where {T}
+    c = AtomsBase.cell(ab)
+    if c isa AtomsBase.IsolatedCell{3}
+        return bounding_cell(X)                                                   # :17-31 on the device (nl_bounding_box)
+    elseif c isa AtomsBase.IsolatedCell
+        error("NeighbourLists.jl does not support $(AtomsBase.n_dimensions(ab))-dimensional isolated AtomsBase systems yet.")
+    end
+    return SMat{T}(Unitful.ustrip.(length_unit, hcat(AtomsBase.cell_vectors(ab)...)'))  # :36
+end
+
+function NeighbourLists.build_cell_list(ab, X::CuVector{SVec{T}}, cutoff; length_unit = Unitful.unit(cutoff),
+                                        int_type::Type = Int32) where {T}
+    C = _device_cell_matrix(ab, X, length_unit)
+    return NeighbourLists.build_cell_list(X, T(Unitful.ustrip(length_unit, cutoff)), C, AtomsBase.periodicity(ab); int_type = int_type)
+end
+
+function NeighbourLists.neighbour_list(ab, X::CuVector{SVec{T}}, cutoff; lazy::Bool = false, kwargs...) where {T}
+    clist = NeighbourLists.build_cell_list(ab, X, cutoff; kwargs...)
+    return lazy ? clist : NeighbourLists.materialize_pairlist(clist)
+end
+
+NeighbourLists.PairList(ab, X::CuVector{SVec{T}}, cutoff; kwargs...) where {T} = NeighbourLists.neighbour_list(ab, X, cutoff; kwargs...)
+
+# ---- multi-GPU slabs through the library (include/nlcuda.h: nl_shard_prepare / nl_shard_exchange; NCCL inside libnlcuda.so).
+# One Julia process per GPU.  `comm` is an ncclComm_t: NCCL.jl's `comm.handle`, or nccl_comm(...) below with the unique id
+# shipped by MPI.jl / Distributed.
+struct NlShardInfo
+    axis::Int32; halo::Int32; periodic::Int32; nranks::Int32; rank::Int32; nplanes::Int32
+    has_dn::Int32; has_up::Int32; dn_peer::Int32; up_peer::Int32
+    n_local::Int64; n_owned::Int64; n_halo_dn::Int64; n_halo_up::Int64; n_send_dn::Int64; n_send_up::Int64
+    bounds::NTuple{65,Int64}; send_count::NTuple{64,Int64}; recv_count::NTuple{64,Int64}
+end
+@assert sizeof(NlShardInfo) == 1632 "NlShardInfo must match struct nl_shard_info (include/nlcuda.h)"
+
+nccl_unique_id() = (id = zeros(UInt8, 128); _check(ccall((:nl_nccl_unique_id, libnlcuda), Cint, (Ptr{UInt8},), id)); id)
+function nccl_comm(id::Vector{UInt8}, rank::Integer, nranks::Integer)
+    c = Ref{Ptr{Cvoid}}(C_NULL)
+    _check(ccall((:nl_nccl_comm_init, libnlcuda), Cint, (Ref{Ptr{Cvoid}}, Int32, Ptr{UInt8}, Int32), c, nranks, id, rank))
+    return c[]
+end
+
+"""
+    sharded_pairlist(X, gidx, cutoff, cell, pbc, comm, rank, nranks) -> (owned, first, i, j, S)
+
+Rows of the atoms this rank owns after the slab redistribution, with GLOBAL i / j.  X / gidx: any subset of the system per rank
+(positions and global 1-based indices); rank is 0-based.
+"""
+function sharded_pairlist(X::CuVector{SVec{T}}, gidx::CuVector{TI}, cutoff::T, cell::SMat{T}, pbc::SVec{Bool},
+                          comm::Ptr{Cvoid}, rank::Integer, nranks::Integer) where {T,TI}
+    inv_cell, ncells, lens = analyze_cell(cell, cutoff, TI)
+    p = _params(cell, inv_cell, pbc, cutoff, ncells)
+    n = length(X)
+    wsb(nmax) = max(256, Int(ccall((:nl_shard_workspace_bytes, libnlcuda), Csize_t, (Ref{NlParams}, Int64, Int32), p, nmax, nranks)))
+    ws = CuVector{UInt8}(undef, wsb(n))
+    info = Ref{NlShardInfo}()
+    _check(ccall((:nl_shard_prepare, libnlcuda), Cint,
+                 (Ref{NlParams}, CuPtr{Cvoid}, Int64, Ptr{Cvoid}, Int32, Int32, Ref{NlShardInfo}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                 p, X, n, comm, rank, nranks, info, ws, length(ws), _stream()))
+    f = info[]
+    nall = f.n_owned + f.n_halo_dn + f.n_halo_up
+    length(ws) < wsb(max(n, f.n_owned)) && (ws = CuVector{UInt8}(undef, wsb(max(n, f.n_owned))))
+    Xall = CuVector{SVec{T}}(undef, nall); gall = CuVector{TI}(undef, nall)
+    plane_active = ones(UInt8, ncells[3])
+    _check(ccall((:nl_shard_exchange, libnlcuda), Cint,
+                 (Ref{NlParams}, Ref{NlShardInfo}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{UInt8},
+                  CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                 p, info, X, gidx, n, comm, Xall, gall, plane_active, ws, length(ws), _stream()))
+    clist = NeighbourLists.build_cell_list(Xall, cutoff, cell, pbc; int_type = TI)
+    first, i, j, S = shard_pairlist(clist, f.n_owned, gall, (nranks > 1 && f.axis == 2) ? plane_active : nothing)
+    return (@view gall[1:f.n_owned]), first, i, j, S
 end
 
 end # module

@@ -521,10 +521,9 @@ __global__ void __launch_bounds__(256) k_fix_boundaries(const TI* __restrict__ f
 // ------------------------------------------------------------------------------------------------
 // i stream: i[p] = (row of pair p) for p in [0, first[n_rows] - 1); rows through gmap in shard mode.  One block per
 // EXP_RB consecutive ROWS, whose pairs are one contiguous range of the output: first[] of those rows sits in shared memory,
-// a thread owns EXP_PER consecutive pairs at a time (one binary search in shared memory, then a linear walk), 16-byte stores.
+// 16-byte stores, 512 contiguous bytes per warp instruction.
 constexpr int EXP_NT = 256;
 constexpr int EXP_RB = 512;
-constexpr int EXP_PER = 16;
 template <class TI>
 __global__ void __launch_bounds__(EXP_NT) k_expand_rows(const TI* __restrict__ first, long long n_rows, const TI* __restrict__ gmap, TI* __restrict__ io) {
   __shared__ long long sfirst[EXP_RB + 1];
@@ -534,18 +533,23 @@ __global__ void __launch_bounds__(EXP_NT) k_expand_rows(const TI* __restrict__ f
   __syncthreads();
   const long long P0 = sfirst[0], P1 = sfirst[nr];
   constexpr int VEC = 16 / (int)sizeof(TI);
-  // chunks of EXP_PER pairs aligned to EXP_PER in the GLOBAL pair index (16-byte aligned stores); the first and the last chunk
-  // of a block are shared with the neighbouring blocks and written element by element
-  for (long long q0 = (P0 & ~(long long)(EXP_PER - 1)) + (long long)EXP_PER * threadIdx.x; q0 < P1; q0 += (long long)EXP_PER * EXP_NT) {
-    const long long qs = q0 < P0 ? P0 : q0;
+  // A warp covers 128 consecutive 16-byte pieces (aligned in the GLOBAL pair index) per round; lane l owns pieces l, l + 32,
+  // l + 64, l + 96, so that every store instruction of the warp writes 512 contiguous bytes.  One binary search for the first
+  // piece, then a linear walk along first[] (rows are tens of pairs long).  The first and last piece of a block may be
+  // shared with the neighbouring blocks and are written element by element.
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  constexpr int WPAIRS = 128 * VEC;   // pairs per warp round
+  for (long long w0 = (P0 & ~(long long)(VEC - 1)) + (long long)wid * WPAIRS; w0 < P1; w0 += (long long)(EXP_NT / 32) * WPAIRS) {
+    long long q = w0 + (long long)lane * VEC;
+    const long long qs = q < P0 ? P0 : (q >= P1 ? P1 - 1 : q);
     int l = 0, h = nr;
     while (h - l > 1) { const int mid = (l + h) >> 1; if (sfirst[mid] <= qs) l = mid; else h = mid; }
     long long rend = sfirst[l + 1];
     TI cur = gmap ? gmap[r0 + l] : (TI)(r0 + l + 1);
 #pragma unroll
-    for (int c = 0; c < EXP_PER / VEC; c++) {
+    for (int c = 0; c < 4; c++, q += 32 * VEC) {
+      if (q >= P1) break;
       TI v[VEC];
-      const long long q = q0 + c * VEC;
 #pragma unroll
       for (int u = 0; u < VEC; u++) {
         while (q + u >= rend && l < nr - 1) {

@@ -91,10 +91,12 @@ __global__ void __launch_bounds__(256) k_prep_records(const T* __restrict__ Xs, 
   pz[s] = z;
   pidx[s] = idx;
   pw[s] = pwv;
-  RecAoS<T> r;
-  r.x = x; r.y = y; r.z = z; r.idx = idx; r.w = pwv;
-  ra[s] = r;
-  pkey[s] = (uint32_t)c[0] + (uint32_t)g.nc[0] * ((uint32_t)c[1] + (uint32_t)g.nc[1] * (uint32_t)c[2]);
+  if (ra) {  // AoS twin + cell key: only the original-order fill experiment (NL_FILL_ROWS=1) reads them
+    RecAoS<T> r;
+    r.x = x; r.y = y; r.z = z; r.idx = idx; r.w = pwv;
+    ra[s] = r;
+    pkey[s] = (uint32_t)c[0] + (uint32_t)g.nc[0] * ((uint32_t)c[1] + (uint32_t)g.nc[1] * (uint32_t)c[2]);
+  }
 }
 
 template <class TI>

@@ -179,11 +179,13 @@ int cell_ids_impl(const nl_params* p, const void* X, int64_t N, void* out, cudaS
   return NL_OK;
 }
 
+inline bool fill_tiled_requested();
+
 template <class T, class TI>
 int prep_impl(const nl_params* p, const void* Xs, int64_t N, const void* perm, PairWs& w, Geo<T>& g, cudaStream_t st) {
   if (N > 0) {
     k_prep_records<T, TI><<<(unsigned)((N + 255) / 256), 256, 0, st>>>((const T*)Xs, (const TI*)perm, N, g, (T*)w.px, (T*)w.py, (T*)w.pz,
-                                                                      w.pidx, w.pw, (RecAoS<T>*)w.ra, w.pkey);
+                                                                      w.pidx, w.pw, fill_tiled_requested() ? nullptr : (RecAoS<T>*)w.ra, w.pkey);
     NL_LAUNCHED(1);
     NL_LAUNCH_CHECK();
   }
