@@ -165,7 +165,8 @@ __device__ __forceinline__ int tile_table_nt(const int nc[3], const int pbc[3], 
 constexpr int SHP_ZERO = 1 | (1 << 2) | (1 << 4);  // pack_shift(0, 0, 0)
 
 template <class T, class TI, bool PARK>
-__global__ void __launch_bounds__(F2_NT, 2) k_fill_park(const MaskArgs<T, TI> a, unsigned char* __restrict__ parkA, unsigned char* __restrict__ parkR, int prefetch) {
+__global__ void __launch_bounds__(F2_NT, 2) k_fill_park(const MaskArgs<T, TI> a, unsigned char* __restrict__ parkA, unsigned char* __restrict__ parkR, int prefetch,
+                                                        int s_zeroed) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int CAP = f2_cap<T, TI>();
   constexpr int WB = f2_warp_bytes<T, TI>();
@@ -303,7 +304,8 @@ __global__ void __launch_bounds__(F2_NT, 2) k_fill_park(const MaskArgs<T, TI> a,
         if (sub >= o) incl += t;
       }
       const int my_nhit = __shfl_sync(FULL, incl, 7, 8);
-      if (!PARK && prefetch && my_nhit > 0 && sub < (has_R ? 6 : 4) && sub >= (prefetch >= 3 ? (prefetch == 3 ? 4 : 2) : 0)) {  // 3: R only, 4: S and R (experiments)
+      if (!PARK && prefetch && my_nhit > 0 && sub < (has_R ? 6 : 4) && sub >= (prefetch >= 3 ? (prefetch == 3 ? 4 : 2) : 0) &&
+          !(s_zeroed && (sub >> 1) == 1)) {  // 3: R only, 4: S and R (experiments); S rows are rarely written when the stream was zeroed up front
         // In place, the partial 32-byte sectors at both ends of a row segment are shared with the neighbouring rows, which
         // other warps write at other times: evicted half-written, each costs a DRAM read-modify-write.  Prefetching them
         // into L2 now makes the partial write land on a fully valid sector, which is later written back whole
@@ -396,6 +398,9 @@ __global__ void __launch_bounds__(F2_NT, 2) k_fill_park(const MaskArgs<T, TI> a,
             if (act) jrow[lane] = (TI)jv + 1;
             TI* const bS = (TI*)bufS;
             T* const bR = (T*)bufR;
+            // S: zero away from the periodic boundary.  With the stream zeroed up front by k_expand_rows (s_zeroed) such
+            // chunks skip S altogether: 27 % of the randomly placed bytes become a sequential fill
+            const bool writeS = !(zeroS && s_zeroed);
             if (act) {
               if (has_R) { bR[3 * lane] = R0; bR[3 * lane + 1] = R1; bR[3 * lane + 2] = R2; }
               if (!zeroS) { bS[3 * lane] = (TI)S0; bS[3 * lane + 1] = (TI)S1; bS[3 * lane + 2] = (TI)S2; }
@@ -406,7 +411,7 @@ __global__ void __launch_bounds__(F2_NT, 2) k_fill_park(const MaskArgs<T, TI> a,
             for (int m = 0; m < 3; m++) {
               const int w = m * 32 + lane;
               if (w < nw) {
-                Srow[w] = zeroS ? (TI)0 : bS[w];
+                if (writeS) Srow[w] = zeroS ? (TI)0 : bS[w];
                 if (has_R) a.out.Ro[3 * p0 + w] = bR[w];
               }
             }
@@ -525,7 +530,8 @@ __global__ void __launch_bounds__(256) k_fix_boundaries(const TI* __restrict__ f
 constexpr int EXP_NT = 256;
 constexpr int EXP_RB = 512;
 template <class TI>
-__global__ void __launch_bounds__(EXP_NT) k_expand_rows(const TI* __restrict__ first, long long n_rows, const TI* __restrict__ gmap, TI* __restrict__ io) {
+__global__ void __launch_bounds__(EXP_NT) k_expand_rows(const TI* __restrict__ first, long long n_rows, const TI* __restrict__ gmap, TI* __restrict__ io,
+                                                        TI* __restrict__ Szero) {
   __shared__ long long sfirst[EXP_RB + 1];
   const long long r0 = (long long)blockIdx.x * EXP_RB;
   const int nr = (int)min((long long)EXP_RB, n_rows - r0);
@@ -533,6 +539,21 @@ __global__ void __launch_bounds__(EXP_NT) k_expand_rows(const TI* __restrict__ f
   __syncthreads();
   const long long P0 = sfirst[0], P1 = sfirst[nr];
   constexpr int VEC = 16 / (int)sizeof(TI);
+  if (Szero) {
+    // S of this block's pairs := 0 (the fill pass then writes only the rows that cross a periodic boundary): a pure streaming
+    // fill, 16-byte stores over the aligned interior, element stores for the <= 3 words at either end
+    const long long w0 = 3 * P0, w1 = 3 * P1;                          // word range
+    const long long a0 = (w0 + VEC - 1) & ~(long long)(VEC - 1), a1 = w1 & ~(long long)(VEC - 1);
+    if (a0 >= a1) {
+      for (long long w = w0 + threadIdx.x; w < w1; w += EXP_NT) Szero[w] = (TI)0;
+    } else {
+      if (threadIdx.x < a0 - w0) Szero[w0 + threadIdx.x] = (TI)0;
+      if (threadIdx.x < w1 - a1) Szero[a1 + threadIdx.x] = (TI)0;
+      int4* d = (int4*)(Szero + a0);
+      const long long nv = (a1 - a0) / VEC;
+      for (long long v = threadIdx.x; v < nv; v += EXP_NT) __stcs(d + v, make_int4(0, 0, 0, 0));
+    }
+  }
   // A warp covers 128 consecutive 16-byte pieces (aligned in the GLOBAL pair index) per round; lane l owns pieces l, l + 32,
   // l + 64, l + 96, so that every store instruction of the warp writes 512 contiguous bytes.  One binary search for the first
   // piece, then a linear walk along first[] (rows are tens of pairs long).  The first and last piece of a block may be

@@ -15,6 +15,7 @@
 #include "nl_mask.cuh"
 #include "nl_fillrows.cuh"
 #include "nl_fill2.cuh"
+#include "nl_count2.cuh"
 #include "nl_shard.cuh"
 #include "nl_access.cuh"
 
@@ -278,6 +279,17 @@ inline int fill_prefetch() {
   return v;
 }
 
+inline int count_variant() {  // 1: k_count_mask2 (default), 0: k_count_mask
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NL_COUNT"); v = (e && e[0] == 'l') ? 0 : 1; }
+  return v;
+}
+inline bool fill_szero() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NL_FILL_SZERO"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
+
 // Opt-in to > 48 KB of dynamic shared memory.  The attribute is per DEVICE, so the "done" flags are per device too
 // (one process may drive several GPUs); a benign race at worst sets it twice.
 struct SmemOnce { bool done[64] = {}; };
@@ -387,15 +399,21 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
       a.srow = w.srow;
       k_row_starts<T, TI><<<(unsigned)((N + 255) / 256), 256, 0, st>>>(w.pidx, sk.first, N, sk.n_rows, (typename FillBase<TI>::type*)w.srow);
       NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
+      // the i stream is a pure function of first[]; the same streaming kernel zeroes S up front (NL_FILL_SZERO=0: off), so that
+      // the expansion only writes the S rows that cross a periodic boundary
+      const bool szero = fvar != 2 && fill_szero();
+      const bool expand = total_pairs > 0 && sk.n_rows > 0;
+      if (expand && szero)
+        k_expand_rows<TI><<<(unsigned)((sk.n_rows + EXP_RB - 1) / EXP_RB), EXP_NT, 0, st>>>(sk.first, sk.n_rows, sk.gmap, sk.io, sk.So);
       if (fvar == 2) {
-        k_fill_park<T, TI, true><<<nblk, F2_NT, F2_SMEM_BYTES, st>>>(a, w.parkA, w.parkR, 0);
+        k_fill_park<T, TI, true><<<nblk, F2_NT, F2_SMEM_BYTES, st>>>(a, w.parkA, w.parkR, 0, 0);
         k_fix_boundaries<T, TI><<<(unsigned)((sk.n_rows + 255) / 256), 256, 0, st>>>(sk.first, sk.n_rows, sk.jo, sk.So, sk.Ro, w.parkA, w.parkR);
         NL_LAUNCHED(1);
       } else {
-        k_fill_park<T, TI, false><<<nblk, F2_NT, F2_SMEM_BYTES, st>>>(a, nullptr, nullptr, fill_prefetch());
+        k_fill_park<T, TI, false><<<nblk, F2_NT, F2_SMEM_BYTES, st>>>(a, nullptr, nullptr, fill_prefetch(), expand && szero ? 1 : 0);
       }
-      if (total_pairs > 0 && sk.n_rows > 0)
-        k_expand_rows<TI><<<(unsigned)((sk.n_rows + EXP_RB - 1) / EXP_RB), EXP_NT, 0, st>>>(sk.first, sk.n_rows, sk.gmap, sk.io);
+      if (expand && !szero)
+        k_expand_rows<TI><<<(unsigned)((sk.n_rows + EXP_RB - 1) / EXP_RB), EXP_NT, 0, st>>>(sk.first, sk.n_rows, sk.gmap, sk.io, nullptr);
       NL_LAUNCHED(2);
     } else if (MODE == MODE_FILL) {
       static SmemOnce done;
@@ -410,11 +428,25 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
       k_fill_mask<T, TI><<<nblk, TILE_NT, FILL_SMEM_BYTES, st>>>(a);
     } else {
       // MODE_COUNT: with masks for the fill pass, or (lazy count on a problem the lazy plan rejected) without
-      static SmemOnce done;
-      int rc = set_smem_once(k_count_mask<T, TI, CM_MASK>, cm_smem_bytes(CM_MASK), done);
-      if (rc) return rc;
       NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
-      k_count_mask<T, TI, CM_MASK><<<nblk, TILE_NT, cm_smem_bytes(CM_MASK), st>>>(a);
+      bool launched = false;
+      if constexpr (sizeof(T) == 8) {
+        // Float64 full lists: candidates register-resident, home-atom pairs in the outer loop (nl_count2.cuh);
+        // NL_COUNT=legacy keeps round 1's chunk-major kernel for A/B measurements
+        if (!sk.half && count_variant() == 1) {
+          static SmemOnce done2;
+          int rc = set_smem_once(k_count_mask2<TI>, cm_smem_bytes(CM_MASK), done2);
+          if (rc) return rc;
+          k_count_mask2<TI><<<nblk, TILE_NT, cm_smem_bytes(CM_MASK), st>>>(a);
+          launched = true;
+        }
+      }
+      if (!launched) {
+        static SmemOnce done;
+        int rc = set_smem_once(k_count_mask<T, TI, CM_MASK>, cm_smem_bytes(CM_MASK), done);
+        if (rc) return rc;
+        k_count_mask<T, TI, CM_MASK><<<nblk, TILE_NT, cm_smem_bytes(CM_MASK), st>>>(a);
+      }
     }
     NL_LAUNCHED(1);
   } else if (pl.path != PATH_GENERIC) {
