@@ -15,6 +15,7 @@
 #include "nl_mask.cuh"
 #include "nl_fillrows.cuh"
 #include "nl_fill2.cuh"
+#include "nl_fill3.cuh"
 #include "nl_count2.cuh"
 #include "nl_shard.cuh"
 #include "nl_access.cuh"
@@ -81,9 +82,18 @@ int key_bits(long long nct) {
 struct BuildWs {
   uint32_t *keyA, *keyB, *valA, *valB;
   void* rs_scratch;
+  uint32_t* cnt;                 // bucket build: one counter per cell
+  unsigned long long* cnt_tsum;  //               scan scratch
   size_t total;
 };
-BuildWs build_ws(void* ws, int64_t N) {
+// The bucket (counting-sort) build serves grids that are not much larger than the atom count and cells that are not crowded
+// (the in-cell ordering reads a cell's whole segment per atom); everything else takes the radix sort.  NL_BUILD=radix forces it.
+inline bool bucket_build_ok(long long nct, int64_t N) {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NL_BUILD"); v = (e && e[0] == 'r') ? 0 : 1; }
+  return v == 1 && N > 0 && nct <= 4 * (long long)N + 4096 && (long long)N <= 24 * nct;
+}
+BuildWs build_ws(void* ws, int64_t N, long long nct) {
   BuildWs w;
   char* p = (char*)ws;
   size_t o = 0;
@@ -94,9 +104,13 @@ BuildWs build_ws(void* ws, int64_t N) {
   w.valA = (uint32_t*)take(nb);
   w.valB = (uint32_t*)take(nb);
   w.rs_scratch = take(rs_scratch_bytes(N > 0 ? N : 1));
+  const long long ncnt = bucket_build_ok(nct, N) ? nct : 0;
+  w.cnt = (uint32_t*)take((size_t)(ncnt + 1) * 4);
+  w.cnt_tsum = (unsigned long long*)take((size_t)(scan_tiles(ncnt + 1) + 1) * 8);
   w.total = o;
   return w;
 }
+inline long long params_nct(const nl_params* p) { return (long long)p->ncells[0] * p->ncells[1] * p->ncells[2]; }
 
 struct PairWs {
   void* hdr;
@@ -150,8 +164,20 @@ int build_cells_impl(const nl_params* p, const void* X, int64_t N, void* Xs, voi
                      cudaStream_t st) {
   Geo<T> g = make_geo<T>(p);
   const long long nct = g.nct;
-  BuildWs w = build_ws(ws, N);
+  BuildWs w = build_ws(ws, N, nct);
   const uint32_t* skeys = w.keyA;
+  if (bucket_build_ok(nct, N)) {
+    const unsigned nb = (unsigned)((N + 255) / 256);
+    NL_CUDA(cudaMemsetAsync(w.cnt, 0, (size_t)nct * 4, st));
+    k_bin_count<T><<<nb, 256, 0, st>>>((const T*)X, N, g, w.keyA, w.valA, w.cnt);
+    typedef typename std::conditional<sizeof(TI) == 4, uint32_t, unsigned long long>::type Acc;
+    exclusive_scan<uint32_t, Acc, TI>(w.cnt, nct, (TI*)cell_offsets, (Acc)1, true, (Acc*)w.cnt_tsum, (Acc*)nullptr, st);
+    k_bucket_scatter<TI><<<nb, 256, 0, st>>>(w.keyA, w.valA, (const TI*)cell_offsets, N, w.valB);
+    k_finalize_buckets<T, TI><<<nb, 256, 0, st>>>(w.valB, w.keyA, (const TI*)cell_offsets, (const T*)X, N, (T*)Xs, (TI*)perm, (TI*)cell_id);
+    NL_LAUNCHED(3);
+    NL_LAUNCH_CHECK();
+    return NL_OK;
+  }
   if (N > 0) {
     const unsigned nb = (unsigned)((N + 255) / 256);
     k_bin<T><<<nb, 256, 0, st>>>((const T*)X, N, g, w.keyA);
@@ -258,9 +284,9 @@ inline bool fill_tiled_requested() {
 // NL_FILL=park selects the experiment variant of the round-2 kernel that writes only complete sectors in place and parks the row
 // ends for k_fix_boundaries (nl_fill2.cuh; measured slower than the default: the parking costs more instructions than the
 // read-modify-writes it removes).
-inline int fill_variant() {  // 0 legacy k_fill_mask, 1 lean in-place k_fill_park<false> (default), 2 parked k_fill_park<true>
+inline int fill_variant() {  // 0 legacy k_fill_mask, 1 k_fill3 (default), 2 parked k_fill_park<true>, 3 lean in-place k_fill_park<false>
   static int v = -1;
-  if (v < 0) { const char* e = getenv("NL_FILL"); v = !e ? 1 : (e[0] == 'l' ? 0 : (e[0] == 'p' ? 2 : 1)); }
+  if (v < 0) { const char* e = getenv("NL_FILL"); v = !e ? 1 : (e[0] == 'l' ? 0 : (e[0] == 'p' ? 2 : (e[0] == '2' ? 3 : 1))); }
   return v;
 }
 
@@ -409,6 +435,18 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
         k_fill_park<T, TI, true><<<nblk, F2_NT, F2_SMEM_BYTES, st>>>(a, w.parkA, w.parkR, 0, 0);
         k_fix_boundaries<T, TI><<<(unsigned)((sk.n_rows + 255) / 256), 256, 0, st>>>(sk.first, sk.n_rows, sk.jo, sk.So, sk.Ro, w.parkA, w.parkR);
         NL_LAUNCHED(1);
+      } else if (expand && szero && fvar == 1) {
+        // default: plain / general row bodies over the pre-zeroed S stream (nl_fill3.cuh); NL_FILL=2 keeps k_fill_park for A/B
+        static SmemOnce done3, done3n;
+        if (sk.Ro) {
+          rc = set_smem_once(k_fill3<T, TI, true>, F2_SMEM_BYTES, done3);
+          if (rc) return rc;
+          k_fill3<T, TI, true><<<nblk, F2_NT, F2_SMEM_BYTES, st>>>(a, fill_prefetch());
+        } else {
+          rc = set_smem_once(k_fill3<T, TI, false>, F2_SMEM_BYTES, done3n);
+          if (rc) return rc;
+          k_fill3<T, TI, false><<<nblk, F2_NT, F2_SMEM_BYTES, st>>>(a, fill_prefetch());
+        }
       } else {
         k_fill_park<T, TI, false><<<nblk, F2_NT, F2_SMEM_BYTES, st>>>(a, nullptr, nullptr, fill_prefetch(), expand && szero ? 1 : 0);
       }
@@ -854,7 +892,7 @@ long long nl_launch_count(void) { return nl::launch_counter().load(); }
 
 size_t nl_workspace_bytes(const nl_params* params, int64_t N, int stage) {
   if (check_params(params, N) != NL_OK) return 0;
-  if (stage == NL_STAGE_BUILD) return build_ws(nullptr, N).total;
+  if (stage == NL_STAGE_BUILD) return build_ws(nullptr, N, params_nct(params)).total;
   if (stage == NL_STAGE_PAIRS) return pair_ws(nullptr, params, N).total_bytes;
   return 0;
 }
@@ -864,7 +902,7 @@ int nl_build_cells(const nl_params* params, const void* X, int64_t N, void* X_so
   int rc = check_params(params, N);
   if (rc) return rc;
   if (!cell_offsets || (N > 0 && (!X || !X_sorted || !perm || !cell_id))) return NL_ERR_BAD_ARG;
-  rc = check_ws(ws, ws_bytes, build_ws(nullptr, N).total);
+  rc = check_ws(ws, ws_bytes, build_ws(nullptr, N, params_nct(params)).total);
   if (rc) return rc;
   return NL_DISPATCH(params, build_cells_impl, params, X, N, X_sorted, perm, cell_id, cell_offsets, ws, (cudaStream_t)stream);
 }
