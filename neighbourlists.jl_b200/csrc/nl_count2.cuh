@@ -104,8 +104,17 @@ __device__ __noinline__ void c2_cell_slow(const MaskArgs<double, TI>* ad, const 
 // One home cell with NCH chunks of candidates (NCH = ceil(ncand / 32) exactly).  Returns true if some decision of the cell
 // could not be trusted (band, flagged slot): the caller queues the cell for c2_cell_slow.
 template <class TI, int NCH>
-__device__ __forceinline__ bool c2_cell(const MaskArgs<double, TI>& a, const float4* __restrict__ sq, const uint16_t* cslot, uint32_t* mkT, float* hb,
-                                        int lane, int hstart, int nh, long long hg0, int ncand, int fh) {
+__device__ __forceinline__ bool c2_cell(const MaskArgs<double, TI>& a, unsigned wofs, int lane, int hstart, int nh, long long hg0, int ncand, int fh) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int TABCAP = cm_tabcap(CM_MASK);
+  constexpr int OFF_SQ = 3 * TILE_VPAD * 4 + 64 * 4 + (TILE_NT / 32) * cm_warp_bytes(CM_MASK);
+  // this warp's shared-memory pointers are rebuilt from one opaque offset: carried across the cell loop they get spilled,
+  // and with 4 x 48 KB of shared memory per SM the L1 that is left does not hold the stacks
+  asm volatile("" : "+r"(wofs));
+  const float4* const sq = (const float4*)(smem_raw + OFF_SQ);
+  const uint16_t* const cslot = (const uint16_t*)(smem_raw + wofs);
+  uint32_t* const mkT = (uint32_t*)(smem_raw + wofs + TABCAP * 3);
+  float* const hb = (float*)(smem_raw + wofs + TABCAP * 3 + MASK_WORDS * 34 * 4);
   const float mid = a.mid, hw = a.hw;
   const float2 nmid2 = make_float2(-mid, -mid);
   float qx[NCH], qy[NCH], qz[NCH];
@@ -200,6 +209,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_C2_MINB) k_count_mask2(const MaskA
   const Geo<T>& g = a.g;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   unsigned char* wb = wbase + wid * CNT_WARP_BYTES;
+  const unsigned wofs = (unsigned)(wb - smem_raw);
   uint16_t* cslot = (uint16_t*)wb;
   uint32_t* mkT = (uint32_t*)(wb + TABCAP * 3);                   // [MASK_WORDS][34]: word k of home atom aa at k * 34 + aa
   float* hb = (float*)(wb + TABCAP * 3 + MASK_WORDS * 34 * 4);    // [16 pairs][8]: x0 x1 y0 y1 z0 z1 - -
@@ -280,19 +290,23 @@ __global__ void __launch_bounds__(TILE_NT, NL_C2_MINB) k_count_mask2(const MaskA
     int ncand, fh;
     {
       int st = 0, cn = 0;
-      if (lane < 27) {
-        const int v = ((lz + lane / 9) * VY + (ly + (lane / 3) % 3)) * VX + (lx + lane % 3);
+      int l2 = lane;
+      unsigned wo = wofs;
+      asm volatile("" : "+r"(l2), "+r"(wo));
+      uint16_t* const cs = (uint16_t*)(smem_raw + wo);
+      if (l2 < 27) {
+        const int v = ((lz + l2 / 9) * VY + (ly + (l2 / 3) % 3)) * VX + (lx + l2 % 3);
         st = vstart[v];
         cn = vstart[v + 1] - st;
       }
-      const int incl = warp_incl_scan(cn, lane);
+      const int incl = warp_incl_scan(cn, l2);
       ncand = __shfl_sync(FULL, incl, 31);
       fh = __shfl_sync(FULL, incl, 12);
       if (ncand <= TABCAP) {
         const int pre = incl - cn;
         const int mx = __reduce_max_sync(FULL, cn);
         for (int j = 0; j < mx; j++)
-          if (j < cn) cslot[pre + j] = (uint16_t)(st + j);
+          if (j < cn) cs[pre + j] = (uint16_t)(st + j);
       }
       __syncwarp();
     }
@@ -303,14 +317,14 @@ __global__ void __launch_bounds__(TILE_NT, NL_C2_MINB) k_count_mask2(const MaskA
     }
     bool rare;
     switch ((ncand + 31) >> 5) {
-      case 1: rare = c2_cell<TI, 1>(a, sq, cslot, mkT, hb, lane, hstart, nh, hg0, ncand, fh); break;
-      case 2: rare = c2_cell<TI, 2>(a, sq, cslot, mkT, hb, lane, hstart, nh, hg0, ncand, fh); break;
-      case 3: rare = c2_cell<TI, 3>(a, sq, cslot, mkT, hb, lane, hstart, nh, hg0, ncand, fh); break;
-      case 4: rare = c2_cell<TI, 4>(a, sq, cslot, mkT, hb, lane, hstart, nh, hg0, ncand, fh); break;
-      case 5: rare = c2_cell<TI, 5>(a, sq, cslot, mkT, hb, lane, hstart, nh, hg0, ncand, fh); break;
-      case 6: rare = c2_cell<TI, 6>(a, sq, cslot, mkT, hb, lane, hstart, nh, hg0, ncand, fh); break;
-      case 7: rare = c2_cell<TI, 7>(a, sq, cslot, mkT, hb, lane, hstart, nh, hg0, ncand, fh); break;
-      default: rare = c2_cell<TI, 8>(a, sq, cslot, mkT, hb, lane, hstart, nh, hg0, ncand, fh); break;
+      case 1: rare = c2_cell<TI, 1>(a, wofs, lane, hstart, nh, hg0, ncand, fh); break;
+      case 2: rare = c2_cell<TI, 2>(a, wofs, lane, hstart, nh, hg0, ncand, fh); break;
+      case 3: rare = c2_cell<TI, 3>(a, wofs, lane, hstart, nh, hg0, ncand, fh); break;
+      case 4: rare = c2_cell<TI, 4>(a, wofs, lane, hstart, nh, hg0, ncand, fh); break;
+      case 5: rare = c2_cell<TI, 5>(a, wofs, lane, hstart, nh, hg0, ncand, fh); break;
+      case 6: rare = c2_cell<TI, 6>(a, wofs, lane, hstart, nh, hg0, ncand, fh); break;
+      case 7: rare = c2_cell<TI, 7>(a, wofs, lane, hstart, nh, hg0, ncand, fh); break;
+      default: rare = c2_cell<TI, 8>(a, wofs, lane, hstart, nh, hg0, ncand, fh); break;
     }
     if (rare) {
       if (lane == 0) rare_list[nrare] = (uint8_t)hc;

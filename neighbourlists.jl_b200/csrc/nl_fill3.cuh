@@ -16,6 +16,10 @@
 
 namespace nl {
 
+#ifndef NL_F3_LIST2
+#define NL_F3_LIST2 0
+#endif
+
 // One row, plain case: nhit hits of the home atom staged at slot hs; L = its hit list (flat candidate numbers), tab = flat
 // candidate -> staged slot.  j straight from the lane, R transposed through shared memory so that every store instruction
 // writes one contiguous run.
@@ -200,7 +204,15 @@ __global__ void __launch_bounds__(F2_NT, 2) k_fill3(const MaskArgs<T, TI> a, int
     const int lx = hcell[tid] & 255, ly = (hcell[tid] >> 8) & 255, lz = (hcell[tid] >> 16) & 255;
     if (a.cellflag[cell_linear(g.nc, hx0 + lx, hy0 + ly, hz0 + lz)]) hcell[tid] |= 1 << 24;
   }
-  const bool tile_plain = __syncthreads_and(all_zero_wind) != 0;  // every staged atom lies inside the box (winding 0): no per-pair compare
+  // every staged atom lies inside the box (winding 0): no per-pair compare.  Kept in shared memory, like every other tile-wide
+  // value the cell loop needs only once per cell: in registers they get spilled, and a spill reload at the head of a cell
+  // was 8 % of this kernel's stall samples (the L1 left beside 2 x 104 KB of shared memory does not hold the stacks)
+  __shared__ int s_tile_plain;
+  {
+    const int tp = __syncthreads_and(all_zero_wind);
+    if (tid == 0) s_tile_plain = tp;
+  }
+  __syncthreads();
   const BaseT* __restrict__ srow = (const BaseT*)a.srow;
   const T cz0 = cstab[4 * SHP_ZERO], cz1 = cstab[4 * SHP_ZERO + 1], cz2 = cstab[4 * SHP_ZERO + 2];  // cell' * 0 under the contract (+0)
 
@@ -228,12 +240,18 @@ __global__ void __launch_bounds__(F2_NT, 2) k_fill3(const MaskArgs<T, TI> a, int
     bool fastcell;
     {
       int st = 0, cn = 0, shp = SHP_ZERO;
-      if (lane < 27) {
-        const int v = ((lz + lane / 9) * VY + (ly + (lane / 3) % 3)) * VX + (lx + lane % 3);
+      int l2 = lane;
+      unsigned wo = wofs;
+      asm volatile("" : "+r"(l2), "+r"(wo));  // rebuild the stencil coordinates and this warp's shared-memory pointers here
+                                              // instead of carrying (and spilling) them across the cell loop
+      uint16_t* const tab = (uint16_t*)(smem_raw + wo);
+      uint8_t* const shc = smem_raw + wo + 6 * MASK_MAXCAND;
+      if (l2 < 27) {
+        const int v = ((lz + l2 / 9) * VY + (ly + (l2 / 3) % 3)) * VX + (lx + l2 % 3);
         st = vstart[v];
         cn = vstart[v + 1] - st;
         if (cn > 0) shp = vsh[v];
-        shc[lane] = (uint8_t)shp;
+        shc[l2] = (uint8_t)shp;
       }
       const int incl = warp_incl_scan(cn, lane);
       const int pre = incl - cn;
@@ -244,7 +262,7 @@ __global__ void __launch_bounds__(F2_NT, 2) k_fill3(const MaskArgs<T, TI> a, int
       fastcell = __all_sync(FULL, shp == SHP_ZERO);
     }
     __syncwarp();
-    const bool plain = tile_plain && fastcell;
+    const bool plain = fastcell && s_tile_plain != 0;
 
     for (int a0 = 0; a0 < nh; a0 += 4) {
       uint32_t word = nx_word;
@@ -276,13 +294,28 @@ __global__ void __launch_bounds__(F2_NT, 2) k_fill3(const MaskArgs<T, TI> a, int
       }
       __syncwarp();
       {
-        uint8_t* Lw = lists + grp * MASK_MAXCAND + (incl - pc);
+        unsigned wo = wofs;
+        asm volatile("" : "+r"(wo));
+        uint8_t* Lw = smem_raw + wo + 2 * MASK_MAXCAND + grp * MASK_MAXCAND + (incl - pc);
         const int fb = sub * 32;
+#if NL_F3_LIST2
+        // the lane with the fullest word sets the pace of the whole warp (~14 hits against ~3 on average: the chunks of the
+        // cells next to the home cell), so every trip takes the lowest AND the highest set bit: half the trips
+        uint8_t* Lh = Lw + pc - 1;
+        while (word) {
+          const int lo = __ffs(word) - 1, hi = 31 - __clz(word);
+          *Lw++ = (uint8_t)(fb + lo);
+          *Lh-- = (uint8_t)(fb + hi);   // lo == hi on the last trip of an odd count: same value, same place
+          word &= word - 1;
+          word &= ~(1u << hi);
+        }
+#else
         while (word) {
           const int bit = __ffs(word) - 1;
           word &= word - 1;
           *Lw++ = (uint8_t)(fb + bit);
         }
+#endif
       }
       __syncwarp();
 
