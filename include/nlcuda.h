@@ -266,6 +266,30 @@ NL_API int nl_bounding_box(int32_t float_type, const void* X, int64_t N, void* m
 NL_API int nl_max_displacement2(int32_t float_type, const void* X, const void* X_ref, int64_t N, void* d2_out, void* ws,
                                 size_t ws_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Array(PairList): the whole materialised list into HOST memory -- what a host consumer of neighbour_list receives
+ * (the reference's CPU path returns host Vectors, src/cell_list.jl:897-916; its GPU tests bring the device list back with
+ * Array(...) field by field, test/test_utils.jl:127-131).  Transfer format: over the bus go `first` (n_rows + 1 TI), `j`
+ * (P TI) and ONE BYTE per pair for S, code = (Sx+1) + 3 (Sy+1) + 9 (Sz+1) packed on the device; `i` is rebuilt from `first`
+ * (i[p] = r for first[r] <= p+1 < first[r+1]) and S from the codes by `nthreads` host threads of the library (non-temporal
+ * stores) while the copies are in flight: 5 B/pair instead of 20 B/pair of PCIe traffic.  A list with a shift component
+ * outside {-1, 0, 1} sends S as it is (detected on the device, no caller involvement).
+ *   first, j, S     in   DEVICE  the PairList arrays (S must be 16-byte aligned for the fast path; any alignment works)
+ *   i               in   DEVICE  NULL: rebuild i from first (a whole list, i[p] = row).  Non-NULL: copy it (shard lists,
+ *                                whose i runs through an index map)
+ *   *_host          out  HOST    n_rows + 1, P, P, 3 P elements of TI; pinned memory for full PCIe speed
+ *   dev_scratch / host_scratch   nl_to_host_scratch_bytes(P) bytes each, 16-byte aligned; host_scratch pinned
+ *   nthreads        host worker threads (<= 0: hardware concurrency)
+ * Blocks until every host array is complete (it is a device -> host read); enqueues on `stream`.
+ * NL_ERR_BAD_ARG if first[n_rows] - 1 != P.                                                                        */
+NL_API size_t nl_to_host_scratch_bytes(int64_t P);
+NL_API int nl_pairs_to_host(const nl_params* params, const void* first, int64_t n_rows, const void* i, const void* j,
+                            const void* S, int64_t P, void* first_host, void* i_host, void* j_host, void* S_host,
+                            void* dev_scratch, void* host_scratch, size_t scratch_bytes, int32_t nthreads, void* stream);
+/* The two host-side decoders of that format on their own (pure host code, no CUDA call): pairs [p_lo, p_hi), 0-based.  */
+NL_API int nl_host_expand_rows(int32_t int_type, const void* first, int64_t n_rows, int64_t p_lo, int64_t p_hi, void* i_out);
+NL_API int nl_host_unpack_shifts(int32_t int_type, const uint8_t* codes, int64_t p_lo, int64_t p_hi, void* S_out);
+
 #ifdef __cplusplus
 }
 #endif

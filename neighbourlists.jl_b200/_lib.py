@@ -60,7 +60,8 @@ _lib = None
 EXPORTS = ("nl_version", "nl_strerror", "nl_last_cuda_error", "nl_launch_count", "nl_workspace_bytes", "nl_build_cells", "nl_count_pairs",
            "nl_fill_pairs", "nl_fill_pairs_rows", "nl_count_pairs_window", "nl_fill_pairs_window", "nl_cell_ids", "nl_shard_plan", "nl_lazy_count", "nl_lazy_lj_energy", "nl_lazy_lj_forces",
            "nl_pairs_R", "nl_max_neighbours", "nl_rows_padded", "nl_lazy_neighbours", "nl_bounding_box", "nl_max_displacement2",
-           "nl_shard_workspace_bytes", "nl_shard_prepare", "nl_shard_exchange", "nl_nccl_unique_id", "nl_nccl_comm_init", "nl_nccl_comm_destroy")
+           "nl_shard_workspace_bytes", "nl_shard_prepare", "nl_shard_exchange", "nl_nccl_unique_id", "nl_nccl_comm_init", "nl_nccl_comm_destroy",
+           "nl_to_host_scratch_bytes", "nl_pairs_to_host", "nl_host_expand_rows", "nl_host_unpack_shifts")
 NL_REDUCE_WS_BYTES = 32768
 
 
@@ -118,6 +119,14 @@ def lib():
         for n in ("nl_build_cells", "nl_count_pairs", "nl_fill_pairs", "nl_fill_pairs_rows", "nl_count_pairs_window", "nl_fill_pairs_window", "nl_cell_ids", "nl_shard_plan", "nl_lazy_count",
                   "nl_lazy_lj_energy"):
             getattr(L, n).restype = C.c_int
+        L.nl_to_host_scratch_bytes.restype = sz
+        L.nl_to_host_scratch_bytes.argtypes = [i64]
+        L.nl_pairs_to_host.argtypes = [pp, vp, i64, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, sz, C.c_int32, vp]
+        L.nl_pairs_to_host.restype = C.c_int
+        L.nl_host_expand_rows.argtypes = [C.c_int32, vp, i64, i64, i64, vp]
+        L.nl_host_expand_rows.restype = C.c_int
+        L.nl_host_unpack_shifts.argtypes = [C.c_int32, vp, i64, i64, vp]
+        L.nl_host_unpack_shifts.restype = C.c_int
         _lib = L
     return _lib
 

@@ -261,6 +261,81 @@ def neighbour_list(X, cutoff, cell=None, pbc=None, *, lazy: bool = False, int_ty
     return materialize_pairlist(clist, with_R=with_R, half=half)
 
 
+
+# ------------------------------------------------------------------ Array(PairList): the list in host memory
+@dataclass
+class HostPairList:
+    """PairList with every array in HOST memory (numpy views of the pinned buffers they were copied into): what
+    `Array(...)` of each field gives in the reference (test/test_utils.jl:127-131).  1-based like the device list."""
+    X: object
+    C: np.ndarray
+    cutoff: float
+    i: np.ndarray
+    j: np.ndarray
+    S: np.ndarray
+    first: np.ndarray
+
+
+class HostPairBuffers:
+    """Pinned host buffers (and the device / host scratch of the transfer) for `to_host`, reusable across lists:
+    allocating 5 GB of pinned memory costs more than building the list."""
+
+    def __init__(self, pair_capacity: int, n_rows: int, int_type=np.int32, device=None):
+        it = _int_dtype(int_type)
+        self.int_dtype = it
+        self.pair_capacity = int(pair_capacity)
+        self.row_capacity = int(n_rows)
+        self.device = torch.device(device if device is not None else "cuda")
+        nb = _lib.lib().nl_to_host_scratch_bytes(self.pair_capacity)
+        self.first = torch.empty(self.row_capacity + 1, dtype=it).pin_memory()
+        self.i = torch.empty(max(self.pair_capacity, 1), dtype=it).pin_memory()
+        self.j = torch.empty(max(self.pair_capacity, 1), dtype=it).pin_memory()
+        self.S = torch.empty((max(self.pair_capacity, 1), 3), dtype=it).pin_memory()
+        self.host_scratch = torch.empty(nb, dtype=torch.uint8).pin_memory()
+        self.dev_scratch = torch.empty(nb, dtype=torch.uint8, device=self.device)
+
+    def fits(self, P: int, n_rows: int, it) -> bool:
+        return P <= self.pair_capacity and n_rows <= self.row_capacity and it == self.int_dtype
+
+
+_host_buffers: Optional[HostPairBuffers] = None
+
+
+def to_host(nlist: PairList, out: Optional[HostPairBuffers] = None, nthreads: int = 0, rebuild_i: Optional[bool] = None) -> HostPairList:
+    """The whole list into host memory through nl_pairs_to_host (include/nlcuda.h): `first`, `j` and one byte per pair for S
+    cross the bus; i and S are rebuilt by host threads of the library while the copies run.  Returns when every array is
+    complete.  `out`: buffers to reuse (default: a module-level set grown on demand).  rebuild_i=False copies i instead of
+    rebuilding it from `first` (needed for shard lists, whose i carries global indices; detected from the list's length)."""
+    global _host_buffers
+    P = int(nlist.i.shape[0])
+    n_rows = int(nlist.first.shape[0]) - 1
+    it = nlist.i.dtype
+    dev = nlist.i.device
+    if out is None:
+        if _host_buffers is None or not _host_buffers.fits(P, n_rows, it) or _host_buffers.device != dev:
+            _host_buffers = None
+            _host_buffers = HostPairBuffers(int(P * 1.05) + 1024, n_rows, it, dev)
+        out = _host_buffers
+    elif not out.fits(P, n_rows, it):
+        raise ValueError("host buffers too small for this list")
+    if rebuild_i is None:
+        rebuild_i = n_rows == int(nlist.X.shape[0])   # a whole list: i[p] is the row of p
+    S = nlist.S if nlist.S.is_contiguous() else nlist.S.contiguous()
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().nl_pairs_to_host(nlist.params, _ptr(nlist.first), n_rows, None if rebuild_i else _ptr(nlist.i), _ptr(nlist.j),
+                                               _ptr(S), P, out.first.data_ptr(), out.i.data_ptr(), out.j.data_ptr(), out.S.data_ptr(),
+                                               out.dev_scratch.data_ptr(), out.host_scratch.data_ptr(), out.dev_scratch.numel(),
+                                               int(nthreads), _stream(dev)))
+    return HostPairList(X=nlist.X, C=nlist.C, cutoff=nlist.cutoff, i=out.i[:P].numpy(), j=out.j[:P].numpy(), S=out.S[:P].numpy(),
+                        first=out.first[:n_rows + 1].numpy())
+
+
+def to_host_bytes(nlist: PairList, rebuild_i: bool = True) -> int:
+    """Bytes nl_pairs_to_host moves over the bus for this list (when no shift component escapes the one-byte code)."""
+    P = int(nlist.i.shape[0])
+    w = nlist.i.element_size()
+    return (int(nlist.first.shape[0])) * w + P * w + P + 4 + (0 if rebuild_i else P * w)
+
 # ------------------------------------------------------------------ accessors (src/cell_list.jl:25-27, 507-611, 753-833, 919-927)
 def npairs(nlist: PairList) -> int:
     return int(nlist.i.shape[0])

@@ -19,6 +19,7 @@
 #include "nl_count2.cuh"
 #include "nl_shard.cuh"
 #include "nl_access.cuh"
+#include "nl_tohost.cuh"
 
 namespace {
 
@@ -866,6 +867,101 @@ int check_ws(const void* ws, size_t have, size_t need) {
   return NL_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// nl_pairs_to_host: see nl_tohost.cuh.  Only the calling thread talks to CUDA; the worker threads wait on a counter.
+template <class TI>
+int pairs_to_host_impl(const void* first_d, int64_t n_rows, const void* i_d, const void* j_d, const void* S_d, int64_t P, void* first_h,
+                       void* i_h, void* j_h, void* S_h, void* dscratch, void* hscratch, int nthreads, cudaStream_t st) {
+  NL_CUDA(cudaMemcpyAsync(first_h, first_d, (size_t)(n_rows + 1) * sizeof(TI), cudaMemcpyDeviceToHost, st));
+  if (P == 0) {
+    NL_CUDA(cudaStreamSynchronize(st));
+    return NL_OK;
+  }
+  uint8_t* codes_d = (uint8_t*)dscratch;
+  uint8_t* codes_h = (uint8_t*)hscratch;
+  unsigned* flag_d = (unsigned*)(codes_d + al256((size_t)P));
+  volatile unsigned* flag_h = (volatile unsigned*)(codes_h + al256((size_t)P));
+  NL_CUDA(cudaMemsetAsync(flag_d, 0, 4, st));
+  const unsigned nb = (unsigned)((P + 256 * TH_PAIRS - 1) / (256 * TH_PAIRS));
+  k_pack_shifts<TI><<<nb, 256, 0, st>>>((const TI*)S_d, (long long)P, codes_d, flag_d, (((uintptr_t)S_d) & 15) == 0 ? 1 : 0);
+  NL_LAUNCHED(1);
+  NL_LAUNCH_CHECK();
+  NL_CUDA(cudaMemcpyAsync((void*)flag_h, flag_d, 4, cudaMemcpyDeviceToHost, st));
+
+  const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(16, (P + (32ll << 20) - 1) / (32ll << 20)));
+  const int64_t chunk = ((P + nchunks - 1) / nchunks + 63) & ~(int64_t)63;  // multiple of 64 pairs: slices of S stay 16-byte aligned
+  std::vector<cudaEvent_t> ev(nchunks + 1, nullptr);
+  auto destroy = [&]() { for (auto e : ev) if (e) cudaEventDestroy(e); };
+  for (auto& e : ev) {
+    cudaError_t ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (ce != cudaSuccess) { destroy(); return cuda_fail(ce); }
+  }
+#define NL_CUDA_EV(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { destroy(); return cuda_fail(e__); } } while (0)
+  NL_CUDA_EV(cudaEventRecord(ev[0], st));  // first + escape flag are on the host
+  for (int k = 0; k < nchunks; k++) {
+    const int64_t c0 = (int64_t)k * chunk, c1 = std::min<int64_t>(P, c0 + chunk);
+    if (c1 > c0) NL_CUDA_EV(cudaMemcpyAsync(codes_h + c0, codes_d + c0, (size_t)(c1 - c0), cudaMemcpyDeviceToHost, st));
+    NL_CUDA_EV(cudaEventRecord(ev[k + 1], st));
+  }
+  if (i_d) NL_CUDA_EV(cudaMemcpyAsync(i_h, i_d, (size_t)P * sizeof(TI), cudaMemcpyDeviceToHost, st));
+  NL_CUDA_EV(cudaMemcpyAsync(j_h, j_d, (size_t)P * sizeof(TI), cudaMemcpyDeviceToHost, st));
+#undef NL_CUDA_EV
+
+  std::atomic<int> ready{0};  // 1: first + flag; 2 + k: code chunk k; -1: abort
+  std::atomic<int> escape{0};
+  const int T = std::max(1, std::min(nthreads, 256));
+  std::vector<std::thread> workers;
+  workers.reserve(T);
+  auto wait_for = [&ready](int need) {
+    int v;
+    while ((v = ready.load(std::memory_order_acquire)) < need && v >= 0) std::this_thread::yield();
+    return v >= 0;
+  };
+  for (int t = 0; t < T; t++) {
+    workers.emplace_back([&, t]() {
+      if (!wait_for(1)) return;
+      if (!i_d) {
+        const int64_t q = ((P + T - 1) / T + 3) & ~(int64_t)3;
+        host_expand_rows<TI>((const TI*)first_h, (long long)n_rows, std::min<int64_t>(P, q * t), std::min<int64_t>(P, q * (t + 1)), (TI*)i_h);
+      }
+      if (escape.load(std::memory_order_relaxed)) return;
+      for (int k = 0; k < nchunks; k++) {
+        if (!wait_for(2 + k)) return;
+        const int64_t c0 = (int64_t)k * chunk, c1 = std::min<int64_t>(P, c0 + chunk);
+        if (c1 <= c0) continue;
+        const int64_t q = ((c1 - c0 + T - 1) / T + 3) & ~(int64_t)3;
+        host_unpack_shifts<TI>(codes_h, std::min(c1, c0 + q * t), std::min(c1, c0 + q * (t + 1)), (TI*)S_h);
+      }
+    });
+  }
+  int rc = NL_OK;
+  auto stop_workers = [&](int code) { rc = code; ready.store(-1, std::memory_order_release); };
+  cudaError_t ce = cudaEventSynchronize(ev[0]);
+  if (ce != cudaSuccess) stop_workers(cuda_fail(ce));
+  else if ((int64_t)((const TI*)first_h)[n_rows] - 1 != P || ((const TI*)first_h)[0] != 1) stop_workers(NL_ERR_BAD_ARG);  // first and P do not belong together
+  else {
+    const bool esc = *flag_h != 0;
+    if (esc) escape.store(1, std::memory_order_relaxed);
+    ready.store(1, std::memory_order_release);
+    if (esc) {  // a shift component outside {-1, 0, 1}: S goes over the bus as it is
+      ce = cudaMemcpyAsync(S_h, S_d, (size_t)P * 3 * sizeof(TI), cudaMemcpyDeviceToHost, st);
+      if (ce != cudaSuccess) stop_workers(cuda_fail(ce));
+    } else {
+      for (int k = 0; k < nchunks && rc == NL_OK; k++) {
+        ce = cudaEventSynchronize(ev[k + 1]);
+        if (ce != cudaSuccess) stop_workers(cuda_fail(ce));
+        else ready.store(2 + k, std::memory_order_release);
+      }
+    }
+  }
+  ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess && rc == NL_OK) stop_workers(cuda_fail(ce));
+  for (auto& w : workers) w.join();
+  destroy();
+  return rc;
+}
+
 }  // namespace
 
 // ================================================================ exported C ABI
@@ -1138,6 +1234,48 @@ int nl_max_displacement2(int32_t float_type, const void* X, const void* X_ref, i
   if (rc) return rc;
   return float_type == NL_F64 ? maxdisp_impl<double>(X, X_ref, N, d2_out, ws, (cudaStream_t)stream)
                               : maxdisp_impl<float>(X, X_ref, N, d2_out, ws, (cudaStream_t)stream);
+}
+
+size_t nl_to_host_scratch_bytes(int64_t P) { return al256((size_t)(P > 0 ? P : 0)) + 256; }
+
+int nl_pairs_to_host(const nl_params* params, const void* first, int64_t n_rows, const void* i, const void* j, const void* S, int64_t P,
+                     void* first_host, void* i_host, void* j_host, void* S_host, void* dev_scratch, void* host_scratch, size_t scratch_bytes,
+                     int32_t nthreads, void* stream) {
+  if (!params || (params->int_type != NL_I32 && params->int_type != NL_I64)) return NL_ERR_BAD_ARG;
+  if (n_rows < 0 || P < 0 || !first || !first_host) return NL_ERR_BAD_ARG;
+  if (P > 0 && (!j || !S || !i_host || !j_host || !S_host)) return NL_ERR_BAD_ARG;
+  if (P > 0) {
+    if (!dev_scratch || !host_scratch || scratch_bytes < nl_to_host_scratch_bytes(P)) return NL_ERR_WORKSPACE;
+    if ((((uintptr_t)dev_scratch) | ((uintptr_t)host_scratch)) & 15) return NL_ERR_WORKSPACE;
+  }
+  if (nthreads <= 0) nthreads = (int32_t)std::max(1u, std::thread::hardware_concurrency());
+  cudaStream_t st = (cudaStream_t)stream;
+  return params->int_type == NL_I64
+             ? pairs_to_host_impl<int64_t>(first, n_rows, i, j, S, P, first_host, i_host, j_host, S_host, dev_scratch, host_scratch, nthreads, st)
+             : pairs_to_host_impl<int32_t>(first, n_rows, i, j, S, P, first_host, i_host, j_host, S_host, dev_scratch, host_scratch, nthreads, st);
+}
+
+int nl_host_expand_rows(int32_t int_type, const void* first, int64_t n_rows, int64_t p_lo, int64_t p_hi, void* i_out) {
+  if ((int_type != NL_I32 && int_type != NL_I64) || n_rows < 0 || p_lo < 0 || p_hi < p_lo) return NL_ERR_BAD_ARG;
+  if (p_hi == p_lo) return NL_OK;
+  if (!first || !i_out || n_rows == 0) return NL_ERR_BAD_ARG;
+  if (int_type == NL_I64) {
+    if (p_hi > ((const int64_t*)first)[n_rows] - 1) return NL_ERR_BAD_ARG;
+    host_expand_rows<int64_t>((const int64_t*)first, n_rows, p_lo, p_hi, (int64_t*)i_out);
+  } else {
+    if (p_hi > (int64_t)((const int32_t*)first)[n_rows] - 1) return NL_ERR_BAD_ARG;
+    host_expand_rows<int32_t>((const int32_t*)first, n_rows, p_lo, p_hi, (int32_t*)i_out);
+  }
+  return NL_OK;
+}
+
+int nl_host_unpack_shifts(int32_t int_type, const uint8_t* codes, int64_t p_lo, int64_t p_hi, void* S_out) {
+  if ((int_type != NL_I32 && int_type != NL_I64) || p_lo < 0 || p_hi < p_lo) return NL_ERR_BAD_ARG;
+  if (p_hi == p_lo) return NL_OK;
+  if (!codes || !S_out) return NL_ERR_BAD_ARG;
+  if (int_type == NL_I64) host_unpack_shifts<int64_t>(codes, p_lo, p_hi, (int64_t*)S_out);
+  else host_unpack_shifts<int32_t>(codes, p_lo, p_hi, (int32_t*)S_out);
+  return NL_OK;
 }
 
 }  // extern "C"
