@@ -275,16 +275,18 @@ NL_API int nl_max_displacement2(int32_t float_type, const void* X, const void* X
  * stores) while the copies are in flight: 5 B/pair instead of 20 B/pair of PCIe traffic.  A list with a shift component
  * outside {-1, 0, 1} sends S as it is (detected on the device, no caller involvement).
  *   first, j, S     in   DEVICE  the PairList arrays (S must be 16-byte aligned for the fast path; any alignment works)
- *   i               in   DEVICE  NULL: rebuild i from first (a whole list, i[p] = row).  Non-NULL: copy it (shard lists,
- *                                whose i runs through an index map)
+ *   i, i_copy_from  in   DEVICE  pairs [0, i_copy_from) of i are rebuilt from first (a whole list: i[p] = row of p), pairs
+ *                                [i_copy_from, P) are copied from the device array `i` (NULL allowed when i_copy_from == P).
+ *                                Shard lists, whose i runs through an index map, pass 0.  A whole list may split i between
+ *                                the host threads and the bus; i_copy_from == P was fastest where measured.
  *   *_host          out  HOST    n_rows + 1, P, P, 3 P elements of TI; pinned memory for full PCIe speed
  *   dev_scratch / host_scratch   nl_to_host_scratch_bytes(P) bytes each, 16-byte aligned; host_scratch pinned
  *   nthreads        host worker threads (<= 0: hardware concurrency)
  * Blocks until every host array is complete (it is a device -> host read); enqueues on `stream`.
  * NL_ERR_BAD_ARG if first[n_rows] - 1 != P.                                                                        */
 NL_API size_t nl_to_host_scratch_bytes(int64_t P);
-NL_API int nl_pairs_to_host(const nl_params* params, const void* first, int64_t n_rows, const void* i, const void* j,
-                            const void* S, int64_t P, void* first_host, void* i_host, void* j_host, void* S_host,
+NL_API int nl_pairs_to_host(const nl_params* params, const void* first, int64_t n_rows, const void* i, int64_t i_copy_from,
+                            const void* j, const void* S, int64_t P, void* first_host, void* i_host, void* j_host, void* S_host,
                             void* dev_scratch, void* host_scratch, size_t scratch_bytes, int32_t nthreads, void* stream);
 /* The two host-side decoders of that format on their own (pure host code, no CUDA call): pairs [p_lo, p_hi), 0-based.  */
 NL_API int nl_host_expand_rows(int32_t int_type, const void* first, int64_t n_rows, int64_t p_lo, int64_t p_hi, void* i_out);

@@ -301,11 +301,14 @@ class HostPairBuffers:
 _host_buffers: Optional[HostPairBuffers] = None
 
 
-def to_host(nlist: PairList, out: Optional[HostPairBuffers] = None, nthreads: int = 0, rebuild_i: Optional[bool] = None) -> HostPairList:
+def to_host(nlist: PairList, out: Optional[HostPairBuffers] = None, nthreads: int = 0, rebuild_i: Optional[bool] = None,
+            i_copy_fraction: float = 0.0) -> HostPairList:
     """The whole list into host memory through nl_pairs_to_host (include/nlcuda.h): `first`, `j` and one byte per pair for S
     cross the bus; i and S are rebuilt by host threads of the library while the copies run.  Returns when every array is
     complete.  `out`: buffers to reuse (default: a module-level set grown on demand).  rebuild_i=False copies i instead of
-    rebuilding it from `first` (needed for shard lists, whose i carries global indices; detected from the list's length)."""
+    rebuilding it from `first` (needed for shard lists, whose i carries global indices; detected from the list's length);
+    otherwise the last i_copy_fraction of i is copied and the rest rebuilt (0 is fastest where measured: the host's memory
+    bandwidth, which DMA writes and host stores share, is the bound, not the host threads' instruction rate)."""
     global _host_buffers
     P = int(nlist.i.shape[0])
     n_rows = int(nlist.first.shape[0]) - 1
@@ -322,7 +325,8 @@ def to_host(nlist: PairList, out: Optional[HostPairBuffers] = None, nthreads: in
         rebuild_i = n_rows == int(nlist.X.shape[0])   # a whole list: i[p] is the row of p
     S = nlist.S if nlist.S.is_contiguous() else nlist.S.contiguous()
     with torch.cuda.device(dev):
-        _lib.check(_lib.lib().nl_pairs_to_host(nlist.params, _ptr(nlist.first), n_rows, None if rebuild_i else _ptr(nlist.i), _ptr(nlist.j),
+        i_from = _i_copy_from(P, rebuild_i, i_copy_fraction)
+        _lib.check(_lib.lib().nl_pairs_to_host(nlist.params, _ptr(nlist.first), n_rows, _ptr(nlist.i), i_from, _ptr(nlist.j),
                                                _ptr(S), P, out.first.data_ptr(), out.i.data_ptr(), out.j.data_ptr(), out.S.data_ptr(),
                                                out.dev_scratch.data_ptr(), out.host_scratch.data_ptr(), out.dev_scratch.numel(),
                                                int(nthreads), _stream(dev)))
@@ -330,11 +334,19 @@ def to_host(nlist: PairList, out: Optional[HostPairBuffers] = None, nthreads: in
                         first=out.first[:n_rows + 1].numpy())
 
 
-def to_host_bytes(nlist: PairList, rebuild_i: bool = True) -> int:
+def _i_copy_from(P: int, rebuild_i: bool, i_copy_fraction: float) -> int:
+    if not rebuild_i:
+        return 0
+    if i_copy_fraction <= 0.0:
+        return P
+    return min(P, max(0, int(P * (1.0 - min(1.0, max(0.0, i_copy_fraction))))) & ~63)
+
+
+def to_host_bytes(nlist: PairList, rebuild_i: bool = True, i_copy_fraction: float = 0.0) -> int:
     """Bytes nl_pairs_to_host moves over the bus for this list (when no shift component escapes the one-byte code)."""
     P = int(nlist.i.shape[0])
     w = nlist.i.element_size()
-    return (int(nlist.first.shape[0])) * w + P * w + P + 4 + (0 if rebuild_i else P * w)
+    return (int(nlist.first.shape[0])) * w + P * w + P + 4 + (P - _i_copy_from(P, rebuild_i, i_copy_fraction)) * w
 
 # ------------------------------------------------------------------ accessors (src/cell_list.jl:25-27, 507-611, 753-833, 919-927)
 def npairs(nlist: PairList) -> int:

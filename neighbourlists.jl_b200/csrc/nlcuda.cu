@@ -871,7 +871,7 @@ int check_ws(const void* ws, size_t have, size_t need) {
 // ---------------------------------------------------------------------------------------------------------------------
 // nl_pairs_to_host: see nl_tohost.cuh.  Only the calling thread talks to CUDA; the worker threads wait on a counter.
 template <class TI>
-int pairs_to_host_impl(const void* first_d, int64_t n_rows, const void* i_d, const void* j_d, const void* S_d, int64_t P, void* first_h,
+int pairs_to_host_impl(const void* first_d, int64_t n_rows, const void* i_d, int64_t i_from, const void* j_d, const void* S_d, int64_t P, void* first_h,
                        void* i_h, void* j_h, void* S_h, void* dscratch, void* hscratch, int nthreads, cudaStream_t st) {
   NL_CUDA(cudaMemcpyAsync(first_h, first_d, (size_t)(n_rows + 1) * sizeof(TI), cudaMemcpyDeviceToHost, st));
   if (P == 0) {
@@ -904,7 +904,8 @@ int pairs_to_host_impl(const void* first_d, int64_t n_rows, const void* i_d, con
     if (c1 > c0) NL_CUDA_EV(cudaMemcpyAsync(codes_h + c0, codes_d + c0, (size_t)(c1 - c0), cudaMemcpyDeviceToHost, st));
     NL_CUDA_EV(cudaEventRecord(ev[k + 1], st));
   }
-  if (i_d) NL_CUDA_EV(cudaMemcpyAsync(i_h, i_d, (size_t)P * sizeof(TI), cudaMemcpyDeviceToHost, st));
+  if (i_from < P)  // this part of i crosses the bus, [0, i_from) is rebuilt from first
+    NL_CUDA_EV(cudaMemcpyAsync((TI*)i_h + i_from, (const TI*)i_d + i_from, (size_t)(P - i_from) * sizeof(TI), cudaMemcpyDeviceToHost, st));
   NL_CUDA_EV(cudaMemcpyAsync(j_h, j_d, (size_t)P * sizeof(TI), cudaMemcpyDeviceToHost, st));
 #undef NL_CUDA_EV
 
@@ -921,9 +922,9 @@ int pairs_to_host_impl(const void* first_d, int64_t n_rows, const void* i_d, con
   for (int t = 0; t < T; t++) {
     workers.emplace_back([&, t]() {
       if (!wait_for(1)) return;
-      if (!i_d) {
-        const int64_t q = ((P + T - 1) / T + 3) & ~(int64_t)3;
-        host_expand_rows<TI>((const TI*)first_h, (long long)n_rows, std::min<int64_t>(P, q * t), std::min<int64_t>(P, q * (t + 1)), (TI*)i_h);
+      if (i_from > 0) {
+        const int64_t q = ((i_from + T - 1) / T + 3) & ~(int64_t)3;
+        host_expand_rows<TI>((const TI*)first_h, (long long)n_rows, std::min<int64_t>(i_from, q * t), std::min<int64_t>(i_from, q * (t + 1)), (TI*)i_h);
       }
       if (escape.load(std::memory_order_relaxed)) return;
       for (int k = 0; k < nchunks; k++) {
@@ -1238,12 +1239,15 @@ int nl_max_displacement2(int32_t float_type, const void* X, const void* X_ref, i
 
 size_t nl_to_host_scratch_bytes(int64_t P) { return al256((size_t)(P > 0 ? P : 0)) + 256; }
 
-int nl_pairs_to_host(const nl_params* params, const void* first, int64_t n_rows, const void* i, const void* j, const void* S, int64_t P,
+int nl_pairs_to_host(const nl_params* params, const void* first, int64_t n_rows, const void* i, int64_t i_copy_from, const void* j, const void* S,
+                     int64_t P,
                      void* first_host, void* i_host, void* j_host, void* S_host, void* dev_scratch, void* host_scratch, size_t scratch_bytes,
                      int32_t nthreads, void* stream) {
   if (!params || (params->int_type != NL_I32 && params->int_type != NL_I64)) return NL_ERR_BAD_ARG;
   if (n_rows < 0 || P < 0 || !first || !first_host) return NL_ERR_BAD_ARG;
   if (P > 0 && (!j || !S || !i_host || !j_host || !S_host)) return NL_ERR_BAD_ARG;
+  if (i_copy_from < 0 || i_copy_from > P || (i_copy_from < P && !i)) return NL_ERR_BAD_ARG;
+  if (i_copy_from < P) i_copy_from &= ~(int64_t)63;  // the two parts of i meet on a 256-byte boundary
   if (P > 0) {
     if (!dev_scratch || !host_scratch || scratch_bytes < nl_to_host_scratch_bytes(P)) return NL_ERR_WORKSPACE;
     if ((((uintptr_t)dev_scratch) | ((uintptr_t)host_scratch)) & 15) return NL_ERR_WORKSPACE;
@@ -1251,8 +1255,8 @@ int nl_pairs_to_host(const nl_params* params, const void* first, int64_t n_rows,
   if (nthreads <= 0) nthreads = (int32_t)std::max(1u, std::thread::hardware_concurrency());
   cudaStream_t st = (cudaStream_t)stream;
   return params->int_type == NL_I64
-             ? pairs_to_host_impl<int64_t>(first, n_rows, i, j, S, P, first_host, i_host, j_host, S_host, dev_scratch, host_scratch, nthreads, st)
-             : pairs_to_host_impl<int32_t>(first, n_rows, i, j, S, P, first_host, i_host, j_host, S_host, dev_scratch, host_scratch, nthreads, st);
+             ? pairs_to_host_impl<int64_t>(first, n_rows, i, i_copy_from, j, S, P, first_host, i_host, j_host, S_host, dev_scratch, host_scratch, nthreads, st)
+             : pairs_to_host_impl<int32_t>(first, n_rows, i, i_copy_from, j, S, P, first_host, i_host, j_host, S_host, dev_scratch, host_scratch, nthreads, st);
 }
 
 int nl_host_expand_rows(int32_t int_type, const void* first, int64_t n_rows, int64_t p_lo, int64_t p_hi, void* i_out) {

@@ -66,4 +66,4 @@ def test_decoder_argument_checks():
     # the whole-list entry point validates before touching CUDA
     p = nl._lib.NlParams()
     p.int_type = 0
-    assert L.nl_pairs_to_host(p, None, 3, None, None, None, 5, None, None, None, None, None, None, 0, 0, None) == nl._lib.NL_ERR_BAD_ARG
+    assert L.nl_pairs_to_host(p, None, 3, None, 5, None, None, 5, None, None, None, None, None, None, 0, 0, None) == nl._lib.NL_ERR_BAD_ARG

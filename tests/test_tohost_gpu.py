@@ -40,6 +40,8 @@ def test_to_host_equals_field_copies(nl, pbc, int_type):
     U.assert_same_pairs(dict(i=h.i, j=h.j, S=h.S), orc)
     for nt in (1, 3, 64):   # any number of host threads gives the same arrays
         _check(nl, pl, nthreads=nt)
+    for f in (0.0, 0.5, 1.0):   # any split of i between the host threads and the bus as well
+        _check(nl, pl, i_copy_fraction=f)
 
 
 def test_to_host_triclinic_many_chunks(nl):
@@ -91,7 +93,7 @@ def test_to_host_copied_i_and_buffer_reuse(nl):
     small = nl.HostPairBuffers(10, 5000)
     with pytest.raises(ValueError):
         nl.to_host(pl, out=small)
-    assert nl.to_host_bytes(pl) == 4 * 5001 + 5 * nl.npairs(pl) + 4
+    assert nl.to_host_bytes(pl, i_copy_fraction=0.0) == 4 * 5001 + 5 * nl.npairs(pl) + 4
 
 
 def test_to_host_rejects_first_that_does_not_match(nl):
