@@ -161,6 +161,43 @@ function NeighbourLists.maxneigs(nl::DevPairList)
     return Array(out)[1]
 end
 
+# ---- Array(PairList): the whole list into host memory (include/nlcuda.h: nl_pairs_to_host) --------------------
+# 5 B/pair cross the bus (first, j, one byte per pair for S); i and S are rebuilt by host threads of the library while the copies
+# run.  Pinned buffers and the transfer scratch are cached per (TI, capacity): pinning 5 GB costs more than building the list.
+mutable struct HostPairBuffers{TI}
+    cap::Int
+    rows::Int
+    first::Vector{TI}; i::Vector{TI}; j::Vector{TI}; S::Vector{SVec{TI}}
+    hscratch::Vector{UInt8}; dscratch::CuVector{UInt8}
+end
+function HostPairBuffers{TI}(cap::Integer, rows::Integer) where {TI}
+    nb = Int(ccall((:nl_to_host_scratch_bytes, libnlcuda), Csize_t, (Int64,), cap))
+    pin(v) = (CUDA.Mem.pin(v); v)
+    HostPairBuffers{TI}(cap, rows, pin(Vector{TI}(undef, rows + 1)), pin(Vector{TI}(undef, max(cap, 1))), pin(Vector{TI}(undef, max(cap, 1))),
+                        pin(Vector{SVec{TI}}(undef, max(cap, 1))), pin(Vector{UInt8}(undef, nb)), CuVector{UInt8}(undef, nb))
+end
+const _HOST_BUF = Ref{Any}(nothing)
+
+"PairList with every array in host memory (views of pinned buffers): `Array` of each field, in one compressed transfer"
+function to_host(nl::DevPairList{T,TI}; nthreads::Integer = Threads.nthreads(), buffers = nothing) where {T,TI}
+    P, rows = length(nl.i), length(nl.first) - 1
+    b = buffers
+    if b === nothing
+        b = _HOST_BUF[]
+        if !(b isa HostPairBuffers{TI}) || b.cap < P || b.rows < rows
+            b = _HOST_BUF[] = HostPairBuffers{TI}(P + P ÷ 20 + 1024, rows)
+        end
+    end
+    whole = rows == length(nl.X)                       # a whole list: i[p] is the row of p; shard lists copy their global i
+    GC.@preserve b _check(ccall((:nl_pairs_to_host, libnlcuda), Cint,
+                 (Ref{NlParams}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
+                  Ptr{Cvoid}, CuPtr{Cvoid}, Ptr{Cvoid}, Csize_t, Int32, Ptr{Cvoid}),
+                 _params(nl), nl.first, rows, nl.i, whole ? P : 0, nl.j, nl.S, P, b.first, b.i, b.j, b.S, b.dscratch, b.hscratch,
+                 length(b.hscratch), nthreads, _stream()))
+    return PairList(Array(nl.X), nl.C, nl.cutoff, view(b.i, 1:P), view(b.j, 1:P), view(b.S, 1:P), view(b.first, 1:rows+1))
+end
+
+
 "neighbourhoods of the atoms `rows` as padded blocks: (n, j, R, S) with j :: width x n_sel etc."
 function sites_padded(nl::DevPairList{T,TI}, rows::CuVector{TI}, width::Integer = maxneigs(nl)) where {T,TI}
     ns = length(rows)
