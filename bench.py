@@ -402,6 +402,7 @@ def run_ours(args):
                                              "reference CPU path (not Julia)"}
         print(json.dumps(out))
     if world > 1:
+        sharded.shard_disconnect(comm)
         nl._lib.check(L_.nl_nccl_comm_destroy(comm))
         dist.destroy_process_group()
 

@@ -172,6 +172,11 @@ typedef struct nl_shard_info {
   int64_t bounds[NL_MAX_RANKS + 1];    /* rank r owns planes [bounds[r], bounds[r+1])                                     */
   int64_t send_count[NL_MAX_RANKS];    /* local atoms owned by rank d (send_count[rank]: atoms that stay)                 */
   int64_t recv_count[NL_MAX_RANKS];    /* atoms rank s holds that this rank owns                                          */
+  /* what the PEER path (nl_shard_connect / nl_shard_exchange_peer) needs to know about the other ranks; all of it follows
+   * from the all-gathered histograms, so every rank computes the same numbers:                                           */
+  int64_t n_max_all;                   /* max over ranks of max(atoms passed in, atoms owned): the workspace capacity needed */
+  int64_t src_offset[NL_MAX_RANKS];    /* where, in rank s's send buffer (atoms), the block for THIS rank starts          */
+  int64_t halo_src_offset_dn, halo_src_offset_up; /* where, in the dn / up peer's halo buffer, this rank's halo starts   */
 } nl_shard_info;
 
 /* Scratch for nl_shard_prepare / nl_shard_exchange with at most n_max atoms on either side of the redistribution
@@ -190,6 +195,32 @@ NL_API int nl_shard_prepare(const nl_params* params, const void* X, int64_t n, v
 NL_API int nl_shard_exchange(const nl_params* params, const nl_shard_info* info, const void* X, const void* gidx, int64_t n,
                              void* comm, void* X_all, void* gidx_all, uint8_t* plane_active_out, void* ws, size_t ws_bytes,
                              void* stream);
+
+/* ---- Peer path: the same exchange as direct NVLink COPIES between the ranks' workspaces instead of ncclSend / ncclRecv.
+ * Every rank maps the other ranks' workspace into its address space once (CUDA IPC; one process per GPU on one node) and then
+ * PULLS its blocks of the all-to-all-v and its halos straight from the peers' send buffers into X_all / gidx_all with
+ * cudaMemcpyAsync (copy engines over NVLink / NVSwitch); the only collectives left per list are two 8-byte all-gathers used as
+ * stream-ordered barriers ("every send buffer is ready").  Measured on 2 B200: all-to-all-v of 2 x 160 MB 1.09 ms with
+ * ncclSend / ncclRecv, see DESIGN.md 6 for the peer path.
+ *   nl_shard_connect     collective.  `ws` is THE workspace of this rank for every later exchange: nl_shard_workspace_bytes(params,
+ *                        cap, nranks) bytes for the SAME cap on every rank (the layout must agree), alive until nl_shard_disconnect.
+ *   nl_shard_exchange_peer  like nl_shard_exchange; NL_ERR_WORKSPACE when info->n_max_all > peers->cap (on every rank alike:
+ *                        reconnect with a larger workspace) or when ws is not the connected one.
+ *   nl_shard_disconnect  unmaps the peers' workspaces.                                                                      */
+typedef struct nl_shard_peers {
+  int32_t nranks, rank;
+  int64_t cap;                   /* atoms the workspace layout is made for                                               */
+  uint64_t ws_bytes;
+  void* ws;                      /* this rank's workspace                                                                */
+  void* peer_ws[NL_MAX_RANKS];   /* rank r's workspace in this process's address space (NULL for r == rank)             */
+  void* peer_base[NL_MAX_RANKS]; /* what cudaIpcOpenMemHandle returned (for nl_shard_disconnect)                         */
+} nl_shard_peers;
+NL_API int nl_shard_connect(const nl_params* params, int64_t cap, void* comm, int32_t rank, int32_t nranks, void* ws,
+                            size_t ws_bytes, nl_shard_peers* peers_out, void* stream);
+NL_API int nl_shard_exchange_peer(const nl_params* params, const nl_shard_info* info, const void* X, const void* gidx,
+                                  int64_t n, void* comm, const nl_shard_peers* peers, void* X_all, void* gidx_all,
+                                  uint8_t* plane_active_out, void* ws, size_t ws_bytes, void* stream);
+NL_API int nl_shard_disconnect(nl_shard_peers* peers);
 
 /* Communicator helpers for hosts without an NCCL binding of their own: rank 0 calls nl_nccl_unique_id, ships the 128 bytes to
  * the other ranks by any means, then every rank calls nl_nccl_comm_init (collective). */

@@ -44,6 +44,15 @@ class NlShardInfo(C.Structure):
         ("n_local", C.c_int64), ("n_owned", C.c_int64), ("n_halo_dn", C.c_int64), ("n_halo_up", C.c_int64),
         ("n_send_dn", C.c_int64), ("n_send_up", C.c_int64),
         ("bounds", C.c_int64 * (NL_MAX_RANKS + 1)), ("send_count", C.c_int64 * NL_MAX_RANKS), ("recv_count", C.c_int64 * NL_MAX_RANKS),
+        ("n_max_all", C.c_int64), ("src_offset", C.c_int64 * NL_MAX_RANKS), ("halo_src_offset_dn", C.c_int64), ("halo_src_offset_up", C.c_int64),
+    ]
+
+
+class NlShardPeers(C.Structure):
+    """struct nl_shard_peers (include/nlcuda.h): the other ranks' workspaces mapped into this process (peer path)."""
+    _fields_ = [
+        ("nranks", C.c_int32), ("rank", C.c_int32), ("cap", C.c_int64), ("ws_bytes", C.c_uint64), ("ws", C.c_void_p),
+        ("peer_ws", C.c_void_p * NL_MAX_RANKS), ("peer_base", C.c_void_p * NL_MAX_RANKS),
     ]
 
 
@@ -61,7 +70,8 @@ EXPORTS = ("nl_version", "nl_strerror", "nl_last_cuda_error", "nl_launch_count",
            "nl_fill_pairs", "nl_fill_pairs_rows", "nl_count_pairs_window", "nl_fill_pairs_window", "nl_cell_ids", "nl_shard_plan", "nl_lazy_count", "nl_lazy_lj_energy", "nl_lazy_lj_forces",
            "nl_pairs_R", "nl_max_neighbours", "nl_rows_padded", "nl_lazy_neighbours", "nl_bounding_box", "nl_max_displacement2",
            "nl_shard_workspace_bytes", "nl_shard_prepare", "nl_shard_exchange", "nl_nccl_unique_id", "nl_nccl_comm_init", "nl_nccl_comm_destroy",
-           "nl_to_host_scratch_bytes", "nl_pairs_to_host", "nl_host_expand_rows", "nl_host_unpack_shifts")
+           "nl_to_host_scratch_bytes", "nl_pairs_to_host", "nl_host_expand_rows", "nl_host_unpack_shifts",
+           "nl_shard_connect", "nl_shard_exchange_peer", "nl_shard_disconnect")
 NL_REDUCE_WS_BYTES = 32768
 
 
@@ -108,6 +118,12 @@ def lib():
         L.nl_shard_workspace_bytes.argtypes = [pp, i64, C.c_int32]
         L.nl_shard_prepare.argtypes = [pp, vp, i64, vp, C.c_int32, C.c_int32, ps, vp, sz, vp]
         L.nl_shard_exchange.argtypes = [pp, ps, vp, vp, i64, vp, vp, vp, vp, vp, sz, vp]
+        pq = C.POINTER(NlShardPeers)
+        L.nl_shard_connect.argtypes = [pp, i64, vp, C.c_int32, C.c_int32, vp, sz, pq, vp]
+        L.nl_shard_exchange_peer.argtypes = [pp, ps, vp, vp, i64, vp, pq, vp, vp, vp, vp, sz, vp]
+        L.nl_shard_disconnect.argtypes = [pq]
+        for n in ("nl_shard_connect", "nl_shard_exchange_peer", "nl_shard_disconnect"):
+            getattr(L, n).restype = C.c_int
         L.nl_nccl_unique_id.argtypes = [vp]
         L.nl_nccl_comm_init.argtypes = [C.POINTER(vp), C.c_int32, vp, C.c_int32]
         L.nl_nccl_comm_destroy.argtypes = [vp]

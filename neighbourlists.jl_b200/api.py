@@ -301,7 +301,7 @@ class HostPairBuffers:
 _host_buffers: Optional[HostPairBuffers] = None
 
 
-def to_host(nlist: PairList, out: Optional[HostPairBuffers] = None, nthreads: int = 0, rebuild_i: Optional[bool] = None,
+def to_host(nlist, out: Optional[HostPairBuffers] = None, nthreads: int = 0, rebuild_i: Optional[bool] = None,
             i_copy_fraction: float = 0.0) -> HostPairList:
     """The whole list into host memory through nl_pairs_to_host (include/nlcuda.h): `first`, `j` and one byte per pair for S
     cross the bus; i and S are rebuilt by host threads of the library while the copies run.  Returns when every array is
@@ -321,16 +321,24 @@ def to_host(nlist: PairList, out: Optional[HostPairBuffers] = None, nthreads: in
         out = _host_buffers
     elif not out.fits(P, n_rows, it):
         raise ValueError("host buffers too small for this list")
+    whole = isinstance(nlist, PairList) and n_rows == int(nlist.X.shape[0])   # a whole list: i[p] is the row of p
     if rebuild_i is None:
-        rebuild_i = n_rows == int(nlist.X.shape[0])   # a whole list: i[p] is the row of p
+        rebuild_i = whole
+    elif rebuild_i and not whole:
+        raise ValueError("rebuild_i needs a whole PairList: the i of a shard list carries global indices")
+    params = getattr(nlist, "params", None)
+    if params is None:   # sharded.ShardedPairList: only the integer type is read
+        params = _lib.NlParams()
+        params.int_type = _lib.NL_I64 if it == torch.int64 else _lib.NL_I32
     S = nlist.S if nlist.S.is_contiguous() else nlist.S.contiguous()
     with torch.cuda.device(dev):
         i_from = _i_copy_from(P, rebuild_i, i_copy_fraction)
-        _lib.check(_lib.lib().nl_pairs_to_host(nlist.params, _ptr(nlist.first), n_rows, _ptr(nlist.i), i_from, _ptr(nlist.j),
+        _lib.check(_lib.lib().nl_pairs_to_host(params, _ptr(nlist.first), n_rows, _ptr(nlist.i), i_from, _ptr(nlist.j),
                                                _ptr(S), P, out.first.data_ptr(), out.i.data_ptr(), out.j.data_ptr(), out.S.data_ptr(),
                                                out.dev_scratch.data_ptr(), out.host_scratch.data_ptr(), out.dev_scratch.numel(),
                                                int(nthreads), _stream(dev)))
-    return HostPairList(X=nlist.X, C=nlist.C, cutoff=nlist.cutoff, i=out.i[:P].numpy(), j=out.j[:P].numpy(), S=out.S[:P].numpy(),
+    return HostPairList(X=getattr(nlist, "X", getattr(nlist, "X_owned", None)), C=getattr(nlist, "C", None), cutoff=getattr(nlist, "cutoff", None),
+                        i=out.i[:P].numpy(), j=out.j[:P].numpy(), S=out.S[:P].numpy(),
                         first=out.first[:n_rows + 1].numpy())
 
 
@@ -342,7 +350,7 @@ def _i_copy_from(P: int, rebuild_i: bool, i_copy_fraction: float) -> int:
     return min(P, max(0, int(P * (1.0 - min(1.0, max(0.0, i_copy_fraction))))) & ~63)
 
 
-def to_host_bytes(nlist: PairList, rebuild_i: bool = True, i_copy_fraction: float = 0.0) -> int:
+def to_host_bytes(nlist, rebuild_i: bool = True, i_copy_fraction: float = 0.0) -> int:
     """Bytes nl_pairs_to_host moves over the bus for this list (when no shift component escapes the one-byte code)."""
     P = int(nlist.i.shape[0])
     w = nlist.i.element_size()

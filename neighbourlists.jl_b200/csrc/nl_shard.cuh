@@ -132,6 +132,8 @@ struct ShardWs {
   uint32_t *keyA, *keyB, *valA, *valB;
   void* rs_scratch;
   void *sendX, *sendg;
+  void *haloX, *halog;            // halo send buffers of the peer path (the NCCL path reuses sendX / sendg)
+  unsigned long long* bar;        // 8 (nranks + 1) bytes: the all-gather used as a barrier
   size_t total;
 };
 inline ShardWs shard_ws(void* ws, long long n, int nplanes, int nranks, size_t fbytes, size_t ibytes) {
@@ -153,6 +155,9 @@ inline ShardWs shard_ws(void* ws, long long n, int nplanes, int nranks, size_t f
   w.rs_scratch = take(rs_scratch_bytes((long long)n1));
   w.sendX = take(n1 * 3 * fbytes);
   w.sendg = take(n1 * ibytes);
+  w.haloX = take(n1 * 3 * fbytes);
+  w.halog = take(n1 * ibytes);
+  w.bar = (unsigned long long*)take((size_t)(nranks + 1) * 8);
   w.total = o;
   return w;
 }

@@ -3,6 +3,7 @@
 #include "../../include/nlcuda.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -27,7 +28,8 @@ using namespace nl;
 
 
 static_assert(sizeof(nl_params) == 192, "nl_params layout is part of the ABI");
-static_assert(sizeof(nl_shard_info) == 1632, "nl_shard_info layout is part of the ABI");
+static_assert(sizeof(nl_shard_info) == 1632 + 8 + 8 * NL_MAX_RANKS + 16, "nl_shard_info layout is part of the ABI");
+static_assert(sizeof(nl_shard_peers) == 8 + 8 + 8 + 8 + 16 * NL_MAX_RANKS, "nl_shard_peers layout is part of the ABI");
 
 inline int cuda_fail(cudaError_t e) {
   last_cuda_slot() = (int)e;
@@ -740,17 +742,65 @@ int shard_prepare_impl(const nl_params* p, const void* X, int64_t n, void* comm,
   const int64_t lo = f.bounds[rank], hi = f.bounds[rank + 1];
   if (f.has_dn) { f.n_send_dn = sumt(lo, lo + halo); f.n_halo_dn = sumt(f.bounds[f.dn_peer + 1] - halo, f.bounds[f.dn_peer + 1]); }
   if (f.has_up) { f.n_send_up = sumt(hi - halo, hi); f.n_halo_up = sumt(f.bounds[f.up_peer], f.bounds[f.up_peer] + halo); }
+  // what the peer path needs to know about the other ranks (all from the gathered histograms: the same on every rank)
+  for (int r = 0; r < nranks; r++) {
+    const unsigned long long* row = &h[(size_t)r * nplanes];
+    f.n_max_all = std::max(f.n_max_all, std::max(sum(row, 0, nplanes), sumt(f.bounds[r], f.bounds[r + 1])));
+    f.src_offset[r] = sum(row, 0, f.bounds[rank]);  // slabs are contiguous plane ranges in rank order
+  }
+  // the halo from below is the dn peer's UP block, which follows its DOWN block; the halo from above is the up peer's DOWN block
+  if (f.has_dn) {
+    const int q = f.dn_peer;
+    const bool q_has_dn = f.periodic || q > 0;
+    f.halo_src_offset_dn = q_has_dn ? sumt(f.bounds[q], f.bounds[q] + halo) : 0;
+  }
+  f.halo_src_offset_up = 0;
   return NL_OK;
 }
 
+// NL_SHARD_PROFILE=1: device time of the phases of nl_shard_exchange, printed by rank 0 (synchronises; measurement only).
+struct PhaseTimer {
+  bool on;
+  cudaStream_t st;
+  std::vector<std::pair<const char*, cudaEvent_t>> marks;
+  PhaseTimer(bool enable, cudaStream_t s) : on(enable), st(s) {}
+  void mark(const char* name) {
+    if (!on) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; }
+    cudaEventRecord(e, st);
+    marks.emplace_back(name, e);
+  }
+  void report(const char* what) {
+    if (!on || marks.size() < 2) return;
+    cudaStreamSynchronize(st);
+    fprintf(stderr, "[%s ms]", what);
+    for (size_t k = 1; k < marks.size(); k++) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, marks[k - 1].second, marks[k].second);
+      fprintf(stderr, " %s=%.3f", marks[k].first, ms);
+    }
+    fprintf(stderr, "\n");
+    for (auto& m : marks) cudaEventDestroy(m.second);
+  }
+};
+inline bool shard_profile() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("NL_SHARD_PROFILE"); v = (e && e[0] && e[0] != '0') ? 1 : 0; }
+  return v == 1;
+}
+
 template <class T, class TI>
-int shard_exchange_impl(const nl_params* p, const nl_shard_info* info, const void* X, const void* gidx, int64_t n, void* comm, void* X_all,
-                        void* g_all, uint8_t* plane_active_out, void* ws, cudaStream_t st) {
+int shard_exchange_impl(const nl_params* p, const nl_shard_info* info, const void* X, const void* gidx, int64_t n, void* comm,
+                        const nl_shard_peers* peers, void* X_all, void* g_all, uint8_t* plane_active_out, void* ws, cudaStream_t st) {
   const nl_shard_info& f = *info;
   Geo<T> g = make_geo<T>(p);
   const int G = f.nranks, me = f.rank;
-  const int64_t n_max = std::max<int64_t>(n, f.n_owned);
+  // peer path: every rank lays its workspace out for the SAME capacity, so that a peer's send buffers can be addressed
+  const int64_t n_max = peers ? peers->cap : std::max<int64_t>(n, f.n_owned);
   ShardWs w = shard_ws(ws, n_max, f.nplanes, G, sizeof(T), sizeof(TI));
+  auto peer_view = [&](int r) { return shard_ws(peers->peer_ws[r], n_max, f.nplanes, G, sizeof(T), sizeof(TI)); };
+  auto barrier = [&]() { return nccl().AllGather(w.bar, w.bar + 1, 1, NCCL_UINT64, comm, st); };
   T* Xa = (T*)X_all;
   TI* ga = (TI*)g_all;
   if (plane_active_out) {
@@ -773,6 +823,8 @@ int shard_exchange_impl(const nl_params* p, const nl_shard_info* info, const voi
     return NL_OK;
   }
   if (!nccl().ok || !comm) return NL_ERR_NCCL;
+  PhaseTimer pt(shard_profile() && me == 0, st);
+  pt.mark("start");
   // ---- owners, stable partition by destination
   const uint32_t* order = nullptr;
   if (n > 0) {
@@ -786,6 +838,7 @@ int shard_exchange_impl(const nl_params* p, const nl_shard_info* info, const voi
     NL_LAUNCHED(3);
     NL_LAUNCH_CHECK();
   }
+  pt.mark("partition");
   // ---- all-to-all-v straight into the local arrays: [atoms that stay | from rank 0 | from rank 1 | ...]
   std::vector<int64_t> soff(G + 1, 0), roff(G, 0);
   for (int d = 0; d < G; d++) soff[d + 1] = soff[d] + f.send_count[d];
@@ -800,38 +853,71 @@ int shard_exchange_impl(const nl_params* p, const nl_shard_info* info, const voi
     NL_CUDA(cudaMemcpyAsync(ga, (const TI*)w.sendg + k0, (size_t)c * sizeof(TI), cudaMemcpyDeviceToDevice, st));
     NL_CUDA(cudaMemcpyAsync(w.planes_owned, w.sendp + k0, (size_t)c * 4, cudaMemcpyDeviceToDevice, st));
   }
-  bool any = false;
-  for (int r = 0; r < G; r++) any = any || (r != me && (f.send_count[r] > 0 || f.recv_count[r] > 0));
-  if (any) {
-    NL_NCCL(nccl().GroupStart());
-    for (int r = 0; r < G; r++) {
-      if (r == me) continue;
-      if (f.send_count[r] > 0) {
-        const int64_t k0 = soff[r], c = f.send_count[r];
-        NL_NCCL(nccl().Send((const T*)w.sendX + 3 * k0, (size_t)c * 3 * sizeof(T), NCCL_INT8, r, comm, st));
-        NL_NCCL(nccl().Send((const TI*)w.sendg + k0, (size_t)c * sizeof(TI), NCCL_INT8, r, comm, st));
-        NL_NCCL(nccl().Send(w.sendp + k0, (size_t)c * 4, NCCL_INT8, r, comm, st));
-      }
-      if (f.recv_count[r] > 0) {
-        const int64_t k0 = roff[r], c = f.recv_count[r];
-        NL_NCCL(nccl().Recv(Xa + 3 * k0, (size_t)c * 3 * sizeof(T), NCCL_INT8, r, comm, st));
-        NL_NCCL(nccl().Recv(ga + k0, (size_t)c * sizeof(TI), NCCL_INT8, r, comm, st));
-        NL_NCCL(nccl().Recv(w.planes_owned + k0, (size_t)c * 4, NCCL_INT8, r, comm, st));
-      }
+  if (peers) {
+    // every send buffer is ready once this (stream-ordered) barrier has completed; then PULL my blocks out of the peers' buffers
+    NL_NCCL(barrier());
+    for (int k = 1; k < G; k++) {
+      const int r = (me + k) % G;  // staggered: at any time every rank reads from a different peer
+      const int64_t c = f.recv_count[r];
+      if (c <= 0) continue;
+      const ShardWs pw = peer_view(r);
+      const int64_t s0 = f.src_offset[r], k0 = roff[r];
+      NL_CUDA(cudaMemcpyAsync(Xa + 3 * k0, (const T*)pw.sendX + 3 * s0, (size_t)c * 3 * sizeof(T), cudaMemcpyDefault, st));
+      NL_CUDA(cudaMemcpyAsync(ga + k0, (const TI*)pw.sendg + s0, (size_t)c * sizeof(TI), cudaMemcpyDefault, st));
+      NL_CUDA(cudaMemcpyAsync(w.planes_owned + k0, pw.sendp + s0, (size_t)c * 4, cudaMemcpyDefault, st));
     }
-    NL_NCCL(nccl().GroupEnd());
+  } else {
+    bool any = false;
+    for (int r = 0; r < G; r++) any = any || (r != me && (f.send_count[r] > 0 || f.recv_count[r] > 0));
+    if (any) {
+      NL_NCCL(nccl().GroupStart());
+      for (int r = 0; r < G; r++) {
+        if (r == me) continue;
+        if (f.send_count[r] > 0) {
+          const int64_t k0 = soff[r], c = f.send_count[r];
+          NL_NCCL(nccl().Send((const T*)w.sendX + 3 * k0, (size_t)c * 3 * sizeof(T), NCCL_INT8, r, comm, st));
+          NL_NCCL(nccl().Send((const TI*)w.sendg + k0, (size_t)c * sizeof(TI), NCCL_INT8, r, comm, st));
+          NL_NCCL(nccl().Send(w.sendp + k0, (size_t)c * 4, NCCL_INT8, r, comm, st));
+        }
+        if (f.recv_count[r] > 0) {
+          const int64_t k0 = roff[r], c = f.recv_count[r];
+          NL_NCCL(nccl().Recv(Xa + 3 * k0, (size_t)c * 3 * sizeof(T), NCCL_INT8, r, comm, st));
+          NL_NCCL(nccl().Recv(ga + k0, (size_t)c * sizeof(TI), NCCL_INT8, r, comm, st));
+          NL_NCCL(nccl().Recv(w.planes_owned + k0, (size_t)c * 4, NCCL_INT8, r, comm, st));
+        }
+      }
+      NL_NCCL(nccl().GroupEnd());
+    }
   }
+  pt.mark("all-to-all");
   // ---- halos: bottom planes to the rank below, top planes to the rank above
   const int64_t no = f.n_owned, ns = f.n_send_dn + f.n_send_up;
   if (no > 0 && ns > 0) {
     k_shard_halo_class<<<(unsigned)((no + 255) / 256), 256, 0, st>>>(w.planes_owned, no, f.bounds[me], f.bounds[me + 1], f.halo, f.has_dn, f.has_up, w.keyA);
     const int where = radix_sort_pairs(w.keyA, w.valA, w.keyB, w.valB, no, 2, w.rs_scratch, st);
     const uint32_t* order2 = where ? w.valB : w.valA;
-    k_shard_gather<T, TI><<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(order2, 0, ns, Xa, ga, nullptr, (T*)w.sendX, (TI*)w.sendg, nullptr);
+    // peer path: a separate halo buffer -- the peers may still be pulling their all-to-all blocks out of sendX / sendg
+    k_shard_gather<T, TI><<<(unsigned)((ns + 255) / 256), 256, 0, st>>>(order2, 0, ns, Xa, ga, nullptr, (T*)(peers ? w.haloX : w.sendX),
+                                                                        (TI*)(peers ? w.halog : w.sendg), nullptr);
     NL_LAUNCHED(2);
     NL_LAUNCH_CHECK();
   }
-  if (ns > 0 || f.n_halo_dn > 0 || f.n_halo_up > 0) {
+  pt.mark("halo-select");
+  if (peers) {
+    // second barrier: every halo buffer is ready (and, stream-ordered, every rank has finished pulling from sendX / sendg, so the
+    // next list may overwrite them; its own first barrier protects the halo buffers in the same way)
+    NL_NCCL(barrier());
+    if (f.has_dn && f.n_halo_dn > 0) {
+      const ShardWs pw = peer_view(f.dn_peer);
+      NL_CUDA(cudaMemcpyAsync(Xa + 3 * no, (const T*)pw.haloX + 3 * f.halo_src_offset_dn, (size_t)f.n_halo_dn * 3 * sizeof(T), cudaMemcpyDefault, st));
+      NL_CUDA(cudaMemcpyAsync(ga + no, (const TI*)pw.halog + f.halo_src_offset_dn, (size_t)f.n_halo_dn * sizeof(TI), cudaMemcpyDefault, st));
+    }
+    if (f.has_up && f.n_halo_up > 0) {
+      const ShardWs pw = peer_view(f.up_peer);
+      NL_CUDA(cudaMemcpyAsync(Xa + 3 * (no + f.n_halo_dn), (const T*)pw.haloX + 3 * f.halo_src_offset_up, (size_t)f.n_halo_up * 3 * sizeof(T), cudaMemcpyDefault, st));
+      NL_CUDA(cudaMemcpyAsync(ga + no + f.n_halo_dn, (const TI*)pw.halog + f.halo_src_offset_up, (size_t)f.n_halo_up * sizeof(TI), cudaMemcpyDefault, st));
+    }
+  } else if (ns > 0 || f.n_halo_dn > 0 || f.n_halo_up > 0) {
     // message order matters when both neighbours are the same rank (2 ranks, periodic): everyone sends [up, down] and
     // receives [from below, from above], so the k-th send to a peer meets its k-th receive
     NL_NCCL(nccl().GroupStart());
@@ -853,6 +939,8 @@ int shard_exchange_impl(const nl_params* p, const nl_shard_info* info, const voi
     }
     NL_NCCL(nccl().GroupEnd());
   }
+  pt.mark("halo-exchange");
+  pt.report("nl_shard_exchange");
   return NL_OK;
 }
 
@@ -1110,7 +1198,89 @@ int nl_shard_exchange(const nl_params* params, const nl_shard_info* info, const 
   if (info->n_owned + info->n_halo_dn + info->n_halo_up > 0 && (!X_all || !gidx_all)) return NL_ERR_BAD_ARG;
   rc = check_ws(ws, ws_bytes, nl_shard_workspace_bytes(params, std::max<int64_t>(n, info->n_owned), info->nranks));
   if (rc) return rc;
-  return NL_DISPATCH(params, shard_exchange_impl, params, info, X, gidx, n, comm, X_all, gidx_all, plane_active_out, ws, (cudaStream_t)stream);
+  return NL_DISPATCH(params, shard_exchange_impl, params, info, X, gidx, n, comm, nullptr, X_all, gidx_all, plane_active_out, ws, (cudaStream_t)stream);
+}
+
+int nl_shard_exchange_peer(const nl_params* params, const nl_shard_info* info, const void* X, const void* gidx, int64_t n, void* comm,
+                           const nl_shard_peers* peers, void* X_all, void* gidx_all, uint8_t* plane_active_out, void* ws, size_t ws_bytes,
+                           void* stream) {
+  int rc = check_params(params, n);
+  if (rc) return rc;
+  if (!info || info->nranks < 1 || info->nranks > NL_MAX_RANKS || info->n_local != n || (n > 0 && (!X || !gidx))) return NL_ERR_BAD_ARG;
+  if (info->n_owned + info->n_halo_dn + info->n_halo_up > 0 && (!X_all || !gidx_all)) return NL_ERR_BAD_ARG;
+  if (!peers || peers->nranks != info->nranks || peers->rank != info->rank) return NL_ERR_BAD_ARG;
+  if (ws != peers->ws || ws_bytes != peers->ws_bytes || info->n_max_all > peers->cap) return NL_ERR_WORKSPACE;  // the same verdict on every rank
+  rc = check_ws(ws, ws_bytes, nl_shard_workspace_bytes(params, peers->cap, info->nranks));
+  if (rc) return rc;
+  return NL_DISPATCH(params, shard_exchange_impl, params, info, X, gidx, n, comm, info->nranks > 1 ? peers : nullptr, X_all, gidx_all,
+                     plane_active_out, ws, (cudaStream_t)stream);
+}
+
+int nl_shard_connect(const nl_params* params, int64_t cap, void* comm, int32_t rank, int32_t nranks, void* ws, size_t ws_bytes,
+                     nl_shard_peers* peers_out, void* stream) {
+  int rc = check_params(params, cap);
+  if (rc) return rc;
+  if (!peers_out || nranks < 1 || nranks > NL_MAX_RANKS || rank < 0 || rank >= nranks || cap < 1) return NL_ERR_BAD_ARG;
+  rc = check_ws(ws, ws_bytes, nl_shard_workspace_bytes(params, cap, nranks));
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  nl_shard_peers& P = *peers_out;
+  P = nl_shard_peers{};
+  P.nranks = nranks; P.rank = rank; P.cap = cap; P.ws_bytes = ws_bytes; P.ws = ws;
+  if (nranks == 1) return NL_OK;
+  if (!nccl().ok || !comm) return NL_ERR_NCCL;
+  // the allocation `ws` lives in (a caching allocator hands out interior pointers; IPC handles name whole allocations)
+  typedef int (*GetRange)(unsigned long long*, size_t*, unsigned long long);
+  static GetRange get_range = nullptr;
+  if (!get_range) {
+    void* h = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+    if (h) get_range = (GetRange)dlsym(h, "cuMemGetAddressRange_v2");
+    if (!get_range) return NL_ERR_UNSUPPORTED;
+  }
+  unsigned long long base = 0;
+  size_t alloc_bytes = 0;
+  if (get_range(&base, &alloc_bytes, (unsigned long long)(uintptr_t)ws) != 0) return NL_ERR_BAD_ARG;
+  struct Desc { cudaIpcMemHandle_t h; unsigned long long offset, bytes, cap; unsigned long long pad; };
+  static_assert(sizeof(Desc) == 96, "descriptor size");
+  Desc mine{};
+  NL_CUDA(cudaIpcGetMemHandle(&mine.h, (void*)(uintptr_t)base));
+  mine.offset = (unsigned long long)(uintptr_t)ws - base; mine.bytes = ws_bytes; mine.cap = (unsigned long long)cap;
+  std::vector<Desc> all(nranks);
+  char* dsc = (char*)ws;  // the workspace is free at connect time: descriptor at 0, the gathered ones from 4096 on
+  NL_CUDA(cudaMemcpyAsync(dsc, &mine, sizeof(Desc), cudaMemcpyHostToDevice, st));
+  NL_NCCL(nccl().AllGather(dsc, dsc + 4096, sizeof(Desc), NCCL_INT8, comm, st));
+  NL_CUDA(cudaMemcpyAsync(all.data(), dsc + 4096, sizeof(Desc) * nranks, cudaMemcpyDeviceToHost, st));
+  NL_CUDA(cudaStreamSynchronize(st));
+  for (int r = 0; r < nranks; r++)
+    if (all[r].cap != (unsigned long long)cap || all[r].bytes != ws_bytes) return NL_ERR_BAD_ARG;  // the layouts must agree (seen by every rank alike)
+  for (int r = 0; r < nranks; r++) {
+    if (r == rank) continue;
+    void* m = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&m, all[r].h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      for (int q = 0; q < r; q++) if (P.peer_base[q]) cudaIpcCloseMemHandle(P.peer_base[q]);
+      P = nl_shard_peers{};
+      return cuda_fail(e);
+    }
+    P.peer_base[r] = m;
+    P.peer_ws[r] = (char*)m + all[r].offset;
+  }
+  // nobody may start writing into its workspace (the first exchange) before every rank has read the descriptors out of it
+  NL_NCCL(nccl().AllGather(dsc + 2048, dsc + 4096, 8, NCCL_INT8, comm, st));
+  NL_CUDA(cudaStreamSynchronize(st));
+  return NL_OK;
+}
+
+int nl_shard_disconnect(nl_shard_peers* peers) {
+  if (!peers) return NL_ERR_BAD_ARG;
+  int rc = NL_OK;
+  for (int r = 0; r < NL_MAX_RANKS; r++)
+    if (peers->peer_base[r]) {
+      if (cudaIpcCloseMemHandle(peers->peer_base[r]) != cudaSuccess) rc = NL_ERR_CUDA;
+      peers->peer_base[r] = nullptr;
+      peers->peer_ws[r] = nullptr;
+    }
+  return rc;
 }
 
 int nl_nccl_unique_id(void* id128_out) {

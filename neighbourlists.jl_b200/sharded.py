@@ -30,6 +30,18 @@ import torch.distributed as dist
 from .cellmath import CellGeometry, geometry
 
 _PROFILE = bool(os.environ.get("NL_SHARD_PROFILE"))
+_PEER = os.environ.get("NL_SHARD_PEER", "1") != "0"   # 0: ncclSend / ncclRecv instead of NVLink peer copies (A/B runs)
+_peer_state = {}   # (device index, communicator) -> persistent workspace + nl_shard_peers of the peer path
+
+
+def shard_disconnect(comm=None):
+    """Unmaps the peer workspaces of the peer path (all communicators, or one).  Call before destroying the communicator."""
+    from . import _lib
+    import ctypes as C
+    for key in list(_peer_state):
+        if comm is None or key[1] == int(comm.value or 0):
+            st = _peer_state.pop(key)
+            _lib.check(_lib.lib().nl_shard_disconnect(C.byref(st["peers"])))
 
 
 class _Phases:
@@ -298,19 +310,41 @@ def neighbour_list_sharded_native(X_local, gidx_local, cutoff, cell, pbc, comm, 
     ph = _Phases(_PROFILE)
     ph.mark("start")
     with torch.cuda.device(dev):
-        ws = torch.empty(max(L.nl_shard_workspace_bytes(params, n, world), 256), dtype=torch.uint8, device=dev)
+        use_peer = world > 1 and _PEER
+        state = _peer_state.get((dev.index, int(comm.value or 0))) if use_peer else None
+        need_n = L.nl_shard_workspace_bytes(params, n, world)
+        if state is not None and state["ws"].numel() >= need_n:
+            ws = state["ws"]
+        else:
+            ws = torch.empty(max(need_n, 256), dtype=torch.uint8, device=dev)
         info = _lib.NlShardInfo()
         _lib.check(L.nl_shard_prepare(params, api._ptr(X), n, comm, rank, world, C.byref(info), api._ptr(ws), ws.numel(), st))
         ph.mark("prepare")
         n_owned, n_all = int(info.n_owned), int(info.n_owned + info.n_halo_dn + info.n_halo_up)
-        need = L.nl_shard_workspace_bytes(params, max(n, n_owned), world)
-        if need > ws.numel():
-            ws = torch.empty(need, dtype=torch.uint8, device=dev)
         X_all = torch.empty((n_all, 3), dtype=X.dtype, device=dev)
         g_all = torch.empty(n_all, dtype=it, device=dev)
         plane_active = np.ones(int(geo.ncells[2]), dtype=np.uint8)
-        _lib.check(L.nl_shard_exchange(params, C.byref(info), api._ptr(X), api._ptr(gidx), n, comm, api._ptr(X_all), api._ptr(g_all),
-                                       plane_active.ctypes.data, api._ptr(ws), ws.numel(), st))
+        if use_peer:
+            # peer path: one persistent workspace per (device, communicator), mapped into every other rank (nl_shard_connect).
+            # info.n_max_all is the same number on every rank, so every rank takes the same decision here (connect is collective).
+            key = (dev.index, int(comm.value or 0))
+            if state is None or int(info.n_max_all) > state["cap"] or state["params_key"] != (params.float_type, params.int_type, int(info.nplanes)):
+                if state is not None:
+                    _lib.check(L.nl_shard_disconnect(C.byref(state["peers"])))
+                cap = int(int(info.n_max_all) * 1.2) + 4096
+                wsp = torch.empty(L.nl_shard_workspace_bytes(params, cap, world), dtype=torch.uint8, device=dev)
+                peers = _lib.NlShardPeers()
+                _lib.check(L.nl_shard_connect(params, cap, comm, rank, world, api._ptr(wsp), wsp.numel(), C.byref(peers), st))
+                state = _peer_state[key] = dict(ws=wsp, peers=peers, cap=cap, params_key=(params.float_type, params.int_type, int(info.nplanes)))
+            ws = state["ws"]
+            _lib.check(L.nl_shard_exchange_peer(params, C.byref(info), api._ptr(X), api._ptr(gidx), n, comm, C.byref(state["peers"]), api._ptr(X_all),
+                                                api._ptr(g_all), plane_active.ctypes.data, api._ptr(ws), ws.numel(), st))
+        else:
+            need = L.nl_shard_workspace_bytes(params, max(n, n_owned), world)
+            if need > ws.numel():
+                ws = torch.empty(need, dtype=torch.uint8, device=dev)
+            _lib.check(L.nl_shard_exchange(params, C.byref(info), api._ptr(X), api._ptr(gidx), n, comm, api._ptr(X_all), api._ptr(g_all),
+                                           plane_active.ctypes.data, api._ptr(ws), ws.numel(), st))
         ph.mark("exchange")
         clist = api.build_cell_list(X_all, cutoff, cell, pbc, int_type=int_type)
         ph.mark("build")

@@ -32,6 +32,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_params_layout_and_validation():
     assert C.sizeof(nl._lib.NlParams) == 192
+    assert C.sizeof(nl._lib.NlShardInfo) == 1632 + 8 + 8 * 64 + 16     # static_assert in csrc/nlcuda.cu
+    assert C.sizeof(nl._lib.NlShardPeers) == 32 + 16 * 64
     geo = nl.cellmath.geometry(np.eye(3) * 20.0, 5.0, (True, True, False), np.float64)
     p = nl._lib.make_params(geo, np.float64, np.int32)
     L = nl._lib.lib()

@@ -55,6 +55,11 @@ def _worker(rank, world, port, case, outdir):
         # a second list on the same communicator (steady state of an MD loop) must give the same rows
         res2 = sh.neighbour_list_sharded_native(Xl, gl, cutoff, cell, pbc, comm, rank, world, with_R=True)
         assert torch.equal(res.first, res2.first) and torch.equal(res.owned_index, res2.owned_index)
+        # the shard's rows in host memory through the compressed transfer (global i is copied, not rebuilt)
+        import neighbourlists_jl_b200 as nl
+        h = nl.to_host(res)
+        for k in ("first", "i", "j", "S"):
+            assert np.array_equal(getattr(h, k), getattr(res, k).cpu().numpy()), k
     else:
         res = sh.neighbour_list_sharded(Xl, gl, cutoff, cell, pbc, with_R=True)
     torch.cuda.synchronize()
@@ -62,6 +67,7 @@ def _worker(rank, world, port, case, outdir):
              j=res.j.cpu().numpy(), S=res.S.cpu().numpy(), R=res.R.cpu().numpy(), bounds=res.plan.bounds, axis=res.plan.axis, n_halo=res.n_halo)
     if driver == "native":
         from neighbourlists_jl_b200 import _lib
+        sh.shard_disconnect(comm)
         _lib.check(_lib.lib().nl_nccl_comm_destroy(comm))
     dist.destroy_process_group()
 
@@ -138,3 +144,6 @@ def test_single_rank_shard_entry_points():
     assert np.array_equal(res.owned_index.cpu().numpy(), np.arange(1, X.shape[0] + 1))
     U.assert_engine_matches_oracle(dict(first=res.first.cpu().numpy(), i=res.i.cpu().numpy(), j=res.j.cpu().numpy(), S=res.S.cpu().numpy(),
                                         R=res.R.cpu().numpy()), orc, 1e-12, msg="one-rank shard path")
+    h = nl.to_host(res)
+    for k in ("first", "i", "j", "S"):
+        assert np.array_equal(getattr(h, k), getattr(res, k).cpu().numpy()), k
