@@ -297,8 +297,31 @@ struct NlShardInfo
     has_dn::Int32; has_up::Int32; dn_peer::Int32; up_peer::Int32
     n_local::Int64; n_owned::Int64; n_halo_dn::Int64; n_halo_up::Int64; n_send_dn::Int64; n_send_up::Int64
     bounds::NTuple{65,Int64}; send_count::NTuple{64,Int64}; recv_count::NTuple{64,Int64}
+    n_max_all::Int64; src_offset::NTuple{64,Int64}; halo_src_offset_dn::Int64; halo_src_offset_up::Int64
 end
-@assert sizeof(NlShardInfo) == 1632 "NlShardInfo must match struct nl_shard_info (include/nlcuda.h)"
+@assert sizeof(NlShardInfo) == 2168 "NlShardInfo must match struct nl_shard_info (include/nlcuda.h)"
+
+# Peer path (nl_shard_connect / nl_shard_exchange_peer): the ranks' workspaces mapped into each other (CUDA IPC), the all-to-all-v
+# and the halos as NVLink copies.  One persistent workspace per communicator, laid out for the same `cap` on every rank.
+mutable struct NlShardPeers
+    nranks::Int32; rank::Int32; cap::Int64; ws_bytes::UInt64; ws::Ptr{Cvoid}
+    peer_ws::NTuple{64,Ptr{Cvoid}}; peer_base::NTuple{64,Ptr{Cvoid}}
+    NlShardPeers() = new(0, 0, 0, 0, C_NULL, ntuple(_ -> C_NULL, 64), ntuple(_ -> C_NULL, 64))
+end
+const _PEERS = Dict{Ptr{Cvoid},Tuple{NlShardPeers,CuVector{UInt8}}}()      # per communicator: (peers, workspace)
+function _connect(p::NlParams, cap::Integer, comm::Ptr{Cvoid}, rank::Integer, nranks::Integer)
+    nb = Int(ccall((:nl_shard_workspace_bytes, libnlcuda), Csize_t, (Ref{NlParams}, Int64, Int32), p, cap, nranks))
+    ws = CuVector{UInt8}(undef, nb); peers = NlShardPeers()
+    _check(ccall((:nl_shard_connect, libnlcuda), Cint,
+                 (Ref{NlParams}, Int64, Ptr{Cvoid}, Int32, Int32, CuPtr{Cvoid}, Csize_t, Ref{NlShardPeers}, Ptr{Cvoid}),
+                 p, cap, comm, rank, nranks, ws, nb, peers, _stream()))
+    return _PEERS[comm] = (peers, ws)
+end
+function shard_disconnect(comm::Ptr{Cvoid})
+    haskey(_PEERS, comm) || return
+    peers, _ = pop!(_PEERS, comm)
+    _check(ccall((:nl_shard_disconnect, libnlcuda), Cint, (Ref{NlShardPeers},), peers))
+end
 
 nccl_unique_id() = (id = zeros(UInt8, 128); _check(ccall((:nl_nccl_unique_id, libnlcuda), Cint, (Ptr{UInt8},), id)); id)
 function nccl_comm(id::Vector{UInt8}, rank::Integer, nranks::Integer)
@@ -326,13 +349,18 @@ function sharded_pairlist(X::CuVector{SVec{T}}, gidx::CuVector{TI}, cutoff::T, c
                  p, X, n, comm, rank, nranks, info, ws, length(ws), _stream()))
     f = info[]
     nall = f.n_owned + f.n_halo_dn + f.n_halo_up
-    length(ws) < wsb(max(n, f.n_owned)) && (ws = CuVector{UInt8}(undef, wsb(max(n, f.n_owned))))
     Xall = CuVector{SVec{T}}(undef, nall); gall = CuVector{TI}(undef, nall)
     plane_active = ones(UInt8, ncells[3])
-    _check(ccall((:nl_shard_exchange, libnlcuda), Cint,
-                 (Ref{NlParams}, Ref{NlShardInfo}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{UInt8},
-                  CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
-                 p, info, X, gidx, n, comm, Xall, gall, plane_active, ws, length(ws), _stream()))
+    # f.n_max_all is the same number on every rank, so every rank (re)connects in the same call
+    if !haskey(_PEERS, comm) || _PEERS[comm][1].cap < f.n_max_all
+        shard_disconnect(comm)
+        _connect(p, f.n_max_all + f.n_max_all ÷ 5 + 4096, comm, rank, nranks)
+    end
+    peers, pws = _PEERS[comm]
+    _check(ccall((:nl_shard_exchange_peer, libnlcuda), Cint,
+                 (Ref{NlParams}, Ref{NlShardInfo}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, Ptr{Cvoid}, Ref{NlShardPeers}, CuPtr{Cvoid}, CuPtr{Cvoid},
+                  Ptr{UInt8}, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
+                 p, info, X, gidx, n, comm, peers, Xall, gall, plane_active, pws, length(pws), _stream()))
     clist = NeighbourLists.build_cell_list(Xall, cutoff, cell, pbc; int_type = TI)
     first, i, j, S = shard_pairlist(clist, f.n_owned, gall, (nranks > 1 && f.axis == 2) ? plane_active : nothing)
     return (@view gall[1:f.n_owned]), first, i, j, S
