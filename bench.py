@@ -280,7 +280,9 @@ def run_ours(args):
 
     def e2e_step():
         if world == 1:
-            pl = nl.neighbour_list(X_host, CUTOFF, C, pbc, device=dev)  # pinned H2D inside; reference layout (no R)
+            # pinned H2D inside; reference layout (no R); first is copied and i rebuilt by host threads while the fill pass runs
+            d2h_bytes[0] = 4 * (n_atoms + 1) + 5 * P + 4
+            return nl.neighbour_list(X_host, CUTOFF, C, pbc, device=dev, host_out=hbuf, host_threads=host_threads)
         else:
             pl = sharded.neighbour_list_sharded_native(X_host.to(dev, non_blocking=True), gidx_host.to(dev, non_blocking=True), CUTOFF, C, pbc,
                                                        comm, rank, world)

@@ -71,7 +71,7 @@ EXPORTS = ("nl_version", "nl_strerror", "nl_last_cuda_error", "nl_launch_count",
            "nl_pairs_R", "nl_max_neighbours", "nl_rows_padded", "nl_lazy_neighbours", "nl_bounding_box", "nl_max_displacement2",
            "nl_shard_workspace_bytes", "nl_shard_prepare", "nl_shard_exchange", "nl_nccl_unique_id", "nl_nccl_comm_init", "nl_nccl_comm_destroy",
            "nl_to_host_scratch_bytes", "nl_pairs_to_host", "nl_host_expand_rows", "nl_host_unpack_shifts",
-           "nl_shard_connect", "nl_shard_exchange_peer", "nl_shard_disconnect")
+           "nl_shard_connect", "nl_shard_exchange_peer", "nl_shard_disconnect", "nl_pairs_to_host_begin", "nl_pairs_to_host_finish")
 NL_REDUCE_WS_BYTES = 32768
 
 
@@ -122,7 +122,7 @@ def lib():
         L.nl_shard_connect.argtypes = [pp, i64, vp, C.c_int32, C.c_int32, vp, sz, pq, vp]
         L.nl_shard_exchange_peer.argtypes = [pp, ps, vp, vp, i64, vp, pq, vp, vp, vp, vp, sz, vp]
         L.nl_shard_disconnect.argtypes = [pq]
-        for n in ("nl_shard_connect", "nl_shard_exchange_peer", "nl_shard_disconnect"):
+        for n in ("nl_shard_connect", "nl_shard_exchange_peer", "nl_shard_disconnect", "nl_pairs_to_host_begin", "nl_pairs_to_host_finish"):
             getattr(L, n).restype = C.c_int
         L.nl_nccl_unique_id.argtypes = [vp]
         L.nl_nccl_comm_init.argtypes = [C.POINTER(vp), C.c_int32, vp, C.c_int32]
@@ -139,6 +139,10 @@ def lib():
         L.nl_to_host_scratch_bytes.argtypes = [i64]
         L.nl_pairs_to_host.argtypes = [pp, vp, i64, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, sz, C.c_int32, vp]
         L.nl_pairs_to_host.restype = C.c_int
+        L.nl_pairs_to_host_begin.argtypes = [pp, vp, i64, i64, vp, vp, C.c_int32, C.POINTER(vp)]
+        L.nl_pairs_to_host_begin.restype = C.c_int
+        L.nl_pairs_to_host_finish.argtypes = [vp, vp, vp, vp, vp, vp, vp, sz, vp]
+        L.nl_pairs_to_host_finish.restype = C.c_int
         L.nl_host_expand_rows.argtypes = [C.c_int32, vp, i64, i64, i64, vp]
         L.nl_host_expand_rows.restype = C.c_int
         L.nl_host_unpack_shifts.argtypes = [C.c_int32, vp, i64, i64, vp]

@@ -154,7 +154,7 @@ def build_cell_list(X, cutoff, cell=None, pbc=None, *, int_type=np.int32, device
 
 def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers: Optional[dict] = None,
                          n_rows: Optional[int] = None, index_map: Optional[torch.Tensor] = None, half: bool = False,
-                         plane_active: Optional[np.ndarray] = None) -> PairList:
+                         plane_active: Optional[np.ndarray] = None, host_out=None, host_threads: int = 0):
     """materialize_pairlist(clist) -> PairList  (src/gpu_kernels.jl:299-364).  with_R additionally
     stores R = X[j] - X[i] + C' S per pair (what the reference recomputes in _getR).
 
@@ -165,7 +165,10 @@ def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers:
     caller promises all other planes are empty and only those tile layers are launched (nl_*_window).
 
     half=True stores one pair of every mirror couple (i, j, S) / (j, i, -S) (NL_FLAG_HALF, include/nlcuda.h): half the
-    pairs, half the output traffic; which of the two is kept is unspecified."""
+    pairs, half the output traffic; which of the two is kept is unspecified.
+
+    host_out (HostPairBuffers, or True for the module-level set): the list goes straight to HOST memory and a HostPairList is
+    returned (nl_pairs_to_host_begin / _finish: `first` is copied and i rebuilt by host threads while the fill pass runs)."""
     import ctypes as C
     params = clist.params
     if half:
@@ -197,6 +200,14 @@ def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers:
         P = int(total.value)
         if n_rows is not None and not 0 <= n_rows <= N:
             raise ValueError("n_rows out of range")
+        job = None
+        if host_out is not None and host_out is not False:
+            if n_rows is not None or index_map is not None or with_R:
+                raise ValueError("host_out is for whole lists without R")
+            host_out = _host_buffers_for(P, N, it, dev, None if host_out is True else host_out)
+            job = C.c_void_p()
+            _lib.check(L.nl_pairs_to_host_begin(params, _ptr(first), N, P, host_out.first.data_ptr(), host_out.i.data_ptr(), int(host_threads),
+                                                C.byref(job)))
         # shard mode: the owned rows hold first[n_rows] - 1 <= total pairs.  The arrays are allocated for `total` and trimmed
         # AFTER the fill has been enqueued, so that this second host read does not leave the GPU idle between the two passes.
         if timers is not None:
@@ -207,26 +218,36 @@ def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers:
         R = torch.empty((P, 3), dtype=clist.X.dtype, device=dev) if with_R else None
         if timers is not None:
             ev[2].record()
-        if P > 0 and pa is not None:
-            if index_map is not None:
-                index_map = index_map.to(device=dev, dtype=it).contiguous()
-                assert index_map.shape[0] == N
-            _lib.check(L.nl_fill_pairs_window(params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
-                                              N if n_rows is None else n_rows, _ptr(index_map), pa_ptr, _ptr(i), _ptr(j), _ptr(S), _ptr(R),
-                                              _ptr(ws), ws.numel(), _stream(dev)))
-        elif P > 0 and n_rows is None and index_map is None:
-            _lib.check(L.nl_fill_pairs(params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
-                                       _ptr(i), _ptr(j), _ptr(S), _ptr(R), _ptr(ws), ws.numel(), _stream(dev)))
-        elif P > 0:
-            if index_map is not None:
-                index_map = index_map.to(device=dev, dtype=it).contiguous()
-                assert index_map.shape[0] == N
-            _lib.check(L.nl_fill_pairs_rows(params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
-                                            N if n_rows is None else n_rows, _ptr(index_map), _ptr(i), _ptr(j), _ptr(S), _ptr(R),
-                                            _ptr(ws), ws.numel(), _stream(dev)))
+        try:
+            if P > 0 and pa is not None:
+                if index_map is not None:
+                    index_map = index_map.to(device=dev, dtype=it).contiguous()
+                    assert index_map.shape[0] == N
+                _lib.check(L.nl_fill_pairs_window(params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
+                                                  N if n_rows is None else n_rows, _ptr(index_map), pa_ptr, _ptr(i), _ptr(j), _ptr(S), _ptr(R),
+                                                  _ptr(ws), ws.numel(), _stream(dev)))
+            elif P > 0 and n_rows is None and index_map is None:
+                _lib.check(L.nl_fill_pairs(params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
+                                           _ptr(i), _ptr(j), _ptr(S), _ptr(R), _ptr(ws), ws.numel(), _stream(dev)))
+            elif P > 0:
+                if index_map is not None:
+                    index_map = index_map.to(device=dev, dtype=it).contiguous()
+                    assert index_map.shape[0] == N
+                _lib.check(L.nl_fill_pairs_rows(params, _ptr(clist.X), N, _ptr(clist.perm), _ptr(clist.cell_offsets), _ptr(first),
+                                                N if n_rows is None else n_rows, _ptr(index_map), _ptr(i), _ptr(j), _ptr(S), _ptr(R),
+                                                _ptr(ws), ws.numel(), _stream(dev)))
+        except BaseException:
+            if job is not None:   # a job must be finished exactly once: this releases its host threads
+                L.nl_pairs_to_host_finish(job, None, None, None, None, None, None, 0, _stream(dev))
+            raise
         if timers is not None:
             ev[3].record()
             timers.setdefault("events", []).append(ev)
+        if job is not None:
+            _lib.check(L.nl_pairs_to_host_finish(job, _ptr(j), _ptr(S), host_out.j.data_ptr(), host_out.S.data_ptr(), host_out.dev_scratch.data_ptr(),
+                                                 host_out.host_scratch.data_ptr(), host_out.dev_scratch.numel(), _stream(dev)))
+            return HostPairList(X=clist.X_orig, C=clist.cell, cutoff=clist.cutoff, i=host_out.i[:P].numpy(), j=host_out.j[:P].numpy(),
+                                S=host_out.S[:P].numpy(), first=host_out.first[:N + 1].numpy())
         if n_rows is not None:
             Pr = int(first[n_rows].item()) - 1
             first = first[:n_rows + 1]
@@ -249,7 +270,7 @@ def cell_ids(X, cutoff, cell, pbc, *, int_type=np.int32, device=None) -> torch.T
 
 
 def neighbour_list(X, cutoff, cell=None, pbc=None, *, lazy: bool = False, int_type=np.int32, with_R: bool = False, device=None,
-                   half: bool = False):
+                   half: bool = False, host_out=None, host_threads: int = 0):
     """neighbour_list(X, cutoff, cell, pbc; lazy, int_type)  (src/cell_list.jl:897-916);
     neighbour_list(system, cutoff; lazy, int_type) for AtomsBase-style systems (atoms.py)."""
     if cell is None and pbc is None and hasattr(X, "positions"):
@@ -258,7 +279,7 @@ def neighbour_list(X, cutoff, cell=None, pbc=None, *, lazy: bool = False, int_ty
     clist = build_cell_list(X, cutoff, cell, pbc, int_type=int_type, device=device)
     if lazy:
         return clist
-    return materialize_pairlist(clist, with_R=with_R, half=half)
+    return materialize_pairlist(clist, with_R=with_R, half=half, host_out=host_out, host_threads=host_threads)
 
 
 
@@ -301,6 +322,18 @@ class HostPairBuffers:
 _host_buffers: Optional[HostPairBuffers] = None
 
 
+def _host_buffers_for(P: int, n_rows: int, it, dev, out: Optional[HostPairBuffers]) -> HostPairBuffers:
+    global _host_buffers
+    if out is None:
+        if _host_buffers is None or not _host_buffers.fits(P, n_rows, it) or _host_buffers.device != dev:
+            _host_buffers = None
+            _host_buffers = HostPairBuffers(int(P * 1.05) + 1024, n_rows, it, dev)
+        return _host_buffers
+    if not out.fits(P, n_rows, it):
+        raise ValueError("host buffers too small for this list")
+    return out
+
+
 def to_host(nlist, out: Optional[HostPairBuffers] = None, nthreads: int = 0, rebuild_i: Optional[bool] = None,
             i_copy_fraction: float = 0.0) -> HostPairList:
     """The whole list into host memory through nl_pairs_to_host (include/nlcuda.h): `first`, `j` and one byte per pair for S
@@ -309,18 +342,11 @@ def to_host(nlist, out: Optional[HostPairBuffers] = None, nthreads: int = 0, reb
     rebuilding it from `first` (needed for shard lists, whose i carries global indices; detected from the list's length);
     otherwise the last i_copy_fraction of i is copied and the rest rebuilt (0 is fastest where measured: the host's memory
     bandwidth, which DMA writes and host stores share, is the bound, not the host threads' instruction rate)."""
-    global _host_buffers
     P = int(nlist.i.shape[0])
     n_rows = int(nlist.first.shape[0]) - 1
     it = nlist.i.dtype
     dev = nlist.i.device
-    if out is None:
-        if _host_buffers is None or not _host_buffers.fits(P, n_rows, it) or _host_buffers.device != dev:
-            _host_buffers = None
-            _host_buffers = HostPairBuffers(int(P * 1.05) + 1024, n_rows, it, dev)
-        out = _host_buffers
-    elif not out.fits(P, n_rows, it):
-        raise ValueError("host buffers too small for this list")
+    out = _host_buffers_for(P, n_rows, it, dev, out)
     whole = isinstance(nlist, PairList) and n_rows == int(nlist.X.shape[0])   # a whole list: i[p] is the row of p
     if rebuild_i is None:
         rebuild_i = whole

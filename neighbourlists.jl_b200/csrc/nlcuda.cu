@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <new>
 #include <vector>
 
 #include "nl_build.cuh"
@@ -1051,6 +1052,138 @@ int pairs_to_host_impl(const void* first_d, int64_t n_rows, const void* i_d, int
   return rc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// nl_pairs_to_host_begin / _finish: the same transfer with the `first` copy and the rebuild of i started right after the counting
+// pass, so that they run while the fill pass is still on the GPU.  Worker 0 waits for the `first` copy (its own CUDA call, on the
+// job's private stream); everything else is driven by the thread that calls finish.
+}  // namespace
+struct nl_to_host_job {
+  int dev = 0;
+  int int64 = 0;
+  int64_t n_rows = 0, P = 0;
+  const void* first_h = nullptr;
+  void* i_h = nullptr;
+  cudaStream_t aux = nullptr;
+  cudaEvent_t ev_first = nullptr;
+  int T = 0;
+  std::vector<std::thread> workers;
+  std::atomic<int> ready{0};        // 1: first is on the host and belongs to P; -1: abort
+  std::atomic<int> phase2{0};       // 1: unpack the code chunks as they arrive; 2: nothing to unpack (S copied as it is); -1: abort
+  std::atomic<int> chunks_ready{0};
+  std::atomic<int> error{0};
+  // set by finish before phase2 is published
+  const uint8_t* codes_h = nullptr;
+  void* S_h = nullptr;
+  int nchunks = 0;
+  int64_t chunk = 0;
+};
+namespace {
+
+template <class TI>
+void to_host_worker(nl_to_host_job* J, int t) {
+  if (t == 0) {
+    int ok = cudaSetDevice(J->dev) == cudaSuccess && cudaEventSynchronize(J->ev_first) == cudaSuccess;
+    if (ok && ((int64_t)((const TI*)J->first_h)[J->n_rows] - 1 != J->P || ((const TI*)J->first_h)[0] != 1)) {
+      J->error.store(NL_ERR_BAD_ARG);
+      ok = 0;
+    } else if (!ok) {
+      J->error.store(NL_ERR_CUDA);
+    }
+    J->ready.store(ok ? 1 : -1, std::memory_order_release);
+  }
+  int v;
+  while ((v = J->ready.load(std::memory_order_acquire)) == 0) std::this_thread::yield();
+  if (v < 0) return;
+  const int T = J->T;
+  const int64_t P = J->P;
+  {
+    const int64_t q = ((P + T - 1) / T + 3) & ~(int64_t)3;
+    host_expand_rows<TI>((const TI*)J->first_h, (long long)J->n_rows, std::min<int64_t>(P, q * t), std::min<int64_t>(P, q * (t + 1)), (TI*)J->i_h);
+  }
+  while ((v = J->phase2.load(std::memory_order_acquire)) == 0) std::this_thread::yield();
+  if (v != 1) return;
+  for (int k = 0; k < J->nchunks; k++) {
+    int c;
+    while ((c = J->chunks_ready.load(std::memory_order_acquire)) <= k && c >= 0) std::this_thread::yield();
+    if (c < 0) return;
+    const int64_t c0 = (int64_t)k * J->chunk, c1 = std::min<int64_t>(P, c0 + J->chunk);
+    if (c1 <= c0) continue;
+    const int64_t q = ((c1 - c0 + T - 1) / T + 3) & ~(int64_t)3;
+    host_unpack_shifts<TI>(J->codes_h, std::min(c1, c0 + q * t), std::min(c1, c0 + q * (t + 1)), (TI*)J->S_h);
+  }
+}
+
+void to_host_job_free(nl_to_host_job* J) {
+  for (auto& w : J->workers) if (w.joinable()) w.join();
+  if (J->ev_first) cudaEventDestroy(J->ev_first);
+  if (J->aux) cudaStreamDestroy(J->aux);
+  delete J;
+}
+
+template <class TI>
+int to_host_finish_impl(nl_to_host_job* J, const void* j_d, const void* S_d, void* j_h, void* S_h, void* dscratch, void* hscratch, cudaStream_t st) {
+  const int64_t P = J->P;
+  int rc = NL_OK;
+  auto stop = [&](int code) {
+    if (rc == NL_OK) rc = code;
+    J->phase2.store(-1, std::memory_order_release);
+    J->chunks_ready.store(-1, std::memory_order_release);
+  };
+  std::vector<cudaEvent_t> ev;
+  if (P > 0) {
+    uint8_t* codes_d = (uint8_t*)dscratch;
+    uint8_t* codes_h = (uint8_t*)hscratch;
+    unsigned* flag_d = (unsigned*)(codes_d + al256((size_t)P));
+    volatile unsigned* flag_h = (volatile unsigned*)(codes_h + al256((size_t)P));
+    const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(16, (P + (32ll << 20) - 1) / (32ll << 20)));
+    const int64_t chunk = ((P + nchunks - 1) / nchunks + 63) & ~(int64_t)63;
+    ev.assign(nchunks + 1, nullptr);
+    cudaError_t ce = cudaSuccess;
+    for (auto& e : ev)
+      if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    if (ce == cudaSuccess) ce = cudaMemsetAsync(flag_d, 0, 4, st);
+    if (ce == cudaSuccess) {
+      const unsigned nb = (unsigned)((P + 256 * TH_PAIRS - 1) / (256 * TH_PAIRS));
+      k_pack_shifts<TI><<<nb, 256, 0, st>>>((const TI*)S_d, (long long)P, codes_d, flag_d, (((uintptr_t)S_d) & 15) == 0 ? 1 : 0);
+      NL_LAUNCHED(1);
+      ce = cudaGetLastError();
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync((void*)flag_h, flag_d, 4, cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaEventRecord(ev[0], st);
+    for (int k = 0; k < nchunks && ce == cudaSuccess; k++) {
+      const int64_t c0 = (int64_t)k * chunk, c1 = std::min<int64_t>(P, c0 + chunk);
+      if (c1 > c0) ce = cudaMemcpyAsync(codes_h + c0, codes_d + c0, (size_t)(c1 - c0), cudaMemcpyDeviceToHost, st);
+      if (ce == cudaSuccess) ce = cudaEventRecord(ev[k + 1], st);
+    }
+    if (ce == cudaSuccess) ce = cudaMemcpyAsync(j_h, j_d, (size_t)P * sizeof(TI), cudaMemcpyDeviceToHost, st);
+    if (ce == cudaSuccess) ce = cudaEventSynchronize(ev[0]);
+    if (ce != cudaSuccess) stop(cuda_fail(ce));
+    else if (*flag_h) {  // a shift component outside {-1, 0, 1}: S goes over the bus as it is
+      J->phase2.store(2, std::memory_order_release);
+      ce = cudaMemcpyAsync(S_h, S_d, (size_t)P * 3 * sizeof(TI), cudaMemcpyDeviceToHost, st);
+      if (ce != cudaSuccess) stop(cuda_fail(ce));
+    } else {
+      J->codes_h = codes_h; J->S_h = S_h; J->nchunks = nchunks; J->chunk = chunk;
+      J->phase2.store(1, std::memory_order_release);
+      for (int k = 0; k < nchunks && rc == NL_OK; k++) {
+        ce = cudaEventSynchronize(ev[k + 1]);
+        if (ce != cudaSuccess) stop(cuda_fail(ce));
+        else J->chunks_ready.store(k + 1, std::memory_order_release);
+      }
+    }
+  }
+  cudaError_t ce = cudaStreamSynchronize(st);
+  if (ce != cudaSuccess) stop(cuda_fail(ce));
+  ce = cudaStreamSynchronize(J->aux);
+  if (ce != cudaSuccess) stop(cuda_fail(ce));
+  if (J->phase2.load() == 0) J->phase2.store(2, std::memory_order_release);  // P == 0: nothing was started
+  for (auto& w : J->workers) w.join();
+  for (auto e : ev) if (e) cudaEventDestroy(e);
+  if (rc == NL_OK && J->error.load()) rc = J->error.load();
+  to_host_job_free(J);
+  return rc;
+}
+
 }  // namespace
 
 // ================================================================ exported C ABI
@@ -1427,6 +1560,58 @@ int nl_pairs_to_host(const nl_params* params, const void* first, int64_t n_rows,
   return params->int_type == NL_I64
              ? pairs_to_host_impl<int64_t>(first, n_rows, i, i_copy_from, j, S, P, first_host, i_host, j_host, S_host, dev_scratch, host_scratch, nthreads, st)
              : pairs_to_host_impl<int32_t>(first, n_rows, i, i_copy_from, j, S, P, first_host, i_host, j_host, S_host, dev_scratch, host_scratch, nthreads, st);
+}
+
+int nl_pairs_to_host_begin(const nl_params* params, const void* first, int64_t n_rows, int64_t P, void* first_host, void* i_host,
+                           int32_t nthreads, nl_to_host_job** job_out) {
+  if (!params || (params->int_type != NL_I32 && params->int_type != NL_I64)) return NL_ERR_BAD_ARG;
+  if (!job_out || n_rows < 0 || P < 0 || !first || !first_host || (P > 0 && !i_host)) return NL_ERR_BAD_ARG;
+  *job_out = nullptr;
+  if (nthreads <= 0) nthreads = (int32_t)std::max(1u, std::thread::hardware_concurrency());
+  nl_to_host_job* J = new (std::nothrow) nl_to_host_job();
+  if (!J) return NL_ERR_BAD_ARG;
+  J->int64 = params->int_type == NL_I64;
+  J->n_rows = n_rows; J->P = P; J->first_h = first_host; J->i_h = i_host;
+  J->T = P > 0 ? std::max(1, std::min<int>(nthreads, 256)) : 0;
+  const size_t w = J->int64 ? 8 : 4;
+  cudaError_t ce = cudaGetDevice(&J->dev);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&J->aux, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&J->ev_first, cudaEventDisableTiming);
+  // `first` is final: nl_count_pairs has synchronised the caller's stream before returning P
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(first_host, first, (size_t)(n_rows + 1) * w, cudaMemcpyDeviceToHost, J->aux);
+  if (ce == cudaSuccess) ce = cudaEventRecord(J->ev_first, J->aux);
+  if (ce != cudaSuccess) {
+    to_host_job_free(J);
+    return cuda_fail(ce);
+  }
+  J->workers.reserve(J->T);
+  for (int t = 0; t < J->T; t++) {
+    if (J->int64) J->workers.emplace_back(to_host_worker<int64_t>, J, t);
+    else J->workers.emplace_back(to_host_worker<int32_t>, J, t);
+  }
+  *job_out = J;
+  return NL_OK;
+}
+
+int nl_pairs_to_host_finish(nl_to_host_job* job, const void* j, const void* S, void* j_host, void* S_host, void* dev_scratch,
+                            void* host_scratch, size_t scratch_bytes, void* stream) {
+  if (!job) return NL_ERR_BAD_ARG;
+  const int64_t P = job->P;
+  int bad = NL_OK;
+  if (P > 0 && (!j || !S || !j_host || !S_host)) bad = NL_ERR_BAD_ARG;
+  else if (P > 0 && (!dev_scratch || !host_scratch || scratch_bytes < nl_to_host_scratch_bytes(P) ||
+                     ((((uintptr_t)dev_scratch) | ((uintptr_t)host_scratch)) & 15)))
+    bad = NL_ERR_WORKSPACE;
+  if (bad) {  // the job is consumed either way: stop its workers and release it
+    job->phase2.store(-1, std::memory_order_release);
+    job->chunks_ready.store(-1, std::memory_order_release);
+    cudaStreamSynchronize(job->aux);
+    to_host_job_free(job);
+    return bad;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  return job->int64 ? to_host_finish_impl<int64_t>(job, j, S, j_host, S_host, dev_scratch, host_scratch, st)
+                    : to_host_finish_impl<int32_t>(job, j, S, j_host, S_host, dev_scratch, host_scratch, st);
 }
 
 int nl_host_expand_rows(int32_t int_type, const void* first, int64_t n_rows, int64_t p_lo, int64_t p_hi, void* i_out) {

@@ -104,3 +104,36 @@ def test_to_host_rejects_first_that_does_not_match(nl):
     with pytest.raises(nl.NlError) as e:
         nl.to_host(bad)
     assert e.value.code == nl._lib.NL_ERR_BAD_ARG
+
+
+@pytest.mark.parametrize("int_type", [np.int32, np.int64])
+def test_host_out_overlapped_transfer(nl, int_type):
+    """neighbour_list(..., host_out=...) = nl_pairs_to_host_begin right after the counting pass + _finish after the fill."""
+    import torch
+    X, C, L = U.rand_config(30000, seed=67)
+    Xd = torch.from_numpy(X).cuda()
+    ref = nl.neighbour_list(Xd, 5.0, C, (True, True, False), int_type=int_type).cpu()
+    for host_out in (True, nl.HostPairBuffers(len(ref["i"]) + 7, 30000, int_type)):
+        for nt in (0, 1, 5):
+            h = nl.neighbour_list(Xd, 5.0, C, (True, True, False), int_type=int_type, host_out=host_out, host_threads=nt)
+            assert isinstance(h, nl.HostPairList)
+            for k in ("first", "i", "j", "S"):
+                assert np.array_equal(getattr(h, k), ref[k]), k
+    # host positions in, host list out: the whole end-to-end call
+    h = nl.neighbour_list(X, 5.0, C, (True, True, False), int_type=int_type, host_out=True)
+    assert np.array_equal(h.j, ref["j"]) and np.array_equal(h.i, ref["i"])
+    # wide shifts (S copied as it is), an empty list, and a half list
+    Xw = U.displace_by_lattice(X[:3000], C, (True, True, True), seed=3)
+    pw = nl.neighbour_list(torch.from_numpy(Xw).cuda(), 5.0, C, (True, True, True), int_type=int_type)
+    hw = nl.neighbour_list(torch.from_numpy(Xw).cuda(), 5.0, C, (True, True, True), int_type=int_type, host_out=True)
+    assert np.array_equal(hw.S, pw.S.cpu().numpy()) and np.array_equal(hw.i, pw.i.cpu().numpy())
+    he = nl.neighbour_list(np.array([[0.0, 0, 0], [50.0, 50, 50]]), 1.0, np.eye(3) * 100.0, (False, False, False), int_type=int_type, host_out=True)
+    assert he.first.tolist() == [1, 1, 1] and he.i.shape[0] == 0
+    ph = nl.neighbour_list(Xd, 5.0, C, (True, True, False), int_type=int_type, half=True)
+    hh = nl.neighbour_list(Xd, 5.0, C, (True, True, False), int_type=int_type, half=True, host_out=True)
+    assert np.array_equal(hh.j, ph.j.cpu().numpy()) and np.array_equal(hh.first, ph.first.cpu().numpy())
+    with pytest.raises(ValueError):
+        nl.neighbour_list(Xd, 5.0, C, (True, True, False), with_R=True, host_out=True)
+    small = nl.HostPairBuffers(10, 30000, int_type)
+    with pytest.raises(ValueError):
+        nl.neighbour_list(Xd, 5.0, C, (True, True, False), int_type=int_type, host_out=small)
