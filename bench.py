@@ -8,8 +8,10 @@ cubic box, rho = 0.05 A^-3, rc = 5 A, full PBC, Float64 / Int32, 10 M atoms per 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--atoms A]
 
 One JSON line on stdout (rank 0).  `value` = pairs/s with positions already resident in HBM;
-`e2e` = the same through the public API with HOST buffers (pinned H2D of the positions and D2H of
-the whole PairList inside the timed region); `roofline` = the dominant (pair-fill) kernel against the
+`e2e` = the same through the public API with HOST buffers: pinned H2D of the positions, the list, and the
+whole PairList (i, j, S, first) complete in pinned host memory inside the timed region (nl_pairs_to_host:
+5 B/pair cross the bus, i and S are rebuilt by host threads of the library; d2h_bytes_per_step counts what
+actually crosses the bus); `roofline` = the dominant (pair-fill) kernel against the
 measured HBM peak; `cpu_baseline` = the C++ restatement of the reference's CPU path (oracle/) on a
 bounded sample.  `--impl reference` times that CPU restatement alone (Julia is not installed here, so
 the real reference cannot be run).

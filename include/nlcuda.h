@@ -322,13 +322,14 @@ NL_API int nl_pairs_to_host(const nl_params* params, const void* first, int64_t 
 /* The same transfer in two steps, so that the `first` copy and the rebuild of i (a third of the host-side work) run WHILE the fill pass
  * is still on the GPU:
  *     nl_count_pairs(...)                       -> P
- *     nl_pairs_to_host_begin(first, n_rows, P, first_host, i_host, nthreads, &job)    returns at once; own stream + host threads
+ *     nl_pairs_to_host_begin(first, n_rows, P, first_host, i_host, nthreads, stream, &job)   returns at once; own stream (ordered
+ *                                                  after what `stream` holds at the time of the call) + host threads
  *     nl_fill_pairs(..., stream)
  *     nl_pairs_to_host_finish(job, j, S, j_host, S_host, scratch..., stream)          blocks until every host array is complete
  * For whole lists only (i is rebuilt from first).  Every job must be finished exactly once (finish releases it, also on error). */
 typedef struct nl_to_host_job nl_to_host_job;
 NL_API int nl_pairs_to_host_begin(const nl_params* params, const void* first, int64_t n_rows, int64_t P, void* first_host,
-                                  void* i_host, int32_t nthreads, nl_to_host_job** job_out);
+                                  void* i_host, int32_t nthreads, void* stream, nl_to_host_job** job_out);
 NL_API int nl_pairs_to_host_finish(nl_to_host_job* job, const void* j, const void* S, void* j_host, void* S_host,
                                    void* dev_scratch, void* host_scratch, size_t scratch_bytes, void* stream);
 /* The two host-side decoders of that format on their own (pure host code, no CUDA call): pairs [p_lo, p_hi), 0-based.  */

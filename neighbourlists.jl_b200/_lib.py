@@ -139,7 +139,7 @@ def lib():
         L.nl_to_host_scratch_bytes.argtypes = [i64]
         L.nl_pairs_to_host.argtypes = [pp, vp, i64, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, sz, C.c_int32, vp]
         L.nl_pairs_to_host.restype = C.c_int
-        L.nl_pairs_to_host_begin.argtypes = [pp, vp, i64, i64, vp, vp, C.c_int32, C.POINTER(vp)]
+        L.nl_pairs_to_host_begin.argtypes = [pp, vp, i64, i64, vp, vp, C.c_int32, vp, C.POINTER(vp)]
         L.nl_pairs_to_host_begin.restype = C.c_int
         L.nl_pairs_to_host_finish.argtypes = [vp, vp, vp, vp, vp, vp, vp, sz, vp]
         L.nl_pairs_to_host_finish.restype = C.c_int

@@ -207,7 +207,7 @@ def materialize_pairlist(clist: SortedCellList, *, with_R: bool = False, timers:
             host_out = _host_buffers_for(P, N, it, dev, None if host_out is True else host_out)
             job = C.c_void_p()
             _lib.check(L.nl_pairs_to_host_begin(params, _ptr(first), N, P, host_out.first.data_ptr(), host_out.i.data_ptr(), int(host_threads),
-                                                C.byref(job)))
+                                                _stream(dev), C.byref(job)))
         # shard mode: the owned rows hold first[n_rows] - 1 <= total pairs.  The arrays are allocated for `total` and trimmed
         # AFTER the fill has been enqueued, so that this second host read does not leave the GPU idle between the two passes.
         if timers is not None:

@@ -958,123 +958,33 @@ int check_ws(const void* ws, size_t have, size_t need) {
 
 
 // ---------------------------------------------------------------------------------------------------------------------
-// nl_pairs_to_host: see nl_tohost.cuh.  Only the calling thread talks to CUDA; the worker threads wait on a counter.
-template <class TI>
-int pairs_to_host_impl(const void* first_d, int64_t n_rows, const void* i_d, int64_t i_from, const void* j_d, const void* S_d, int64_t P, void* first_h,
-                       void* i_h, void* j_h, void* S_h, void* dscratch, void* hscratch, int nthreads, cudaStream_t st) {
-  NL_CUDA(cudaMemcpyAsync(first_h, first_d, (size_t)(n_rows + 1) * sizeof(TI), cudaMemcpyDeviceToHost, st));
-  if (P == 0) {
-    NL_CUDA(cudaStreamSynchronize(st));
-    return NL_OK;
-  }
-  uint8_t* codes_d = (uint8_t*)dscratch;
-  uint8_t* codes_h = (uint8_t*)hscratch;
-  unsigned* flag_d = (unsigned*)(codes_d + al256((size_t)P));
-  volatile unsigned* flag_h = (volatile unsigned*)(codes_h + al256((size_t)P));
-  NL_CUDA(cudaMemsetAsync(flag_d, 0, 4, st));
-  const unsigned nb = (unsigned)((P + 256 * TH_PAIRS - 1) / (256 * TH_PAIRS));
-  k_pack_shifts<TI><<<nb, 256, 0, st>>>((const TI*)S_d, (long long)P, codes_d, flag_d, (((uintptr_t)S_d) & 15) == 0 ? 1 : 0);
-  NL_LAUNCHED(1);
-  NL_LAUNCH_CHECK();
-  NL_CUDA(cudaMemcpyAsync((void*)flag_h, flag_d, 4, cudaMemcpyDeviceToHost, st));
-
-  const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(16, (P + (32ll << 20) - 1) / (32ll << 20)));
-  const int64_t chunk = ((P + nchunks - 1) / nchunks + 63) & ~(int64_t)63;  // multiple of 64 pairs: slices of S stay 16-byte aligned
-  std::vector<cudaEvent_t> ev(nchunks + 1, nullptr);
-  auto destroy = [&]() { for (auto e : ev) if (e) cudaEventDestroy(e); };
-  for (auto& e : ev) {
-    cudaError_t ce = cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
-    if (ce != cudaSuccess) { destroy(); return cuda_fail(ce); }
-  }
-#define NL_CUDA_EV(expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { destroy(); return cuda_fail(e__); } } while (0)
-  NL_CUDA_EV(cudaEventRecord(ev[0], st));  // first + escape flag are on the host
-  for (int k = 0; k < nchunks; k++) {
-    const int64_t c0 = (int64_t)k * chunk, c1 = std::min<int64_t>(P, c0 + chunk);
-    if (c1 > c0) NL_CUDA_EV(cudaMemcpyAsync(codes_h + c0, codes_d + c0, (size_t)(c1 - c0), cudaMemcpyDeviceToHost, st));
-    NL_CUDA_EV(cudaEventRecord(ev[k + 1], st));
-  }
-  if (i_from < P)  // this part of i crosses the bus, [0, i_from) is rebuilt from first
-    NL_CUDA_EV(cudaMemcpyAsync((TI*)i_h + i_from, (const TI*)i_d + i_from, (size_t)(P - i_from) * sizeof(TI), cudaMemcpyDeviceToHost, st));
-  NL_CUDA_EV(cudaMemcpyAsync(j_h, j_d, (size_t)P * sizeof(TI), cudaMemcpyDeviceToHost, st));
-#undef NL_CUDA_EV
-
-  std::atomic<int> ready{0};  // 1: first + flag; 2 + k: code chunk k; -1: abort
-  std::atomic<int> escape{0};
-  const int T = std::max(1, std::min(nthreads, 256));
-  std::vector<std::thread> workers;
-  workers.reserve(T);
-  auto wait_for = [&ready](int need) {
-    int v;
-    while ((v = ready.load(std::memory_order_acquire)) < need && v >= 0) std::this_thread::yield();
-    return v >= 0;
-  };
-  for (int t = 0; t < T; t++) {
-    workers.emplace_back([&, t]() {
-      if (!wait_for(1)) return;
-      if (i_from > 0) {
-        const int64_t q = ((i_from + T - 1) / T + 3) & ~(int64_t)3;
-        host_expand_rows<TI>((const TI*)first_h, (long long)n_rows, std::min<int64_t>(i_from, q * t), std::min<int64_t>(i_from, q * (t + 1)), (TI*)i_h);
-      }
-      if (escape.load(std::memory_order_relaxed)) return;
-      for (int k = 0; k < nchunks; k++) {
-        if (!wait_for(2 + k)) return;
-        const int64_t c0 = (int64_t)k * chunk, c1 = std::min<int64_t>(P, c0 + chunk);
-        if (c1 <= c0) continue;
-        const int64_t q = ((c1 - c0 + T - 1) / T + 3) & ~(int64_t)3;
-        host_unpack_shifts<TI>(codes_h, std::min(c1, c0 + q * t), std::min(c1, c0 + q * (t + 1)), (TI*)S_h);
-      }
-    });
-  }
-  int rc = NL_OK;
-  auto stop_workers = [&](int code) { rc = code; ready.store(-1, std::memory_order_release); };
-  cudaError_t ce = cudaEventSynchronize(ev[0]);
-  if (ce != cudaSuccess) stop_workers(cuda_fail(ce));
-  else if ((int64_t)((const TI*)first_h)[n_rows] - 1 != P || ((const TI*)first_h)[0] != 1) stop_workers(NL_ERR_BAD_ARG);  // first and P do not belong together
-  else {
-    const bool esc = *flag_h != 0;
-    if (esc) escape.store(1, std::memory_order_relaxed);
-    ready.store(1, std::memory_order_release);
-    if (esc) {  // a shift component outside {-1, 0, 1}: S goes over the bus as it is
-      ce = cudaMemcpyAsync(S_h, S_d, (size_t)P * 3 * sizeof(TI), cudaMemcpyDeviceToHost, st);
-      if (ce != cudaSuccess) stop_workers(cuda_fail(ce));
-    } else {
-      for (int k = 0; k < nchunks && rc == NL_OK; k++) {
-        ce = cudaEventSynchronize(ev[k + 1]);
-        if (ce != cudaSuccess) stop_workers(cuda_fail(ce));
-        else ready.store(2 + k, std::memory_order_release);
-      }
-    }
-  }
-  ce = cudaStreamSynchronize(st);
-  if (ce != cudaSuccess && rc == NL_OK) stop_workers(cuda_fail(ce));
-  for (auto& w : workers) w.join();
-  destroy();
-  return rc;
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// nl_pairs_to_host_begin / _finish: the same transfer with the `first` copy and the rebuild of i started right after the counting
-// pass, so that they run while the fill pass is still on the GPU.  Worker 0 waits for the `first` copy (its own CUDA call, on the
-// job's private stream); everything else is driven by the thread that calls finish.
+// nl_pairs_to_host (+ _begin / _finish): see nl_tohost.cuh.  One job = one transfer.  begin copies `first` on the job's private
+// stream and starts the host threads; finish enqueues the device side (pack kernel, code chunks, j) on the caller's stream, feeds
+// the threads as the chunks arrive and waits for everything.  The threads take work from two queues -- slices of i (bound by
+// instruction rate) and slices of the arrived S chunks (bound by memory bandwidth) -- half of them preferring one, half the
+// other, so that both kinds of work are in flight at any time.
 }  // namespace
 struct nl_to_host_job {
   int dev = 0;
   int int64 = 0;
-  int64_t n_rows = 0, P = 0;
+  int64_t n_rows = 0, P = 0, i_from = 0;
   const void* first_h = nullptr;
   void* i_h = nullptr;
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_first = nullptr;
   int T = 0;
+  int n_islices = 0;                // i slices of [0, i_from)
+  int64_t islice = 0;
   std::vector<std::thread> workers;
   std::atomic<int> ready{0};        // 1: first is on the host and belongs to P; -1: abort
   std::atomic<int> phase2{0};       // 1: unpack the code chunks as they arrive; 2: nothing to unpack (S copied as it is); -1: abort
   std::atomic<int> chunks_ready{0};
+  std::atomic<int> next_i{0}, next_s{0};
   std::atomic<int> error{0};
   // set by finish before phase2 is published
   const uint8_t* codes_h = nullptr;
   void* S_h = nullptr;
-  int nchunks = 0;
+  int nchunks = 0, sslices = 0;     // S slices per chunk
   int64_t chunk = 0;
 };
 namespace {
@@ -1084,7 +994,7 @@ void to_host_worker(nl_to_host_job* J, int t) {
   if (t == 0) {
     int ok = cudaSetDevice(J->dev) == cudaSuccess && cudaEventSynchronize(J->ev_first) == cudaSuccess;
     if (ok && ((int64_t)((const TI*)J->first_h)[J->n_rows] - 1 != J->P || ((const TI*)J->first_h)[0] != 1)) {
-      J->error.store(NL_ERR_BAD_ARG);
+      J->error.store(NL_ERR_BAD_ARG);  // first and P do not belong together
       ok = 0;
     } else if (!ok) {
       J->error.store(NL_ERR_CUDA);
@@ -1094,22 +1004,36 @@ void to_host_worker(nl_to_host_job* J, int t) {
   int v;
   while ((v = J->ready.load(std::memory_order_acquire)) == 0) std::this_thread::yield();
   if (v < 0) return;
-  const int T = J->T;
   const int64_t P = J->P;
-  {
-    const int64_t q = ((P + T - 1) / T + 3) & ~(int64_t)3;
-    host_expand_rows<TI>((const TI*)J->first_h, (long long)J->n_rows, std::min<int64_t>(P, q * t), std::min<int64_t>(P, q * (t + 1)), (TI*)J->i_h);
-  }
-  while ((v = J->phase2.load(std::memory_order_acquire)) == 0) std::this_thread::yield();
-  if (v != 1) return;
-  for (int k = 0; k < J->nchunks; k++) {
-    int c;
-    while ((c = J->chunks_ready.load(std::memory_order_acquire)) <= k && c >= 0) std::this_thread::yield();
-    if (c < 0) return;
+  const bool prefer_s = (t & 1) != 0;
+  auto take_i = [&]() {
+    if (J->next_i.load(std::memory_order_relaxed) >= J->n_islices) return false;
+    const int k = J->next_i.fetch_add(1, std::memory_order_relaxed);
+    if (k >= J->n_islices) return false;
+    const int64_t a = std::min<int64_t>(J->i_from, J->islice * k), b = std::min<int64_t>(J->i_from, J->islice * (k + 1));
+    host_expand_rows<TI>((const TI*)J->first_h, (long long)J->n_rows, a, b, (TI*)J->i_h);
+    return true;
+  };
+  auto take_s = [&]() {
+    if (J->phase2.load(std::memory_order_acquire) != 1) return false;
+    const int avail = J->chunks_ready.load(std::memory_order_acquire) * J->sslices;
+    int s = J->next_s.load(std::memory_order_relaxed);
+    while (s < avail && !J->next_s.compare_exchange_weak(s, s + 1, std::memory_order_relaxed)) {}
+    if (s >= avail) return false;
+    const int k = s / J->sslices, u = s % J->sslices;
     const int64_t c0 = (int64_t)k * J->chunk, c1 = std::min<int64_t>(P, c0 + J->chunk);
-    if (c1 <= c0) continue;
-    const int64_t q = ((c1 - c0 + T - 1) / T + 3) & ~(int64_t)3;
-    host_unpack_shifts<TI>(J->codes_h, std::min(c1, c0 + q * t), std::min(c1, c0 + q * (t + 1)), (TI*)J->S_h);
+    const int64_t q = ((c1 - c0 + J->sslices - 1) / J->sslices + 3) & ~(int64_t)3;
+    host_unpack_shifts<TI>(J->codes_h, std::min(c1, c0 + q * u), std::min(c1, c0 + q * (u + 1)), (TI*)J->S_h);
+    return true;
+  };
+  while (true) {
+    if (prefer_s ? (take_s() || take_i()) : (take_i() || take_s())) continue;
+    const int p2 = J->phase2.load(std::memory_order_acquire);
+    if (p2 < 0 || J->chunks_ready.load(std::memory_order_acquire) < 0) return;
+    const bool i_done = J->next_i.load(std::memory_order_relaxed) >= J->n_islices;
+    const bool s_done = p2 == 2 || (p2 == 1 && J->next_s.load(std::memory_order_relaxed) >= J->nchunks * J->sslices);
+    if (i_done && s_done) return;
+    std::this_thread::yield();
   }
 }
 
@@ -1120,8 +1044,45 @@ void to_host_job_free(nl_to_host_job* J) {
   delete J;
 }
 
+// `first` must be final in stream order of `st` at the time of the call (after nl_count_pairs it is: that call synchronises)
+int to_host_begin(int int_type, const void* first, int64_t n_rows, int64_t P, int64_t i_from, void* first_host, void* i_host, int nthreads,
+                  cudaStream_t st, nl_to_host_job** job_out) {
+  *job_out = nullptr;
+  if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+  nl_to_host_job* J = new (std::nothrow) nl_to_host_job();
+  if (!J) return NL_ERR_BAD_ARG;
+  J->int64 = int_type == NL_I64;
+  J->n_rows = n_rows; J->P = P; J->i_from = i_from; J->first_h = first_host; J->i_h = i_host;
+  J->T = P > 0 ? std::max(1, std::min<int>(nthreads, 256)) : 0;
+  J->n_islices = i_from > 0 ? (int)std::min<int64_t>(4 * J->T, (i_from + 65535) / 65536) : 0;
+  J->islice = J->n_islices ? ((i_from + J->n_islices - 1) / J->n_islices + 63) & ~(int64_t)63 : 0;
+  const size_t w = J->int64 ? 8 : 4;
+  cudaEvent_t ev_in = nullptr;
+  cudaError_t ce = cudaGetDevice(&J->dev);
+  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&J->aux, cudaStreamNonBlocking);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&J->ev_first, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&ev_in, cudaEventDisableTiming);
+  if (ce == cudaSuccess) ce = cudaEventRecord(ev_in, st);           // whatever produced `first` on the caller's stream comes first
+  if (ce == cudaSuccess) ce = cudaStreamWaitEvent(J->aux, ev_in, 0);
+  if (ce == cudaSuccess) ce = cudaMemcpyAsync(first_host, first, (size_t)(n_rows + 1) * w, cudaMemcpyDeviceToHost, J->aux);
+  if (ce == cudaSuccess) ce = cudaEventRecord(J->ev_first, J->aux);
+  if (ev_in) cudaEventDestroy(ev_in);
+  if (ce != cudaSuccess) {
+    to_host_job_free(J);
+    return cuda_fail(ce);
+  }
+  J->workers.reserve(J->T);
+  for (int t = 0; t < J->T; t++) {
+    if (J->int64) J->workers.emplace_back(to_host_worker<int64_t>, J, t);
+    else J->workers.emplace_back(to_host_worker<int32_t>, J, t);
+  }
+  *job_out = J;
+  return NL_OK;
+}
+
 template <class TI>
-int to_host_finish_impl(nl_to_host_job* J, const void* j_d, const void* S_d, void* j_h, void* S_h, void* dscratch, void* hscratch, cudaStream_t st) {
+int to_host_finish_impl(nl_to_host_job* J, const void* i_d, const void* j_d, const void* S_d, void* j_h, void* S_h, void* dscratch, void* hscratch,
+                        cudaStream_t st) {
   const int64_t P = J->P;
   int rc = NL_OK;
   auto stop = [&](int code) {
@@ -1136,7 +1097,7 @@ int to_host_finish_impl(nl_to_host_job* J, const void* j_d, const void* S_d, voi
     unsigned* flag_d = (unsigned*)(codes_d + al256((size_t)P));
     volatile unsigned* flag_h = (volatile unsigned*)(codes_h + al256((size_t)P));
     const int nchunks = (int)std::max<int64_t>(1, std::min<int64_t>(16, (P + (32ll << 20) - 1) / (32ll << 20)));
-    const int64_t chunk = ((P + nchunks - 1) / nchunks + 63) & ~(int64_t)63;
+    const int64_t chunk = ((P + nchunks - 1) / nchunks + 63) & ~(int64_t)63;  // multiple of 64 pairs: slices of S stay 16-byte aligned
     ev.assign(nchunks + 1, nullptr);
     cudaError_t ce = cudaSuccess;
     for (auto& e : ev)
@@ -1155,6 +1116,8 @@ int to_host_finish_impl(nl_to_host_job* J, const void* j_d, const void* S_d, voi
       if (c1 > c0) ce = cudaMemcpyAsync(codes_h + c0, codes_d + c0, (size_t)(c1 - c0), cudaMemcpyDeviceToHost, st);
       if (ce == cudaSuccess) ce = cudaEventRecord(ev[k + 1], st);
     }
+    if (ce == cudaSuccess && J->i_from < P)  // this part of i crosses the bus, [0, i_from) is rebuilt from first
+      ce = cudaMemcpyAsync((TI*)J->i_h + J->i_from, (const TI*)i_d + J->i_from, (size_t)(P - J->i_from) * sizeof(TI), cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaMemcpyAsync(j_h, j_d, (size_t)P * sizeof(TI), cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaEventSynchronize(ev[0]);
     if (ce != cudaSuccess) stop(cuda_fail(ce));
@@ -1164,6 +1127,7 @@ int to_host_finish_impl(nl_to_host_job* J, const void* j_d, const void* S_d, voi
       if (ce != cudaSuccess) stop(cuda_fail(ce));
     } else {
       J->codes_h = codes_h; J->S_h = S_h; J->nchunks = nchunks; J->chunk = chunk;
+      J->sslices = std::max(1, std::min(J->T, 64));
       J->phase2.store(1, std::memory_order_release);
       for (int k = 0; k < nchunks && rc == NL_OK; k++) {
         ce = cudaEventSynchronize(ev[k + 1]);
@@ -1182,6 +1146,25 @@ int to_host_finish_impl(nl_to_host_job* J, const void* j_d, const void* S_d, voi
   if (rc == NL_OK && J->error.load()) rc = J->error.load();
   to_host_job_free(J);
   return rc;
+}
+
+int to_host_finish(nl_to_host_job* job, const void* i, const void* j, const void* S, void* j_host, void* S_host, void* dev_scratch,
+                   void* host_scratch, size_t scratch_bytes, cudaStream_t st) {
+  const int64_t P = job->P;
+  int bad = NL_OK;
+  if (P > 0 && (!j || !S || !j_host || !S_host || (job->i_from < P && !i))) bad = NL_ERR_BAD_ARG;
+  else if (P > 0 && (!dev_scratch || !host_scratch || scratch_bytes < al256((size_t)P) + 256 ||
+                     ((((uintptr_t)dev_scratch) | ((uintptr_t)host_scratch)) & 15)))
+    bad = NL_ERR_WORKSPACE;
+  if (bad) {  // the job is consumed either way: stop its workers and release it
+    job->phase2.store(-1, std::memory_order_release);
+    job->chunks_ready.store(-1, std::memory_order_release);
+    cudaStreamSynchronize(job->aux);
+    to_host_job_free(job);
+    return bad;
+  }
+  return job->int64 ? to_host_finish_impl<int64_t>(job, i, j, S, j_host, S_host, dev_scratch, host_scratch, st)
+                    : to_host_finish_impl<int32_t>(job, i, j, S, j_host, S_host, dev_scratch, host_scratch, st);
 }
 
 }  // namespace
@@ -1543,8 +1526,7 @@ int nl_max_displacement2(int32_t float_type, const void* X, const void* X_ref, i
 size_t nl_to_host_scratch_bytes(int64_t P) { return al256((size_t)(P > 0 ? P : 0)) + 256; }
 
 int nl_pairs_to_host(const nl_params* params, const void* first, int64_t n_rows, const void* i, int64_t i_copy_from, const void* j, const void* S,
-                     int64_t P,
-                     void* first_host, void* i_host, void* j_host, void* S_host, void* dev_scratch, void* host_scratch, size_t scratch_bytes,
+                     int64_t P, void* first_host, void* i_host, void* j_host, void* S_host, void* dev_scratch, void* host_scratch, size_t scratch_bytes,
                      int32_t nthreads, void* stream) {
   if (!params || (params->int_type != NL_I32 && params->int_type != NL_I64)) return NL_ERR_BAD_ARG;
   if (n_rows < 0 || P < 0 || !first || !first_host) return NL_ERR_BAD_ARG;
@@ -1555,63 +1537,23 @@ int nl_pairs_to_host(const nl_params* params, const void* first, int64_t n_rows,
     if (!dev_scratch || !host_scratch || scratch_bytes < nl_to_host_scratch_bytes(P)) return NL_ERR_WORKSPACE;
     if ((((uintptr_t)dev_scratch) | ((uintptr_t)host_scratch)) & 15) return NL_ERR_WORKSPACE;
   }
-  if (nthreads <= 0) nthreads = (int32_t)std::max(1u, std::thread::hardware_concurrency());
-  cudaStream_t st = (cudaStream_t)stream;
-  return params->int_type == NL_I64
-             ? pairs_to_host_impl<int64_t>(first, n_rows, i, i_copy_from, j, S, P, first_host, i_host, j_host, S_host, dev_scratch, host_scratch, nthreads, st)
-             : pairs_to_host_impl<int32_t>(first, n_rows, i, i_copy_from, j, S, P, first_host, i_host, j_host, S_host, dev_scratch, host_scratch, nthreads, st);
+  nl_to_host_job* job = nullptr;
+  int rc = to_host_begin(params->int_type, first, n_rows, P, i_copy_from, first_host, i_host, nthreads, (cudaStream_t)stream, &job);
+  if (rc) return rc;
+  return to_host_finish(job, i, j, S, j_host, S_host, dev_scratch, host_scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
 int nl_pairs_to_host_begin(const nl_params* params, const void* first, int64_t n_rows, int64_t P, void* first_host, void* i_host,
-                           int32_t nthreads, nl_to_host_job** job_out) {
+                           int32_t nthreads, void* stream, nl_to_host_job** job_out) {
   if (!params || (params->int_type != NL_I32 && params->int_type != NL_I64)) return NL_ERR_BAD_ARG;
   if (!job_out || n_rows < 0 || P < 0 || !first || !first_host || (P > 0 && !i_host)) return NL_ERR_BAD_ARG;
-  *job_out = nullptr;
-  if (nthreads <= 0) nthreads = (int32_t)std::max(1u, std::thread::hardware_concurrency());
-  nl_to_host_job* J = new (std::nothrow) nl_to_host_job();
-  if (!J) return NL_ERR_BAD_ARG;
-  J->int64 = params->int_type == NL_I64;
-  J->n_rows = n_rows; J->P = P; J->first_h = first_host; J->i_h = i_host;
-  J->T = P > 0 ? std::max(1, std::min<int>(nthreads, 256)) : 0;
-  const size_t w = J->int64 ? 8 : 4;
-  cudaError_t ce = cudaGetDevice(&J->dev);
-  if (ce == cudaSuccess) ce = cudaStreamCreateWithFlags(&J->aux, cudaStreamNonBlocking);
-  if (ce == cudaSuccess) ce = cudaEventCreateWithFlags(&J->ev_first, cudaEventDisableTiming);
-  // `first` is final: nl_count_pairs has synchronised the caller's stream before returning P
-  if (ce == cudaSuccess) ce = cudaMemcpyAsync(first_host, first, (size_t)(n_rows + 1) * w, cudaMemcpyDeviceToHost, J->aux);
-  if (ce == cudaSuccess) ce = cudaEventRecord(J->ev_first, J->aux);
-  if (ce != cudaSuccess) {
-    to_host_job_free(J);
-    return cuda_fail(ce);
-  }
-  J->workers.reserve(J->T);
-  for (int t = 0; t < J->T; t++) {
-    if (J->int64) J->workers.emplace_back(to_host_worker<int64_t>, J, t);
-    else J->workers.emplace_back(to_host_worker<int32_t>, J, t);
-  }
-  *job_out = J;
-  return NL_OK;
+  return to_host_begin(params->int_type, first, n_rows, P, P, first_host, i_host, nthreads, (cudaStream_t)stream, job_out);
 }
 
 int nl_pairs_to_host_finish(nl_to_host_job* job, const void* j, const void* S, void* j_host, void* S_host, void* dev_scratch,
                             void* host_scratch, size_t scratch_bytes, void* stream) {
   if (!job) return NL_ERR_BAD_ARG;
-  const int64_t P = job->P;
-  int bad = NL_OK;
-  if (P > 0 && (!j || !S || !j_host || !S_host)) bad = NL_ERR_BAD_ARG;
-  else if (P > 0 && (!dev_scratch || !host_scratch || scratch_bytes < nl_to_host_scratch_bytes(P) ||
-                     ((((uintptr_t)dev_scratch) | ((uintptr_t)host_scratch)) & 15)))
-    bad = NL_ERR_WORKSPACE;
-  if (bad) {  // the job is consumed either way: stop its workers and release it
-    job->phase2.store(-1, std::memory_order_release);
-    job->chunks_ready.store(-1, std::memory_order_release);
-    cudaStreamSynchronize(job->aux);
-    to_host_job_free(job);
-    return bad;
-  }
-  cudaStream_t st = (cudaStream_t)stream;
-  return job->int64 ? to_host_finish_impl<int64_t>(job, j, S, j_host, S_host, dev_scratch, host_scratch, st)
-                    : to_host_finish_impl<int32_t>(job, j, S, j_host, S_host, dev_scratch, host_scratch, st);
+  return to_host_finish(job, nullptr, j, S, j_host, S_host, dev_scratch, host_scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
 int nl_host_expand_rows(int32_t int_type, const void* first, int64_t n_rows, int64_t p_lo, int64_t p_hi, void* i_out) {
