@@ -312,7 +312,7 @@ NL_API int nl_max_displacement2(int32_t float_type, const void* X, const void* X
  *                                the host threads and the bus; i_copy_from == P was fastest where measured.
  *   *_host          out  HOST    n_rows + 1, P, P, 3 P elements of TI; pinned memory for full PCIe speed
  *   dev_scratch / host_scratch   nl_to_host_scratch_bytes(P) bytes each, 16-byte aligned; host_scratch pinned
- *   nthreads        host worker threads (<= 0: hardware concurrency)
+ *   nthreads        host worker threads (<= 0: half the hardware concurrency -- the decoders are bound by memory bandwidth)
  * Blocks until every host array is complete (it is a device -> host read); enqueues on `stream`.
  * NL_ERR_BAD_ARG if first[n_rows] - 1 != P.                                                                        */
 NL_API size_t nl_to_host_scratch_bytes(int64_t P);

@@ -11,9 +11,6 @@
 #include <atomic>
 #include <thread>
 #include <vector>
-#if defined(__SSE2__)
-#include <emmintrin.h>
-#endif
 #include "nl_common.cuh"
 
 namespace nl {
@@ -65,100 +62,22 @@ __global__ void __launch_bounds__(256) k_pack_shifts(const TI* __restrict__ S, l
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-// i[p] = r + 1 for first[r] - 1 <= p < first[r + 1] - 1 (first is 1-based), for p in [p_lo, p_hi).
+// The decoders live in nl_hostcodec.cpp (plain C++, AVX2 variants picked at run time).
+}  // namespace nl
+namespace nl_host {
+void expand_rows(int int64, const void* first, long long n_rows, long long p_lo, long long p_hi, void* i_out);
+void unpack_shifts(int int64, const uint8_t* codes, long long p_lo, long long p_hi, void* S_out);
+}  // namespace nl_host
+namespace nl {
+// i[p] = r + 1 for first[r] - 1 <= p < first[r + 1] - 1 (first is 1-based), for p in [p_lo, p_hi)
 template <class TI>
-void host_expand_rows(const TI* first, long long n_rows, long long p_lo, long long p_hi, TI* i_out) {
-  if (p_hi <= p_lo) return;
-  // row of p_lo: last r with first[r] - 1 <= p_lo
-  long long lo = 0, hi = n_rows;
-  while (hi - lo > 1) {
-    const long long mid = (lo + hi) >> 1;
-    if ((long long)first[mid] - 1 <= p_lo) lo = mid; else hi = mid;
-  }
-  long long r = lo;
-  long long p = p_lo;
-  long long e = (long long)first[r + 1] - 1;  // end of row r
-  while (e <= p && r + 1 < n_rows) { r++; e = (long long)first[r + 1] - 1; }
-#if defined(__SSE2__)
-  if (sizeof(TI) == 4) {
-    int* out = (int*)i_out;
-    while (p < p_hi && (((uintptr_t)(out + p)) & 15)) {  // head up to a 16-byte boundary
-      while (e <= p) { r++; e = (long long)first[r + 1] - 1; }
-      out[p++] = (int)(r + 1);
-    }
-    while (p + 4 <= p_hi) {
-      while (e <= p) { r++; e = (long long)first[r + 1] - 1; }
-      if (p + 4 <= e) {
-        const __m128i v = _mm_set1_epi32((int)(r + 1));
-        const long long stop = (e < p_hi ? e : p_hi) - 3;
-        for (; p < stop; p += 4) _mm_stream_si128((__m128i*)(out + p), v);
-      } else {
-        int t[4];
-        for (int k = 0; k < 4; k++) {
-          while (e <= p + k) { r++; e = (long long)first[r + 1] - 1; }
-          t[k] = (int)(r + 1);
-        }
-        _mm_stream_si128((__m128i*)(out + p), _mm_set_epi32(t[3], t[2], t[1], t[0]));
-        p += 4;
-      }
-    }
-  }
-#endif
-  for (; p < p_hi; p++) {
-    while (e <= p) { r++; e = (long long)first[r + 1] - 1; }
-    i_out[p] = (TI)(r + 1);
-  }
-#if defined(__SSE2__)
-  _mm_sfence();
-#endif
+inline void host_expand_rows(const TI* first, long long n_rows, long long p_lo, long long p_hi, TI* i_out) {
+  nl_host::expand_rows(sizeof(TI) == 8, first, n_rows, p_lo, p_hi, i_out);
 }
-
 // S[p] = decode(codes[p]) for p in [p_lo, p_hi)
 template <class TI>
-void host_unpack_shifts(const uint8_t* codes, long long p_lo, long long p_hi, TI* S_out) {
-  long long p = p_lo;
-#if defined(__SSE2__)
-  if (sizeof(TI) == 4 && (((uintptr_t)S_out) & 15) == 0) {
-    alignas(16) static const struct Lut {
-      int v[256][4];
-      Lut() {
-        for (int c = 0; c < 256; c++) {
-          const int k = c < 27 ? c : 13;
-          v[c][0] = k % 3 - 1; v[c][1] = (k / 3) % 3 - 1; v[c][2] = k / 9 - 1; v[c][3] = 0;
-        }
-      }
-    } lut;
-    int* out = (int*)S_out;
-    for (; p < p_hi && (p & 3); p++) {
-      const int* t = lut.v[codes[p]];
-      out[3 * p] = t[0]; out[3 * p + 1] = t[1]; out[3 * p + 2] = t[2];
-    }
-    for (; p + 4 <= p_hi; p += 4) {  // 4 pairs = 48 bytes = three aligned 16-byte words
-      uint32_t c4;
-      memcpy(&c4, codes + p, 4);
-      if (c4 == 0x0d0d0d0du) {  // the common case: no shift
-        const __m128i z = _mm_setzero_si128();
-        __m128i* d = (__m128i*)(out + 3 * p);
-        _mm_stream_si128(d, z); _mm_stream_si128(d + 1, z); _mm_stream_si128(d + 2, z);
-        continue;
-      }
-      const int* a = lut.v[c4 & 255], *b = lut.v[(c4 >> 8) & 255], *c = lut.v[(c4 >> 16) & 255], *e = lut.v[c4 >> 24];
-      __m128i* d = (__m128i*)(out + 3 * p);
-      _mm_stream_si128(d, _mm_set_epi32(b[0], a[2], a[1], a[0]));
-      _mm_stream_si128(d + 1, _mm_set_epi32(c[1], c[0], b[2], b[1]));
-      _mm_stream_si128(d + 2, _mm_set_epi32(e[2], e[1], e[0], c[2]));
-    }
-  }
-#endif
-  for (; p < p_hi; p++) {
-    const int k = codes[p] < 27 ? codes[p] : 13;
-    S_out[3 * p] = (TI)(k % 3 - 1);
-    S_out[3 * p + 1] = (TI)((k / 3) % 3 - 1);
-    S_out[3 * p + 2] = (TI)(k / 9 - 1);
-  }
-#if defined(__SSE2__)
-  _mm_sfence();
-#endif
+inline void host_unpack_shifts(const uint8_t* codes, long long p_lo, long long p_hi, TI* S_out) {
+  nl_host::unpack_shifts(sizeof(TI) == 8, codes, p_lo, p_hi, S_out);
 }
 
 }  // namespace nl

@@ -1048,7 +1048,7 @@ void to_host_job_free(nl_to_host_job* J) {
 int to_host_begin(int int_type, const void* first, int64_t n_rows, int64_t P, int64_t i_from, void* first_host, void* i_host, int nthreads,
                   cudaStream_t st, nl_to_host_job** job_out) {
   *job_out = nullptr;
-  if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency());
+  if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency() / 2);  // memory-bound work: one thread per core pair
   nl_to_host_job* J = new (std::nothrow) nl_to_host_job();
   if (!J) return NL_ERR_BAD_ARG;
   J->int64 = int_type == NL_I64;

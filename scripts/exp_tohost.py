@@ -28,7 +28,7 @@ print("list (no R): %.2f ms" % timed(lambda: nl.neighbour_list(Xd, CUTOFF, C, pb
 pl = nl.neighbour_list(Xd, CUTOFF, C, pbc)
 P = nl.npairs(pl)
 buf = nl.HostPairBuffers(P + 1024, n)
-for nt in (8, 12, 16):
+for nt in (4, 6, 8, 10, 12, 16):
     print("to_host nthreads=%2d, fraction of i copied 0 / 0.2 / 0.3 / 0.4 / 0.5 / 1: " % nt +
           " ".join("%.2f" % timed(lambda: nl.to_host(pl, out=buf, nthreads=nt, i_copy_fraction=f)) for f in (0.0, 0.2, 0.3, 0.4, 0.5, 1.0)) + " ms")
 print("plain D2H j (%.2f GB): %.2f ms" % (4e-9 * P, timed(lambda: buf.j[:P].copy_(pl.j, non_blocking=True))))

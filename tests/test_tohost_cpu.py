@@ -67,3 +67,12 @@ def test_decoder_argument_checks():
     p = nl._lib.NlParams()
     p.int_type = 0
     assert L.nl_pairs_to_host(p, None, 3, None, 5, None, None, 5, None, None, None, None, None, None, 0, 0, None) == nl._lib.NL_ERR_BAD_ARG
+
+
+def test_decoders_sse2_path_in_a_subprocess():
+    """The AVX2 variants are picked at run time; NL_HOST_NO_AVX2=1 forces the SSE2 ones, which must give the same arrays."""
+    import os, subprocess, sys
+    env = dict(os.environ, NL_HOST_NO_AVX2="1")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-k", "expand_rows or unpack_shifts"], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
