@@ -19,6 +19,69 @@ namespace nl {
 #ifndef NL_F3_LIST2
 #define NL_F3_LIST2 0
 #endif
+#ifndef NL_F3_RDIRECT
+#define NL_F3_RDIRECT 0   // experiment, measured SLOWER (fill stage 6.29 ms against 4.84): see f3_row_plain_direct
+#endif
+
+// Byte offset of component c (0, 1, 2) of a staged record from sA + 16 * slot (layout of f2_store).
+template <class T> __device__ __forceinline__ int f3_comp_off(int c, int cap) {
+  if constexpr (sizeof(T) == 8) return c == 0 ? 0 : (c == 1 ? 8 : cap * 16);
+  else return 4 * c;
+}
+
+// One row, plain case, R WITHOUT the shared-memory transposition: the R row is 3 * nhit contiguous values, lane l of pass m
+// writes element e = l + 32 m = component e % 3 of hit e / 3, which it fetches itself (hit list -> slot -> one component of the
+// staged record).  Three independent passes per chunk, no staging stores, no warp barriers; e % 3 = (l % 3 + 2 m) % 3 is a
+// per-lane constant of each pass, so the home atom's components and the cell' * 0 terms are picked once per row.
+// MEASURED (-DNL_F3_RDIRECT=1, headline): parity green, but the fill stage takes 6.29 ms instead of 4.84: the three 8-byte fetches
+// per lane from random 16-byte slots cost more shared-memory wavefronts than the two 16-byte fetches + conflict-free transposition
+// of f3_row_plain.  Kept as a switch for the record; not the default.
+template <class T, class TI, bool HAS_R>
+__device__ __forceinline__ void f3_row_plain_direct(TI* __restrict__ jo, T* __restrict__ Ro, unsigned wofs, int q, T cz0, T cz1, T cz2, int lane, int nhit,
+                                                    long long base, int hs) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int CAP = f2_cap<T, TI>();
+  constexpr int WB = f2_warp_bytes<T, TI>();
+  constexpr int OFF_SA = 3 * TILE_VPAD * 4 + 64 * 4 + 64 * 4 * (int)sizeof(T) + F2_NW * WB;
+  const unsigned char* const sA = smem_raw + OFF_SA;
+  const int c0 = lane % 3;
+  T xim[3], czm[3];
+#pragma unroll
+  for (int m = 0; m < 3; m++) {
+    const int c = (c0 + 2 * m) % 3;
+    xim[m] = *(const T*)(sA + 16 * hs + f3_comp_off<T>(c, CAP));
+    czm[m] = c == 0 ? cz0 : (c == 1 ? cz1 : cz2);
+  }
+  TI* const jrow = jo + base + lane;
+  T* const Rrow = Ro + 3 * base + lane;
+#pragma unroll 1
+  for (int r0 = 0; r0 < nhit; r0 += 32) {
+    unsigned wo = wofs;
+    asm volatile("" : "+r"(wo));
+    const int nr = min(32, nhit - r0);
+    const uint8_t* const Lq = smem_raw + wo + 2 * MASK_MAXCAND + q * MASK_MAXCAND + r0;
+    const uint16_t* const tabp = (const uint16_t*)(smem_raw + wo);
+    if (lane < nr) {
+      const int slot = (int)(tabp[Lq[lane]] & 2047u);
+      const uint32_t jv = sizeof(T) == 8 ? *(const uint32_t*)(sA + CAP * 16 + 16 * slot + 8) : *(const uint32_t*)(sA + 16 * slot + 12);
+      jrow[r0] = (TI)jv + 1;
+    }
+    if (HAS_R) {
+      const int nw = 3 * nr;
+#pragma unroll
+      for (int m = 0; m < 3; m++) {
+        const int e = lane + 32 * m;
+        if (e < nw) {
+          const int h = (e * 171) >> 9;  // e / 3 for e < 96
+          const int slot = (int)(tabp[Lq[h]] & 2047u);
+          const int c = (c0 + 2 * m) % 3;
+          const T v = *(const T*)(sA + 16 * slot + f3_comp_off<T>(c, CAP));
+          Rrow[3 * r0 + 32 * m] = add_rn(sub_rn(v, xim[m]), czm[m]);
+        }
+      }
+    }
+  }
+}
 
 // One row, plain case: nhit hits of the home atom staged at slot hs; L = its hit list (flat candidate numbers), tab = flat
 // candidate -> staged slot.  j straight from the lane, R transposed through shared memory so that every store instruction
@@ -325,7 +388,11 @@ __global__ void __launch_bounds__(F2_NT, 2) k_fill3(const MaskArgs<T, TI> a, int
         if (nhit == 0) continue;
         const long long base = (long long)__shfl_sync(FULL, my_base, q * 8);
         const uint8_t* L = lists + q * MASK_MAXCAND;
+#if NL_F3_RDIRECT
+        if (plain) f3_row_plain_direct<T, TI, HAS_R>(a.out.jo, a.out.Ro, wofs, q, cz0, cz1, cz2, lane, nhit, base, hstart + a0 + q);
+#else
         if (plain) f3_row_plain<T, TI, HAS_R>(a.out.jo, a.out.Ro, wofs, q, cz0, cz1, cz2, lane, nhit, base, hstart + a0 + q);
+#endif
         else f3_row_general<T, TI, HAS_R>(a, sA, sB, tab, L, shc, cstab, bS, bR, fastcell, lane, nhit, base, hstart + a0 + q);
       }
     }
