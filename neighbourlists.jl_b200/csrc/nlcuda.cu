@@ -132,6 +132,7 @@ struct PairWs {
   void* stamp;           // what nl_count_pairs left in this workspace (WsStamp); nl_fill_pairs* check it
   size_t total_bytes;
 };
+inline int fill_variant();
 PairWs pair_ws(void* ws, const nl_params* prm, int64_t N) {
   PairWs w;
   char* p = (char*)ws;
@@ -155,8 +156,9 @@ PairWs pair_ws(void* ws, const nl_params* prm, int64_t N) {
   w.tsum = (unsigned long long*)take((size_t)(scan_tiles((long long)n1) + 1) * 8);
   w.total = (unsigned long long*)take(256);
   w.tiled = take(tiled_scratch_bytes(prm, N));
-  w.parkA = (unsigned char*)take(n1 * PARK_A_BYTES);
-  w.parkR = (unsigned char*)take(n1 * PARK_R_BYTES);
+  const size_t npark = fill_variant() == 2 ? n1 : 1;  // only the NL_FILL=park experiment uses the park records (192 B per atom)
+  w.parkA = (unsigned char*)take(npark * PARK_A_BYTES);
+  w.parkR = (unsigned char*)take(npark * PARK_R_BYTES);
   w.stamp = take(256);
   w.total_bytes = o;
   return w;
