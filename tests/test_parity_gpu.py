@@ -300,9 +300,12 @@ def test_near_threshold_decisions(nl, dtype):
     assert 0.2 < dimer < 0.8, dimer
 
 
-def test_original_order_fill_variant():
-    """The alternative fill kernel (k_fill_rows: original atom order, one thread per pair; selected with
-    NL_FILL_ROWS=1, read once per process) must produce the same lists.  Runs in a subprocess."""
+@pytest.mark.parametrize("switch", ["NL_FILL_ROWS=1", "NL_FILL=park", "NL_FILL=2", "NL_FILL=legacy", "NL_BUILD=radix", "NL_COUNT=legacy",
+                                    "NL_FILL_SZERO=0", "NL_FILL_PREFETCH=0"])
+def test_kernel_variants_behind_environment_switches(switch):
+    """The alternative kernels kept for A/B runs (environment switches: original-order fill k_fill_rows, the
+    boundary-parking fill, the lean in-place k_fill_park, round 1's k_fill_mask and k_count_mask, the radix-sort build, ...) are
+    selected by variables read once per process; each must produce the same lists.  Runs in a subprocess."""
     import os
     import subprocess
     import sys
@@ -319,10 +322,13 @@ for dtype, pbc, cell, N, rc in ((np.float64, (True, True, True), None, 20000, 5.
         X = U.displace_by_lattice(U.rand_in_cell(N, cell, seed=6, dtype=dtype), cell, pbc)
     pl = nl.neighbour_list(torch.from_numpy(X).cuda(), rc, cell.astype(dtype), pbc, with_R=True)
     orc = O.sortbased(X, rc, cell.astype(dtype), pbc, dtype=dtype)
-    U.assert_engine_matches_oracle(pl.cpu(), orc, 1e-12 if dtype == np.float64 else 1e-5, msg="fill_rows")
+    U.assert_engine_matches_oracle(pl.cpu(), orc, 1e-12 if dtype == np.float64 else 1e-5, msg="variant")
+    cl = nl.build_cell_list(torch.from_numpy(X).cuda(), rc, cell.astype(dtype), pbc)
+    assert np.array_equal(cl.perm.cpu().numpy(), orc["perm"]) and np.array_equal(cl.cell_offsets.cpu().numpy(), orc["cell_offsets"])
 print("OK")
 ''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, NL_FILL_ROWS="1")
+    name, value = switch.split("=")
+    env = dict(os.environ, **{name: value})
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
