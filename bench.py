@@ -387,7 +387,7 @@ def run_ours(args):
                        "stage_ms": {"count_stage": count_mean, "fill_kernel": fill_mean},
                        "step_roofline": {"bytes": step_bytes, "formula": "24 N + 48 P", "gbs": step_bytes / (ms_per_step * 1e-3) / 1e9,
                                          "frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak}},
-            "roofline": {"bound": "hbm", "kernel": "pair fill (nl_fill_pairs: k_fill_mask)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "pair fill (nl_fill_pairs: k_row_starts + k_expand_rows + k_fill3)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "traffic_profiled": fill_traffic_profiled(n_atoms, world), "peak_source": which,
                          "bytes_per_launch": fill_bytes, "formula": "44 P + 36 N"},
             "e2e": {"value": P_total / (e2e_ms * 1e-3), "unit": "pairs/s",
