@@ -26,7 +26,7 @@ namespace nl {
 #define NL_F2_OPAQUE 1
 #endif
 #ifndef NL_F2_NT
-#define NL_F2_NT 384
+#define NL_F2_NT 448   // 14 warps x 2 CTAs / SM at <= 72 registers: measured best for k_fill3 (fill stage 4.84 ms at 384, 4.65 at 448, 5.2 at 480)
 #endif
 constexpr int F2_NT = NL_F2_NT;
 constexpr int F2_NW = F2_NT / 32;
