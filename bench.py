@@ -290,8 +290,8 @@ def run_ours(args):
         else:
             pl = sharded.neighbour_list_sharded_native(X_host.to(dev, non_blocking=True), gidx_host.to(dev, non_blocking=True), CUTOFF, C, pbc,
                                                        comm, rank, world)
-        h = nl.to_host(pl, out=hbuf, nthreads=host_threads, rebuild_i=(world == 1))  # returns when every host array is complete
-        d2h_bytes[0] = nl.to_host_bytes(pl, rebuild_i=(world == 1))
+        h = nl.to_host(pl, out=hbuf, nthreads=host_threads)  # i rebuilt through the shard's row -> global index map; returns when complete
+        d2h_bytes[0] = nl.to_host_bytes(pl)
         return h
 
     e2e_warm, e2e_steps = 1, max(1, min(args.steps, 3))

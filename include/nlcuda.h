@@ -310,6 +310,9 @@ NL_API int nl_max_displacement2(int32_t float_type, const void* X, const void* X
  *                                [i_copy_from, P) are copied from the device array `i` (NULL allowed when i_copy_from == P).
  *                                Shard lists, whose i runs through an index map, pass 0.  A whole list may split i between
  *                                the host threads and the bus; i_copy_from == P was fastest where measured.
+ *   row_index       in   DEVICE  n_rows TI or NULL: the value i takes for the pairs of row r (a shard's rows carry GLOBAL atom
+ *                                indices: pass its index map and i_copy_from = P, and i never crosses the bus); NULL: r + 1.
+ *                                row_index_host: n_rows TI of host memory for its copy (pinned; may be NULL with row_index)
  *   *_host          out  HOST    n_rows + 1, P, P, 3 P elements of TI; pinned memory for full PCIe speed
  *   dev_scratch / host_scratch   nl_to_host_scratch_bytes(P) bytes each, 16-byte aligned; host_scratch pinned
  *   nthreads        host worker threads (<= 0: half the hardware concurrency -- the decoders are bound by memory bandwidth)
@@ -317,7 +320,7 @@ NL_API int nl_max_displacement2(int32_t float_type, const void* X, const void* X
  * NL_ERR_BAD_ARG if first[n_rows] - 1 != P.                                                                        */
 NL_API size_t nl_to_host_scratch_bytes(int64_t P);
 NL_API int nl_pairs_to_host(const nl_params* params, const void* first, int64_t n_rows, const void* i, int64_t i_copy_from,
-                            const void* j, const void* S, int64_t P, void* first_host, void* i_host, void* j_host, void* S_host,
+                            const void* row_index, void* row_index_host, const void* j, const void* S, int64_t P, void* first_host, void* i_host, void* j_host, void* S_host,
                             void* dev_scratch, void* host_scratch, size_t scratch_bytes, int32_t nthreads, void* stream);
 /* The same transfer in two steps, so that the `first` copy and the rebuild of i (a third of the host-side work) run WHILE the fill pass
  * is still on the GPU:
@@ -333,7 +336,8 @@ NL_API int nl_pairs_to_host_begin(const nl_params* params, const void* first, in
 NL_API int nl_pairs_to_host_finish(nl_to_host_job* job, const void* j, const void* S, void* j_host, void* S_host,
                                    void* dev_scratch, void* host_scratch, size_t scratch_bytes, void* stream);
 /* The two host-side decoders of that format on their own (pure host code, no CUDA call): pairs [p_lo, p_hi), 0-based.  */
-NL_API int nl_host_expand_rows(int32_t int_type, const void* first, int64_t n_rows, int64_t p_lo, int64_t p_hi, void* i_out);
+NL_API int nl_host_expand_rows(int32_t int_type, const void* first, const void* row_index, int64_t n_rows, int64_t p_lo, int64_t p_hi,
+                               void* i_out);   /* row_index: HOST n_rows TI or NULL */
 NL_API int nl_host_unpack_shifts(int32_t int_type, const uint8_t* codes, int64_t p_lo, int64_t p_hi, void* S_out);
 
 #ifdef __cplusplus

@@ -190,10 +190,10 @@ function to_host(nl::DevPairList{T,TI}; nthreads::Integer = Threads.nthreads(), 
     end
     whole = rows == length(nl.X)                       # a whole list: i[p] is the row of p; shard lists copy their global i
     GC.@preserve b _check(ccall((:nl_pairs_to_host, libnlcuda), Cint,
-                 (Ref{NlParams}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid},
-                  Ptr{Cvoid}, CuPtr{Cvoid}, Ptr{Cvoid}, Csize_t, Int32, Ptr{Cvoid}),
-                 _params(nl), nl.first, rows, nl.i, whole ? P : 0, nl.j, nl.S, P, b.first, b.i, b.j, b.S, b.dscratch, b.hscratch,
-                 length(b.hscratch), nthreads, _stream()))
+                 (Ref{NlParams}, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Int64, CuPtr{Cvoid}, Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, Ptr{Cvoid},
+                  Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, CuPtr{Cvoid}, Ptr{Cvoid}, Csize_t, Int32, Ptr{Cvoid}),
+                 _params(nl), nl.first, rows, nl.i, whole ? P : 0, CU_NULL, C_NULL, nl.j, nl.S, P, b.first, b.i, b.j, b.S, b.dscratch, b.hscratch,
+                 length(b.hscratch), nthreads, _stream()))     # shard lists: pass the row -> global index map instead (row_index), i_copy_from = P
     return PairList(Array(nl.X), nl.C, nl.cutoff, view(b.i, 1:P), view(b.j, 1:P), view(b.S, 1:P), view(b.first, 1:rows+1))
 end
 

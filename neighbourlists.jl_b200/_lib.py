@@ -137,13 +137,13 @@ def lib():
             getattr(L, n).restype = C.c_int
         L.nl_to_host_scratch_bytes.restype = sz
         L.nl_to_host_scratch_bytes.argtypes = [i64]
-        L.nl_pairs_to_host.argtypes = [pp, vp, i64, vp, i64, vp, vp, i64, vp, vp, vp, vp, vp, vp, sz, C.c_int32, vp]
+        L.nl_pairs_to_host.argtypes = [pp, vp, i64, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, sz, C.c_int32, vp]
         L.nl_pairs_to_host.restype = C.c_int
         L.nl_pairs_to_host_begin.argtypes = [pp, vp, i64, i64, vp, vp, C.c_int32, vp, C.POINTER(vp)]
         L.nl_pairs_to_host_begin.restype = C.c_int
         L.nl_pairs_to_host_finish.argtypes = [vp, vp, vp, vp, vp, vp, vp, sz, vp]
         L.nl_pairs_to_host_finish.restype = C.c_int
-        L.nl_host_expand_rows.argtypes = [C.c_int32, vp, i64, i64, i64, vp]
+        L.nl_host_expand_rows.argtypes = [C.c_int32, vp, vp, i64, i64, i64, vp]
         L.nl_host_expand_rows.restype = C.c_int
         L.nl_host_unpack_shifts.argtypes = [C.c_int32, vp, i64, i64, vp]
         L.nl_host_unpack_shifts.restype = C.c_int

@@ -309,6 +309,7 @@ class HostPairBuffers:
         self.device = torch.device(device if device is not None else "cuda")
         nb = _lib.lib().nl_to_host_scratch_bytes(self.pair_capacity)
         self.first = torch.empty(self.row_capacity + 1, dtype=it).pin_memory()
+        self.rows = torch.empty(max(self.row_capacity, 1), dtype=it).pin_memory()   # a shard's row -> global index map
         self.i = torch.empty(max(self.pair_capacity, 1), dtype=it).pin_memory()
         self.j = torch.empty(max(self.pair_capacity, 1), dtype=it).pin_memory()
         self.S = torch.empty((max(self.pair_capacity, 1), 3), dtype=it).pin_memory()
@@ -338,8 +339,8 @@ def to_host(nlist, out: Optional[HostPairBuffers] = None, nthreads: int = 0, reb
             i_copy_fraction: float = 0.0) -> HostPairList:
     """The whole list into host memory through nl_pairs_to_host (include/nlcuda.h): `first`, `j` and one byte per pair for S
     cross the bus; i and S are rebuilt by host threads of the library while the copies run.  Returns when every array is
-    complete.  `out`: buffers to reuse (default: a module-level set grown on demand).  rebuild_i=False copies i instead of
-    rebuilding it from `first` (needed for shard lists, whose i carries global indices; detected from the list's length);
+    complete.  `out`: buffers to reuse (default: a module-level set grown on demand).  i is rebuilt from `first` -- for a shard
+    list (sharded.ShardedPairList) through its row -> global index map, which is copied instead of i; rebuild_i=False copies i;
     otherwise the last i_copy_fraction of i is copied and the rest rebuilt (0 is fastest where measured: the host's memory
     bandwidth, which DMA writes and host stores share, is the bound, not the host threads' instruction rate)."""
     P = int(nlist.i.shape[0])
@@ -348,10 +349,13 @@ def to_host(nlist, out: Optional[HostPairBuffers] = None, nthreads: int = 0, reb
     dev = nlist.i.device
     out = _host_buffers_for(P, n_rows, it, dev, out)
     whole = isinstance(nlist, PairList) and n_rows == int(nlist.X.shape[0])   # a whole list: i[p] is the row of p
+    row_index = getattr(nlist, "owned_index", None)                          # sharded.ShardedPairList: i[p] = owned_index[row of p]
     if rebuild_i is None:
-        rebuild_i = whole
-    elif rebuild_i and not whole:
-        raise ValueError("rebuild_i needs a whole PairList: the i of a shard list carries global indices")
+        rebuild_i = whole or row_index is not None
+    elif rebuild_i and not (whole or row_index is not None):
+        raise ValueError("rebuild_i needs a whole PairList or a shard list with its row -> global index map")
+    if whole or not rebuild_i:
+        row_index = None
     params = getattr(nlist, "params", None)
     if params is None:   # sharded.ShardedPairList: only the integer type is read
         params = _lib.NlParams()
@@ -359,7 +363,8 @@ def to_host(nlist, out: Optional[HostPairBuffers] = None, nthreads: int = 0, reb
     S = nlist.S if nlist.S.is_contiguous() else nlist.S.contiguous()
     with torch.cuda.device(dev):
         i_from = _i_copy_from(P, rebuild_i, i_copy_fraction)
-        _lib.check(_lib.lib().nl_pairs_to_host(params, _ptr(nlist.first), n_rows, _ptr(nlist.i), i_from, _ptr(nlist.j),
+        _lib.check(_lib.lib().nl_pairs_to_host(params, _ptr(nlist.first), n_rows, _ptr(nlist.i), i_from, _ptr(row_index),
+                                               None if row_index is None else out.rows.data_ptr(), _ptr(nlist.j),
                                                _ptr(S), P, out.first.data_ptr(), out.i.data_ptr(), out.j.data_ptr(), out.S.data_ptr(),
                                                out.dev_scratch.data_ptr(), out.host_scratch.data_ptr(), out.dev_scratch.numel(),
                                                int(nthreads), _stream(dev)))
@@ -380,7 +385,9 @@ def to_host_bytes(nlist, rebuild_i: bool = True, i_copy_fraction: float = 0.0) -
     """Bytes nl_pairs_to_host moves over the bus for this list (when no shift component escapes the one-byte code)."""
     P = int(nlist.i.shape[0])
     w = nlist.i.element_size()
-    return (int(nlist.first.shape[0])) * w + P * w + P + 4 + (P - _i_copy_from(P, rebuild_i, i_copy_fraction)) * w
+    rows = int(nlist.first.shape[0]) - 1
+    rowmap = rows * w if (rebuild_i and getattr(nlist, "owned_index", None) is not None) else 0
+    return (rows + 1) * w + rowmap + P * w + P + 4 + (P - _i_copy_from(P, rebuild_i, i_copy_fraction)) * w
 
 # ------------------------------------------------------------------ accessors (src/cell_list.jl:25-27, 507-611, 753-833, 919-927)
 def npairs(nlist: PairList) -> int:

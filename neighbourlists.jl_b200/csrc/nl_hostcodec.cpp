@@ -15,11 +15,14 @@
 namespace nl_host {
 
 // ------------------------------------------------------------------------------------------------ generic (any TI)
+// value written for the pairs of row r: r + 1, or map[r] (shard lists: the row's GLOBAL atom index)
+template <class TI> static inline TI row_value(const TI* map, long long r) { return map ? map[r] : (TI)(r + 1); }
+
 template <class TI>
-static void expand_scalar(const TI* first, long long n_rows, long long p, long long p_hi, long long& r, long long& e, TI* out) {
+static void expand_scalar(const TI* first, const TI* map, long long n_rows, long long p, long long p_hi, long long& r, long long& e, TI* out) {
   for (; p < p_hi; p++) {
     while (e <= p) { r++; e = (long long)first[r + 1] - 1; }
-    out[p] = (TI)(r + 1);
+    out[p] = row_value<TI>(map, r);
   }
 }
 
@@ -40,15 +43,15 @@ static void locate(const TI* first, long long n_rows, long long p, long long& r,
 // 32-bit indices, groups of 4 (SSE2) / 8 (AVX2) pairs on aligned addresses.  Whole groups inside a row are one broadcast store; a
 // group in which exactly ONE row ends is emitted without a per-element loop (lanes at or after the row end get r + 2, the others
 // r + 1); groups with two or more row ends (rows shorter than the group, empty rows) take the element-wise path.
-__attribute__((target("avx2"))) static void expand_avx2(const int32_t* first, long long n_rows, long long p, long long p_hi, long long& r_io,
-                                                         long long& e_io, int32_t* out) {
+__attribute__((target("avx2"))) static void expand_avx2(const int32_t* first, const int32_t* map, long long n_rows, long long p, long long p_hi,
+                                                         long long& r_io, long long& e_io, int32_t* out) {
   const __m256i iota = _mm256_set_epi32(7, 6, 5, 4, 3, 2, 1, 0);
   long long r = r_io, e = e_io;
   while (p + 8 <= p_hi) {
     while (e <= p) { r++; e = (long long)first[r + 1] - 1; }
     long long d = e - p;                                               // > 0: pairs of row r left from p on
     if (d >= 8) {                                                      // the whole group inside row r: run to the last full group of the row
-      const __m256i v = _mm256_set1_epi32((int)(r + 1));
+      const __m256i v = _mm256_set1_epi32((int)row_value<int32_t>(map, r));
       const long long stop = (e < p_hi ? e : p_hi) - 7;
       for (; p < stop; p += 8) _mm256_stream_si256((__m256i*)(out + p), v);
       continue;
@@ -59,14 +62,15 @@ __attribute__((target("avx2"))) static void expand_avx2(const int32_t* first, lo
       alignas(32) int32_t t[8];
       for (int k = 0; k < 8; k++) {
         while (e <= p + k) { r++; e = (long long)first[r + 1] - 1; }
-        t[k] = (int32_t)(r + 1);
+        t[k] = row_value<int32_t>(map, r);
       }
       _mm256_stream_si256((__m256i*)(out + p), _mm256_load_si256((const __m256i*)t));
       p += 8;
       continue;
     }
     const __m256i past = _mm256_cmpgt_epi32(iota, _mm256_set1_epi32((int)d - 1));   // lanes k >= d belong to row r + 1
-    _mm256_stream_si256((__m256i*)(out + p), _mm256_sub_epi32(_mm256_set1_epi32((int)(r + 1)), past));
+    _mm256_stream_si256((__m256i*)(out + p), _mm256_blendv_epi8(_mm256_set1_epi32((int)row_value<int32_t>(map, r)),
+                                                                 _mm256_set1_epi32((int)row_value<int32_t>(map, r + 1)), past));
     r++; e = e2;
     p += 8;
   }
@@ -81,7 +85,7 @@ static bool have_avx2() {
 #endif
 
 template <class TI>
-static void expand_rows_t(const TI* first, long long n_rows, long long p_lo, long long p_hi, TI* out) {
+static void expand_rows_t(const TI* first, const TI* map, long long n_rows, long long p_lo, long long p_hi, TI* out) {
   if (p_hi <= p_lo) return;
   long long r, e;
   locate<TI>(first, n_rows, p_lo, r, e);
@@ -93,21 +97,22 @@ static void expand_rows_t(const TI* first, long long n_rows, long long p_lo, lon
     // head up to the first aligned group
     long long head = p;
     while (head < p_hi && (((uintptr_t)(out + head)) & (uintptr_t)(4 * G - 1))) head++;
-    expand_scalar<TI>(first, n_rows, p, head, r, e, out);
+    expand_scalar<TI>(first, map, n_rows, p, head, r, e, out);
     p = head;
     const long long body = p + ((p_hi - p) / G) * G;
     if (body > p) {
-      if (avx2) expand_avx2((const int32_t*)first, n_rows, p, body, r, e, (int32_t*)out);
+      if (avx2) expand_avx2((const int32_t*)first, (const int32_t*)map, n_rows, p, body, r, e, (int32_t*)out);
       else {
         // SSE2: same scheme with groups of 4 (kept simple: run loop + boundary groups)
         const int32_t* f32 = (const int32_t*)first;
+        const int32_t* m32 = (const int32_t*)map;
         int32_t* o32 = (int32_t*)out;
         const __m128i iota = _mm_set_epi32(3, 2, 1, 0);
         while (p + 4 <= body) {
           while (e <= p) { r++; e = (long long)f32[r + 1] - 1; }
           const long long d = e - p;
           if (d >= 4) {
-            const __m128i v = _mm_set1_epi32((int)(r + 1));
+            const __m128i v = _mm_set1_epi32((int)row_value<int32_t>(m32, r));
             const long long stop = (e < body ? e : body) - 3;
             for (; p < stop; p += 4) _mm_stream_si128((__m128i*)(o32 + p), v);
             continue;
@@ -117,14 +122,15 @@ static void expand_rows_t(const TI* first, long long n_rows, long long p_lo, lon
             alignas(16) int32_t t[4];
             for (int k = 0; k < 4; k++) {
               while (e <= p + k) { r++; e = (long long)f32[r + 1] - 1; }
-              t[k] = (int32_t)(r + 1);
+              t[k] = row_value<int32_t>(m32, r);
             }
             _mm_stream_si128((__m128i*)(o32 + p), _mm_load_si128((const __m128i*)t));
             p += 4;
             continue;
           }
-          const __m128i past = _mm_cmpgt_epi32(iota, _mm_set1_epi32((int)d - 1));
-          _mm_stream_si128((__m128i*)(o32 + p), _mm_sub_epi32(_mm_set1_epi32((int)(r + 1)), past));
+          const __m128i past = _mm_cmpgt_epi32(iota, _mm_set1_epi32((int)d - 1));   // SSE2 has no blend: (a & ~m) | (b & m)
+          const __m128i va = _mm_set1_epi32((int)row_value<int32_t>(m32, r)), vb = _mm_set1_epi32((int)row_value<int32_t>(m32, r + 1));
+          _mm_stream_si128((__m128i*)(o32 + p), _mm_or_si128(_mm_andnot_si128(past, va), _mm_and_si128(past, vb)));
           r++; e = e2;
           p += 4;
         }
@@ -134,7 +140,7 @@ static void expand_rows_t(const TI* first, long long n_rows, long long p_lo, lon
     }
   }
 #endif
-  expand_scalar<TI>(first, n_rows, p, p_hi, r, e, out);
+  expand_scalar<TI>(first, map, n_rows, p, p_hi, r, e, out);
 #if NL_X86
   _mm_sfence();
 #endif
@@ -190,9 +196,9 @@ static void unpack_shifts_t(const uint8_t* codes, long long p_lo, long long p_hi
 }
 
 // ------------------------------------------------------------------------------------------------ entry points for nlcuda.cu
-void expand_rows(int int64, const void* first, long long n_rows, long long p_lo, long long p_hi, void* i_out) {
-  if (int64) expand_rows_t<int64_t>((const int64_t*)first, n_rows, p_lo, p_hi, (int64_t*)i_out);
-  else expand_rows_t<int32_t>((const int32_t*)first, n_rows, p_lo, p_hi, (int32_t*)i_out);
+void expand_rows(int int64, const void* first, const void* row_map, long long n_rows, long long p_lo, long long p_hi, void* i_out) {
+  if (int64) expand_rows_t<int64_t>((const int64_t*)first, (const int64_t*)row_map, n_rows, p_lo, p_hi, (int64_t*)i_out);
+  else expand_rows_t<int32_t>((const int32_t*)first, (const int32_t*)row_map, n_rows, p_lo, p_hi, (int32_t*)i_out);
 }
 void unpack_shifts(int int64, const uint8_t* codes, long long p_lo, long long p_hi, void* S_out) {
   if (int64) unpack_shifts_t<int64_t>(codes, p_lo, p_hi, (int64_t*)S_out);

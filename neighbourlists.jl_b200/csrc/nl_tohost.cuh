@@ -65,14 +65,14 @@ __global__ void __launch_bounds__(256) k_pack_shifts(const TI* __restrict__ S, l
 // The decoders live in nl_hostcodec.cpp (plain C++, AVX2 variants picked at run time).
 }  // namespace nl
 namespace nl_host {
-void expand_rows(int int64, const void* first, long long n_rows, long long p_lo, long long p_hi, void* i_out);
+void expand_rows(int int64, const void* first, const void* row_map, long long n_rows, long long p_lo, long long p_hi, void* i_out);
 void unpack_shifts(int int64, const uint8_t* codes, long long p_lo, long long p_hi, void* S_out);
 }  // namespace nl_host
 namespace nl {
-// i[p] = r + 1 for first[r] - 1 <= p < first[r + 1] - 1 (first is 1-based), for p in [p_lo, p_hi)
+// i[p] = r + 1 (or row_map[r]) for first[r] - 1 <= p < first[r + 1] - 1 (first is 1-based), for p in [p_lo, p_hi)
 template <class TI>
-inline void host_expand_rows(const TI* first, long long n_rows, long long p_lo, long long p_hi, TI* i_out) {
-  nl_host::expand_rows(sizeof(TI) == 8, first, n_rows, p_lo, p_hi, i_out);
+inline void host_expand_rows(const TI* first, const TI* row_map, long long n_rows, long long p_lo, long long p_hi, TI* i_out) {
+  nl_host::expand_rows(sizeof(TI) == 8, first, row_map, n_rows, p_lo, p_hi, i_out);
 }
 // S[p] = decode(codes[p]) for p in [p_lo, p_hi)
 template <class TI>

@@ -971,6 +971,7 @@ struct nl_to_host_job {
   int int64 = 0;
   int64_t n_rows = 0, P = 0, i_from = 0;
   const void* first_h = nullptr;
+  const void* rowmap_h = nullptr;   // shard lists: global index per row (host copy), else null
   void* i_h = nullptr;
   cudaStream_t aux = nullptr;
   cudaEvent_t ev_first = nullptr;
@@ -1013,7 +1014,7 @@ void to_host_worker(nl_to_host_job* J, int t) {
     const int k = J->next_i.fetch_add(1, std::memory_order_relaxed);
     if (k >= J->n_islices) return false;
     const int64_t a = std::min<int64_t>(J->i_from, J->islice * k), b = std::min<int64_t>(J->i_from, J->islice * (k + 1));
-    host_expand_rows<TI>((const TI*)J->first_h, (long long)J->n_rows, a, b, (TI*)J->i_h);
+    host_expand_rows<TI>((const TI*)J->first_h, (const TI*)J->rowmap_h, (long long)J->n_rows, a, b, (TI*)J->i_h);
     return true;
   };
   auto take_s = [&]() {
@@ -1047,14 +1048,15 @@ void to_host_job_free(nl_to_host_job* J) {
 }
 
 // `first` must be final in stream order of `st` at the time of the call (after nl_count_pairs it is: that call synchronises)
-int to_host_begin(int int_type, const void* first, int64_t n_rows, int64_t P, int64_t i_from, void* first_host, void* i_host, int nthreads,
-                  cudaStream_t st, nl_to_host_job** job_out) {
+int to_host_begin(int int_type, const void* first, int64_t n_rows, int64_t P, int64_t i_from, const void* row_index, void* row_index_host,
+                  void* first_host, void* i_host, int nthreads, cudaStream_t st, nl_to_host_job** job_out) {
   *job_out = nullptr;
   if (nthreads <= 0) nthreads = (int)std::max(1u, std::thread::hardware_concurrency() / 2);  // memory-bound work: one thread per core pair
   nl_to_host_job* J = new (std::nothrow) nl_to_host_job();
   if (!J) return NL_ERR_BAD_ARG;
   J->int64 = int_type == NL_I64;
   J->n_rows = n_rows; J->P = P; J->i_from = i_from; J->first_h = first_host; J->i_h = i_host;
+  J->rowmap_h = row_index ? row_index_host : nullptr;
   J->T = P > 0 ? std::max(1, std::min<int>(nthreads, 256)) : 0;
   J->n_islices = i_from > 0 ? (int)std::min<int64_t>(4 * J->T, (i_from + 65535) / 65536) : 0;
   J->islice = J->n_islices ? ((i_from + J->n_islices - 1) / J->n_islices + 63) & ~(int64_t)63 : 0;
@@ -1067,6 +1069,7 @@ int to_host_begin(int int_type, const void* first, int64_t n_rows, int64_t P, in
   if (ce == cudaSuccess) ce = cudaEventRecord(ev_in, st);           // whatever produced `first` on the caller's stream comes first
   if (ce == cudaSuccess) ce = cudaStreamWaitEvent(J->aux, ev_in, 0);
   if (ce == cudaSuccess) ce = cudaMemcpyAsync(first_host, first, (size_t)(n_rows + 1) * w, cudaMemcpyDeviceToHost, J->aux);
+  if (ce == cudaSuccess && row_index && n_rows > 0) ce = cudaMemcpyAsync(row_index_host, row_index, (size_t)n_rows * w, cudaMemcpyDeviceToHost, J->aux);
   if (ce == cudaSuccess) ce = cudaEventRecord(J->ev_first, J->aux);
   if (ev_in) cudaEventDestroy(ev_in);
   if (ce != cudaSuccess) {
@@ -1527,20 +1530,21 @@ int nl_max_displacement2(int32_t float_type, const void* X, const void* X_ref, i
 
 size_t nl_to_host_scratch_bytes(int64_t P) { return al256((size_t)(P > 0 ? P : 0)) + 256; }
 
-int nl_pairs_to_host(const nl_params* params, const void* first, int64_t n_rows, const void* i, int64_t i_copy_from, const void* j, const void* S,
-                     int64_t P, void* first_host, void* i_host, void* j_host, void* S_host, void* dev_scratch, void* host_scratch, size_t scratch_bytes,
-                     int32_t nthreads, void* stream) {
+int nl_pairs_to_host(const nl_params* params, const void* first, int64_t n_rows, const void* i, int64_t i_copy_from, const void* row_index,
+                     void* row_index_host, const void* j, const void* S, int64_t P, void* first_host, void* i_host, void* j_host, void* S_host,
+                     void* dev_scratch, void* host_scratch, size_t scratch_bytes, int32_t nthreads, void* stream) {
   if (!params || (params->int_type != NL_I32 && params->int_type != NL_I64)) return NL_ERR_BAD_ARG;
   if (n_rows < 0 || P < 0 || !first || !first_host) return NL_ERR_BAD_ARG;
   if (P > 0 && (!j || !S || !i_host || !j_host || !S_host)) return NL_ERR_BAD_ARG;
   if (i_copy_from < 0 || i_copy_from > P || (i_copy_from < P && !i)) return NL_ERR_BAD_ARG;
+  if (row_index && !row_index_host) return NL_ERR_BAD_ARG;
   if (i_copy_from < P) i_copy_from &= ~(int64_t)63;  // the two parts of i meet on a 256-byte boundary
   if (P > 0) {
     if (!dev_scratch || !host_scratch || scratch_bytes < nl_to_host_scratch_bytes(P)) return NL_ERR_WORKSPACE;
     if ((((uintptr_t)dev_scratch) | ((uintptr_t)host_scratch)) & 15) return NL_ERR_WORKSPACE;
   }
   nl_to_host_job* job = nullptr;
-  int rc = to_host_begin(params->int_type, first, n_rows, P, i_copy_from, first_host, i_host, nthreads, (cudaStream_t)stream, &job);
+  int rc = to_host_begin(params->int_type, first, n_rows, P, i_copy_from, row_index, row_index_host, first_host, i_host, nthreads, (cudaStream_t)stream, &job);
   if (rc) return rc;
   return to_host_finish(job, i, j, S, j_host, S_host, dev_scratch, host_scratch, scratch_bytes, (cudaStream_t)stream);
 }
@@ -1549,7 +1553,7 @@ int nl_pairs_to_host_begin(const nl_params* params, const void* first, int64_t n
                            int32_t nthreads, void* stream, nl_to_host_job** job_out) {
   if (!params || (params->int_type != NL_I32 && params->int_type != NL_I64)) return NL_ERR_BAD_ARG;
   if (!job_out || n_rows < 0 || P < 0 || !first || !first_host || (P > 0 && !i_host)) return NL_ERR_BAD_ARG;
-  return to_host_begin(params->int_type, first, n_rows, P, P, first_host, i_host, nthreads, (cudaStream_t)stream, job_out);
+  return to_host_begin(params->int_type, first, n_rows, P, P, nullptr, nullptr, first_host, i_host, nthreads, (cudaStream_t)stream, job_out);
 }
 
 int nl_pairs_to_host_finish(nl_to_host_job* job, const void* j, const void* S, void* j_host, void* S_host, void* dev_scratch,
@@ -1558,16 +1562,16 @@ int nl_pairs_to_host_finish(nl_to_host_job* job, const void* j, const void* S, v
   return to_host_finish(job, nullptr, j, S, j_host, S_host, dev_scratch, host_scratch, scratch_bytes, (cudaStream_t)stream);
 }
 
-int nl_host_expand_rows(int32_t int_type, const void* first, int64_t n_rows, int64_t p_lo, int64_t p_hi, void* i_out) {
+int nl_host_expand_rows(int32_t int_type, const void* first, const void* row_index, int64_t n_rows, int64_t p_lo, int64_t p_hi, void* i_out) {
   if ((int_type != NL_I32 && int_type != NL_I64) || n_rows < 0 || p_lo < 0 || p_hi < p_lo) return NL_ERR_BAD_ARG;
   if (p_hi == p_lo) return NL_OK;
   if (!first || !i_out || n_rows == 0) return NL_ERR_BAD_ARG;
   if (int_type == NL_I64) {
     if (p_hi > ((const int64_t*)first)[n_rows] - 1) return NL_ERR_BAD_ARG;
-    host_expand_rows<int64_t>((const int64_t*)first, n_rows, p_lo, p_hi, (int64_t*)i_out);
+    host_expand_rows<int64_t>((const int64_t*)first, (const int64_t*)row_index, n_rows, p_lo, p_hi, (int64_t*)i_out);
   } else {
     if (p_hi > (int64_t)((const int32_t*)first)[n_rows] - 1) return NL_ERR_BAD_ARG;
-    host_expand_rows<int32_t>((const int32_t*)first, n_rows, p_lo, p_hi, (int32_t*)i_out);
+    host_expand_rows<int32_t>((const int32_t*)first, (const int32_t*)row_index, n_rows, p_lo, p_hi, (int32_t*)i_out);
   }
   return NL_OK;
 }

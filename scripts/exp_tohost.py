@@ -43,7 +43,7 @@ for nt in (1, 4, 8, 16):
         t0 = time.perf_counter()
         [t.start() for t in th]; [t.join() for t in th]
         return 1e3 * (time.perf_counter() - t0)
-    te = min(run(lambda a, b: Lb.nl_host_expand_rows(0, first.ctypes.data, n, a, b, buf.i.data_ptr())) for _ in range(3))
+    te = min(run(lambda a, b: Lb.nl_host_expand_rows(0, first.ctypes.data, None, n, a, b, buf.i.data_ptr())) for _ in range(3))
     tu = min(run(lambda a, b: Lb.nl_host_unpack_shifts(0, codes.ctypes.data, a, b, buf.S.data_ptr())) for _ in range(3))
     print("host decoders, %2d threads: expand i %.2f ms (%.1f GB/s)  unpack S %.2f ms (%.1f GB/s)" % (nt, te, 4e-6 * P / te, tu, 12e-6 * P / tu))
 # memset-like upper bound of host stores

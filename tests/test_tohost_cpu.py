@@ -25,9 +25,15 @@ def test_expand_rows_matches_repeat(it, code):
         hi = int(rng.integers(lo, P + 1))
         if trial % 5 == 0:
             lo, hi = 0, P
-        assert L.nl_host_expand_rows(code, first.ctypes.data, n, lo, hi, out.ctypes.data) == 0
+        assert L.nl_host_expand_rows(code, first.ctypes.data, None, n, lo, hi, out.ctypes.data) == 0
         assert np.array_equal(out[lo:hi], ref[lo:hi])
         assert (buf[:off + lo] == -7).all() and (buf[off + hi:] == -7).all()   # nothing outside the range is touched
+        # through a row -> global index map (shard lists)
+        gmap = rng.integers(1, 10**6, n).astype(it)
+        buf[:] = -7
+        assert L.nl_host_expand_rows(code, first.ctypes.data, gmap.ctypes.data, n, lo, hi, out.ctypes.data) == 0
+        assert np.array_equal(out[lo:hi], np.repeat(gmap, cnt)[lo:hi])
+        assert (buf[:off + lo] == -7).all() and (buf[off + hi:] == -7).all()
 
 
 @pytest.mark.parametrize("it,code", [(np.int32, 0), (np.int64, 1)])
@@ -57,16 +63,16 @@ def test_decoder_argument_checks():
     L = nl._lib.lib()
     first = np.array([1, 3, 3, 6], dtype=np.int32)
     out = np.zeros(5, dtype=np.int32)
-    assert L.nl_host_expand_rows(0, first.ctypes.data, 3, 0, 6, out.ctypes.data) == nl._lib.NL_ERR_BAD_ARG   # beyond first[n_rows] - 1
-    assert L.nl_host_expand_rows(2, first.ctypes.data, 3, 0, 5, out.ctypes.data) == nl._lib.NL_ERR_BAD_ARG   # bad int_type
-    assert L.nl_host_expand_rows(0, None, 3, 0, 5, out.ctypes.data) == nl._lib.NL_ERR_BAD_ARG
-    assert L.nl_host_expand_rows(0, first.ctypes.data, 3, 2, 2, None) == 0                                     # empty range
+    assert L.nl_host_expand_rows(0, first.ctypes.data, None, 3, 0, 6, out.ctypes.data) == nl._lib.NL_ERR_BAD_ARG   # beyond first[n_rows] - 1
+    assert L.nl_host_expand_rows(2, first.ctypes.data, None, 3, 0, 5, out.ctypes.data) == nl._lib.NL_ERR_BAD_ARG   # bad int_type
+    assert L.nl_host_expand_rows(0, None, None, 3, 0, 5, out.ctypes.data) == nl._lib.NL_ERR_BAD_ARG
+    assert L.nl_host_expand_rows(0, first.ctypes.data, None, 3, 2, 2, None) == 0                                     # empty range
     assert L.nl_host_unpack_shifts(0, None, 0, 4, out.ctypes.data) == nl._lib.NL_ERR_BAD_ARG
     assert L.nl_to_host_scratch_bytes(0) >= 256 and L.nl_to_host_scratch_bytes(1000) >= 1000 + 4
     # the whole-list entry point validates before touching CUDA
     p = nl._lib.NlParams()
     p.int_type = 0
-    assert L.nl_pairs_to_host(p, None, 3, None, 5, None, None, 5, None, None, None, None, None, None, 0, 0, None) == nl._lib.NL_ERR_BAD_ARG
+    assert L.nl_pairs_to_host(p, None, 3, None, 5, None, None, None, None, 5, None, None, None, None, None, None, 0, 0, None) == nl._lib.NL_ERR_BAD_ARG
 
 
 def test_decoders_sse2_path_in_a_subprocess():
