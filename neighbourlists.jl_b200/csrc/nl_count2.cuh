@@ -22,6 +22,24 @@ namespace nl {
 #define NL_C2_MINB 4
 #endif
 
+// Half lists (NL_FLAG_HALF; half_keep in nl_traverse.cuh): of every mirror couple keep the pair whose second atom comes later in
+// cell-sorted order; self images keep the lexicographically positive shift.  For one chunk of 32 candidates (lane = candidate:
+// d = its sorted index minus that of the group's first home atom, shp = packed loop shift of its stencil cell) returns, in lane
+// aa < ng, the word of candidates home atom aa keeps: a candidate later than the whole group is kept by every home atom, an
+// earlier one by none, candidates INSIDE the group are settled one by one.
+__device__ __forceinline__ unsigned c2_half_word(bool valid, int d, int shp, int ng, int lane) {
+  const int pos = ((shp & 3) > 1 || ((shp & 3) == 1 && (((shp >> 2) & 3) > 1 || (((shp >> 2) & 3) == 1 && ((shp >> 4) & 3) > 1)))) ? 1 : 0;
+  unsigned word = __ballot_sync(FULL, valid && d >= ng);
+  unsigned ingrp = __ballot_sync(FULL, valid && d >= 0 && d < ng);
+  while (ingrp) {
+    const int l = __ffs(ingrp) - 1;
+    ingrp &= ingrp - 1;
+    const int dl = __shfl_sync(FULL, d, l), pl = __shfl_sync(FULL, pos, l);
+    if (dl > lane || (dl == lane && pl)) word |= 1u << l;
+  }
+  return word;
+}
+
 // Rare path, one whole home cell (deferred to the end of the tile, so that the hot loop never makes a call): the same table,
 // the same chunk order, every decision recomputed with the scalar chain (bit-identical to the packed one) and re-taken with
 // the exact Float64 contract wherever the pre-filter cannot be trusted (band, flagged slots).  Overwrites what the fast
@@ -77,6 +95,11 @@ __device__ __noinline__ void c2_cell_slow(const MaskArgs<double, TI>* ad, const 
         const unsigned bal = __ballot_sync(FULL, hit);
         if (lane == 0) mkT[kc * 34 + aa] = bal;
       }
+      if (ad->out.half) {  // half list: the rule of c2_half_word, applied to this chunk's words
+        __syncwarp();
+        const unsigned word = c2_half_word(valid, valid ? gj - (int)(hg0 + g0) : -1, shp, ng, lane);
+        if (lane < ng) mkT[kc * 34 + lane] &= word;
+      }
     }
     __syncwarp();
     if (lane < ng) {
@@ -103,8 +126,11 @@ __device__ __noinline__ void c2_cell_slow(const MaskArgs<double, TI>* ad, const 
 
 // One home cell with NCH chunks of candidates (NCH = ceil(ncand / 32) exactly).  Returns true if some decision of the cell
 // could not be trusted (band, flagged slot): the caller queues the cell for c2_cell_slow.
-template <class TI, int NCH>
-__device__ __forceinline__ bool c2_cell(const MaskArgs<double, TI>& a, unsigned wofs, int lane, int hstart, int nh, long long hg0, int ncand, int fh) {
+template <class TI, int NCH, bool HALF>
+__device__ __forceinline__ bool c2_cell(const MaskArgs<double, TI>& a, unsigned wofs, int lane, int hstart, int nh, long long hg0, int ncand, int fh,
+                                        int hbase, int hsh) {
+  // HALF: the table entries carry the stencil cell in their upper 5 bits; lane c < 27 holds, for stencil cell c, hbase = sorted index
+  // of its first atom minus its first slot minus hg0 (so hbase + slot = sorted index relative to the home cell) and hsh = its loop shift
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int TABCAP = cm_tabcap(CM_MASK);
   constexpr int OFF_SQ = 3 * TILE_VPAD * 4 + 64 * 4 + (TILE_NT / 32) * cm_warp_bytes(CM_MASK);
@@ -118,14 +144,20 @@ __device__ __forceinline__ bool c2_cell(const MaskArgs<double, TI>& a, unsigned 
   const float mid = a.mid, hw = a.hw;
   const float2 nmid2 = make_float2(-mid, -mid);
   float qx[NCH], qy[NCH], qz[NCH];
+  int hd[HALF ? NCH : 1], hshp[HALF ? NCH : 1];  // half lists: sorted index of the candidate relative to the home cell's first atom, loop shift
   unsigned badm = 0;
 #pragma unroll
   for (int k = 0; k < NCH; k++) {
     const int f = k * 32 + lane;
     float4 q = make_float4(CAND_FAR, CAND_FAR, CAND_FAR, 0.f);
-    if (f < ncand) q = sq[cslot[f]];
+    const unsigned cs = f < ncand ? (unsigned)cslot[f] : 0u;
+    if (f < ncand) q = sq[HALF ? (cs & 2047u) : cs];
     qx[k] = q.x; qy[k] = q.y; qz[k] = q.z;
     if (q.w != 0.f) badm |= 1u << k;
+    if constexpr (HALF) {
+      hd[k] = __shfl_sync(FULL, hbase, (int)(cs >> 11)) + (int)(cs & 2047u);
+      hshp[k] = __shfl_sync(FULL, hsh, (int)(cs >> 11));
+    }
   }
   bool rare = badm != 0;
 
@@ -165,6 +197,15 @@ __device__ __forceinline__ bool c2_cell(const MaskArgs<double, TI>& a, unsigned 
     }
     __syncwarp();
     rare = rare || bmin <= hw || my_bad;
+    if constexpr (HALF) {
+#pragma unroll
+      for (int k = 0; k < NCH; k++) {
+        const bool valid = k * 32 + lane < ncand;
+        const unsigned word = c2_half_word(valid, valid ? hd[k] - g0 : -1, hshp[k], ng, lane);
+        if (lane < ng) mkT[k * 34 + lane] &= word;
+      }
+      __syncwarp();
+    }
     // ---- drop the self pair (same atom, zero shift): flat index fh + g0 + aa of home atom aa
     if (lane < ng) {
       const int fs = fh + g0 + lane;
@@ -190,7 +231,7 @@ __device__ __forceinline__ bool c2_cell(const MaskArgs<double, TI>& a, unsigned 
   return __any_sync(FULL, rare);
 }
 
-template <class TI>
+template <class TI, bool HALF>
 __global__ void __launch_bounds__(TILE_NT, NL_C2_MINB) k_count_mask2(const MaskArgs<double, TI> a) {
   typedef double T;
   constexpr int TABCAP = cm_tabcap(CM_MASK);
@@ -288,6 +329,8 @@ __global__ void __launch_bounds__(TILE_NT, NL_C2_MINB) k_count_mask2(const MaskA
     const long long hg0 = vgs[vh];
     // candidate table: flat candidate -> staged slot (lane c < 27 owns stencil cell c); fh = flat index of home atom 0
     int ncand, fh;
+    int hbase = 0, hsh = 0;
+    static_assert(cm_cap(CM_MASK) <= 2048, "staged slots must fit 11 bits beside the stencil-cell tag");
     {
       int st = 0, cn = 0;
       int l2 = lane;
@@ -298,6 +341,7 @@ __global__ void __launch_bounds__(TILE_NT, NL_C2_MINB) k_count_mask2(const MaskA
         const int v = ((lz + l2 / 9) * VY + (ly + (l2 / 3) % 3)) * VX + (lx + l2 % 3);
         st = vstart[v];
         cn = vstart[v + 1] - st;
+        if constexpr (HALF) { hbase = vgs[v] - st - (int)hg0; hsh = vsh[v]; }
       }
       const int incl = warp_incl_scan(cn, l2);
       ncand = __shfl_sync(FULL, incl, 31);
@@ -305,8 +349,9 @@ __global__ void __launch_bounds__(TILE_NT, NL_C2_MINB) k_count_mask2(const MaskA
       if (ncand <= TABCAP) {
         const int pre = incl - cn;
         const int mx = __reduce_max_sync(FULL, cn);
+        const unsigned tag = HALF ? (unsigned)l2 << 11 : 0u;   // half lists: stencil cell of the candidate in the upper 5 bits
         for (int j = 0; j < mx; j++)
-          if (j < cn) cs[pre + j] = (uint16_t)(st + j);
+          if (j < cn) cs[pre + j] = (uint16_t)(tag | (unsigned)(st + j));
       }
       __syncwarp();
     }
@@ -317,14 +362,14 @@ __global__ void __launch_bounds__(TILE_NT, NL_C2_MINB) k_count_mask2(const MaskA
     }
     bool rare;
     switch ((ncand + 31) >> 5) {
-      case 1: rare = c2_cell<TI, 1>(a, wofs, lane, hstart, nh, hg0, ncand, fh); break;
-      case 2: rare = c2_cell<TI, 2>(a, wofs, lane, hstart, nh, hg0, ncand, fh); break;
-      case 3: rare = c2_cell<TI, 3>(a, wofs, lane, hstart, nh, hg0, ncand, fh); break;
-      case 4: rare = c2_cell<TI, 4>(a, wofs, lane, hstart, nh, hg0, ncand, fh); break;
-      case 5: rare = c2_cell<TI, 5>(a, wofs, lane, hstart, nh, hg0, ncand, fh); break;
-      case 6: rare = c2_cell<TI, 6>(a, wofs, lane, hstart, nh, hg0, ncand, fh); break;
-      case 7: rare = c2_cell<TI, 7>(a, wofs, lane, hstart, nh, hg0, ncand, fh); break;
-      default: rare = c2_cell<TI, 8>(a, wofs, lane, hstart, nh, hg0, ncand, fh); break;
+      case 1: rare = c2_cell<TI, 1, HALF>(a, wofs, lane, hstart, nh, hg0, ncand, fh, hbase, hsh); break;
+      case 2: rare = c2_cell<TI, 2, HALF>(a, wofs, lane, hstart, nh, hg0, ncand, fh, hbase, hsh); break;
+      case 3: rare = c2_cell<TI, 3, HALF>(a, wofs, lane, hstart, nh, hg0, ncand, fh, hbase, hsh); break;
+      case 4: rare = c2_cell<TI, 4, HALF>(a, wofs, lane, hstart, nh, hg0, ncand, fh, hbase, hsh); break;
+      case 5: rare = c2_cell<TI, 5, HALF>(a, wofs, lane, hstart, nh, hg0, ncand, fh, hbase, hsh); break;
+      case 6: rare = c2_cell<TI, 6, HALF>(a, wofs, lane, hstart, nh, hg0, ncand, fh, hbase, hsh); break;
+      case 7: rare = c2_cell<TI, 7, HALF>(a, wofs, lane, hstart, nh, hg0, ncand, fh, hbase, hsh); break;
+      default: rare = c2_cell<TI, 8, HALF>(a, wofs, lane, hstart, nh, hg0, ncand, fh, hbase, hsh); break;
     }
     if (rare) {
       if (lane == 0) rare_list[nrare] = (uint8_t)hc;

@@ -475,13 +475,15 @@ int traverse(const nl_params* p, int64_t N, const void* co, const PairWs& w, con
       NL_CUDA(cudaMemcpyAsync((void*)a.self, &a, sizeof(a), cudaMemcpyHostToDevice, st));
       bool launched = false;
       if constexpr (sizeof(T) == 8) {
-        // Float64 full lists: candidates register-resident, home-atom pairs in the outer loop (nl_count2.cuh);
+        // Float64 lists: candidates register-resident, home-atom pairs in the outer loop (nl_count2.cuh);
         // NL_COUNT=legacy keeps round 1's chunk-major kernel for A/B measurements
-        if (!sk.half && count_variant() == 1) {
-          static SmemOnce done2;
-          int rc = set_smem_once(k_count_mask2<TI>, cm_smem_bytes(CM_MASK), done2);
+        if (count_variant() == 1) {
+          static SmemOnce done2, done2h;
+          int rc = sk.half ? set_smem_once(k_count_mask2<TI, true>, cm_smem_bytes(CM_MASK), done2h)
+                           : set_smem_once(k_count_mask2<TI, false>, cm_smem_bytes(CM_MASK), done2);
           if (rc) return rc;
-          k_count_mask2<TI><<<nblk, TILE_NT, cm_smem_bytes(CM_MASK), st>>>(a);
+          if (sk.half) k_count_mask2<TI, true><<<nblk, TILE_NT, cm_smem_bytes(CM_MASK), st>>>(a);   // the half rule filters the hit words
+          else k_count_mask2<TI, false><<<nblk, TILE_NT, cm_smem_bytes(CM_MASK), st>>>(a);
           launched = true;
         }
       }
