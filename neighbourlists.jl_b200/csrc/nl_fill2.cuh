@@ -527,8 +527,14 @@ __global__ void __launch_bounds__(256) k_fix_boundaries(const TI* __restrict__ f
 // i stream: i[p] = (row of pair p) for p in [0, first[n_rows] - 1); rows through gmap in shard mode.  One block per
 // EXP_RB consecutive ROWS, whose pairs are one contiguous range of the output: first[] of those rows sits in shared memory,
 // 16-byte stores, 512 contiguous bytes per warp instruction.
-constexpr int EXP_NT = 256;
-constexpr int EXP_RB = 512;
+#ifndef NL_EXP_NT
+#define NL_EXP_NT 512   // A/B (experiments/README.md): 512 threads x 256 rows per block: fill stage -0.08 ms against 256 x 512
+#endif
+#ifndef NL_EXP_RB
+#define NL_EXP_RB 256
+#endif
+constexpr int EXP_NT = NL_EXP_NT;
+constexpr int EXP_RB = NL_EXP_RB;
 template <class TI>
 __global__ void __launch_bounds__(EXP_NT) k_expand_rows(const TI* __restrict__ first, long long n_rows, const TI* __restrict__ gmap, TI* __restrict__ io,
                                                         TI* __restrict__ Szero) {
