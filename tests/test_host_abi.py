@@ -224,3 +224,46 @@ def test_lj_force_restatement_is_minus_gradient():
         fd = -(energy(Xp)[0] - energy(Xm)[0]) / (2 * h)
         assert abs(fd - F[n, k]) <= 1e-6 * max(1.0, abs(F[n, k])), (n, k, fd, F[n, k])
     assert np.abs(F.sum(axis=0)).max() <= 1e-9 * np.abs(F).max() * N  # Newton's third law
+
+
+def test_round2_entry_points_validate_arguments():
+    """Shard peer path and host transfer: every argument check happens before the first CUDA / NCCL call."""
+    L = nl._lib.lib()
+    E = nl._lib
+    geo = nl.cellmath.geometry(np.eye(3) * 40.0, 5.0, (True, True, True), np.float64)
+    p = E.make_params(geo, np.float64, np.int32)
+    dummy = (C.c_char * 256)()
+    ptr = C.cast(dummy, C.c_void_p)
+    peers = E.NlShardPeers()
+    info = E.NlShardInfo()
+    # connect: null outputs, bad ranks, capacity < 1, workspace missing / too small
+    assert L.nl_shard_connect(p, 1000, None, 0, 2, ptr, 256, None, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_shard_connect(p, 1000, None, 2, 2, ptr, 256, C.byref(peers), None) == E.NL_ERR_BAD_ARG
+    assert L.nl_shard_connect(p, 0, None, 0, 2, ptr, 256, C.byref(peers), None) == E.NL_ERR_BAD_ARG
+    assert L.nl_shard_connect(p, 1000, None, 0, 2, None, 0, C.byref(peers), None) == E.NL_ERR_WORKSPACE
+    assert L.nl_shard_workspace_bytes(p, 1000, 2) > 1000 * 28 * 2          # send + halo buffers
+    assert L.nl_shard_workspace_bytes(p, 1000, 65) == 0                    # more ranks than NL_MAX_RANKS
+    # exchange_peer: peers must belong to the info and to this workspace, and the capacity must suffice
+    info.nranks, info.rank, info.n_local, info.n_max_all = 2, 0, 10, 5000
+    peers.nranks, peers.rank, peers.cap, peers.ws_bytes, peers.ws = 2, 0, 1000, 256, ptr.value
+    assert L.nl_shard_exchange_peer(p, C.byref(info), ptr, ptr, 10, None, None, ptr, ptr, None, ptr, 256, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_shard_exchange_peer(p, C.byref(info), ptr, ptr, 10, None, C.byref(peers), ptr, ptr, None, ptr, 256, None) == E.NL_ERR_WORKSPACE
+    info.n_max_all = 500
+    assert L.nl_shard_exchange_peer(p, C.byref(info), ptr, ptr, 10, None, C.byref(peers), ptr, ptr, None, ptr, 128, None) == E.NL_ERR_WORKSPACE
+    peers.rank = 1
+    assert L.nl_shard_exchange_peer(p, C.byref(info), ptr, ptr, 10, None, C.byref(peers), ptr, ptr, None, ptr, 256, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_shard_disconnect(None) == E.NL_ERR_BAD_ARG
+    fresh = E.NlShardPeers()
+    assert L.nl_shard_disconnect(C.byref(fresh)) == 0                       # nothing mapped: nothing to do
+    # host transfer
+    job = C.c_void_p()
+    assert L.nl_pairs_to_host_begin(p, None, 3, 5, ptr, ptr, 0, None, C.byref(job)) == E.NL_ERR_BAD_ARG        # first missing
+    assert L.nl_pairs_to_host_begin(p, ptr, 3, 5, ptr, None, 0, None, C.byref(job)) == E.NL_ERR_BAD_ARG         # i_host missing, P > 0
+    assert L.nl_pairs_to_host_begin(p, ptr, -1, 5, ptr, ptr, 0, None, C.byref(job)) == E.NL_ERR_BAD_ARG
+    assert L.nl_pairs_to_host_begin(p, ptr, 3, 5, ptr, ptr, 0, None, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_pairs_to_host_finish(None, ptr, ptr, ptr, ptr, ptr, ptr, 256, None) == E.NL_ERR_BAD_ARG
+    # whole-list call: i_copy_from out of range, row_index without a host buffer, scratch too small
+    assert L.nl_pairs_to_host(p, ptr, 3, None, 6, None, None, ptr, ptr, 5, ptr, ptr, ptr, ptr, ptr, ptr, 4096, 0, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_pairs_to_host(p, ptr, 3, None, 2, None, None, ptr, ptr, 5, ptr, ptr, ptr, ptr, ptr, ptr, 4096, 0, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_pairs_to_host(p, ptr, 3, None, 5, ptr, None, ptr, ptr, 5, ptr, ptr, ptr, ptr, ptr, ptr, 4096, 0, None) == E.NL_ERR_BAD_ARG
+    assert L.nl_pairs_to_host(p, ptr, 3, None, 5, None, None, ptr, ptr, 5, ptr, ptr, ptr, ptr, ptr, ptr, 16, 0, None) == E.NL_ERR_WORKSPACE
